@@ -1,0 +1,180 @@
+/*
+ * tsg.h -- C ABI of libtsg.so: the B200 (sm_100a) hot path of two-stage-gnn graph-classification
+ * training (batched message passing + pooling forward/backward).
+ *
+ * Every entry point replaces a reference-side operator; the citation on each declaration is the
+ * reference file:line (relative to the upstream repo root) whose arithmetic it implements.  The
+ * reference reaches these operators through PyTorch-Geometric 1.6.3 / ATen library calls; this
+ * library is what a maintainer would bind instead (ctypes stub in INTEGRATION.md).
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name ends in _host; caller allocates everything
+ *     (inputs, outputs, workspace); the library never allocates, never retains pointers past
+ *     return, never synchronises the stream, and is CUDA-graph-capture safe;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*);
+ *   - return value: 0 on success, negative TSG_E* on failure; tsg_last_error() gives the message
+ *     (thread local).  No exceptions cross the ABI.  There is no CPU fallback.
+ *   - features are fp32 row-major; node / edge indices arriving from the PyG surface are int64,
+ *     internal CSR indices are int32 (sum n + sum E must stay below 2^31).
+ *   - `*_dev` count pointers are optional device-side scalars: when non-NULL the kernels use
+ *     min(*ptr, capacity) as the element count, so data-dependent sizes (edges surviving
+ *     filter_adj) never need a host synchronisation.
+ */
+#ifndef TSG_H_
+#define TSG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TSG_ABI_VERSION 1
+
+enum {
+  TSG_OK = 0,
+  TSG_EINVAL = -1,     /* bad shape / null pointer / unsupported size            */
+  TSG_EWORKSPACE = -2, /* workspace too small                                    */
+  TSG_ELAUNCH = -3,    /* CUDA launch error (message carries cudaGetErrorString) */
+  TSG_EARCH = -4       /* device is not sm_100                                   */
+};
+
+int tsg_abi_version(void);
+const char* tsg_last_error(void);
+/* 0 if the current device can run this library (compute capability 10.x), else TSG_EARCH. */
+int tsg_check_device(void);
+
+/* ------------------------------------------------------------------------------------------
+ * K1  CSR construction + GCN normalisation
+ *   replaces: PyG GCNConv.norm / gcn_norm (add_remaining_self_loops, scatter_add degree,
+ *   deg^-1/2 A deg^-1/2) as called from Code/sag/network.py:34,38,42 and Code/sag/layers.py:18.
+ *   mode TSG_CSR_GCN : drop input self loops, append one loop per node LAST in its row, weight 1
+ *                      (or the last listed loop's weight when edge_weight is given), val = norm.
+ *   mode TSG_CSR_RAW : keep the edge list as is, val = edge_weight or 1 (the dense directories'
+ *                      0/1 adjacency, Code/sage+gat+diffpool/encoders.py:33).
+ *   Output is the stable counting sort of the (augmented) COO list: within a row entries keep COO
+ *   order.  The dst-major CSR (rows = targets, colidx = sources) drives the forward aggregation,
+ *   the src-major one (rows = sources, colidx = targets) the backward; pass NULL t_* to skip it.
+ *   eid = original edge position (< num_edges) or num_edges + node for an appended self loop.
+ *   Capacity of colidx/val/eid: num_edges + num_nodes (GCN) or num_edges (RAW).
+ * ------------------------------------------------------------------------------------------ */
+#define TSG_CSR_GCN 0
+#define TSG_CSR_RAW 1
+size_t tsg_csr_build_workspace_bytes(int64_t num_edges, int64_t num_nodes);
+int tsg_csr_build(const int64_t* row, const int64_t* col, const float* edge_weight /*nullable*/,
+                  int64_t num_edges, const int64_t* num_edges_dev /*nullable*/, int64_t num_nodes,
+                  int mode,
+                  int32_t* rowptr, int32_t* colidx, float* val, int32_t* eid /*nullable*/,
+                  int32_t* t_rowptr /*nullable*/, int32_t* t_colidx, float* t_val,
+                  int32_t* t_eid /*nullable*/,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K2  CSR segment-sum SpMM:  Y[r,:] = sum_p val[p] * H[colidx[p],:]  (+ bias) (ReLU optional)
+ *   replaces: the gather / mul / scatter_add of PyG GCNConv.propagate (Code/sag/network.py:34)
+ *   and `torch.matmul(adj, x)` of the dense GraphConv (Code/sage+gat+diffpool/encoders.py:33,
+ *   Code/eigengcn/encoders.py:31).  Per-row accumulation is sequential in CSR order with the
+ *   product rounded before the add, so it is bit-identical to index_add_ in COO order.
+ *   The backward (dH = A^T dY) is the same call on the src-major CSR.
+ *   flags: TSG_SPMM_RELU applies max(.,0) after the bias; relu_mask (nullable, uint8 [N,F]) is
+ *   not needed because ReLU's backward is recomputed from Y > 0.
+ * ------------------------------------------------------------------------------------------ */
+#define TSG_SPMM_RELU 1
+int tsg_spmm(const int32_t* rowptr, const int32_t* colidx, const float* val /*nullable => 1*/,
+             const float* H, const float* bias /*nullable*/, float* Y,
+             int64_t num_rows, int64_t feat, int flags, void* stream);
+
+/* dY_masked = dY * (Y > 0): ReLU backward fused with the column sum that gives the bias gradient:
+ * dbias[f] = sum_r dY_masked[r,f]  (deterministic two-stage reduction).  Y may be NULL (no ReLU).
+ * workspace: tsg_colsum_workspace_bytes(num_rows, feat). */
+size_t tsg_colsum_workspace_bytes(int64_t num_rows, int64_t feat);
+int tsg_relu_bwd_colsum(const float* dY, const float* Y /*nullable*/, float* dY_masked /*nullable*/,
+                        float* dbias, int64_t num_rows, int64_t feat,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K5a  per-graph top-k (deterministic: descending score, ties -> lower node id, NaN first)
+ *   replaces: PyG topk_pool.topk as called from Code/sag/layers.py:20.
+ *   graph_ptr[G+1] are node offsets of the (sorted) batch vector; k_g = ceil(ratio * n_g) in
+ *   fp32.  tsg_topk_sizes writes k_ptr[G+1] (exclusive scan of k_g); tsg_topk writes
+ *   perm[k_ptr[G]] (global node ids, graph-major, score-descending) as int64.
+ * ------------------------------------------------------------------------------------------ */
+size_t tsg_topk_workspace_bytes(int64_t num_nodes, int64_t num_graphs);
+int tsg_topk_sizes(const int64_t* graph_ptr, int64_t num_graphs, float ratio, int64_t* k_ptr,
+                   void* workspace, size_t workspace_bytes, void* stream);
+int tsg_topk(const float* score, const int64_t* graph_ptr, const int64_t* k_ptr,
+             int64_t num_graphs, int64_t num_nodes, int64_t* perm,
+             void* workspace, size_t workspace_bytes, void* stream);
+
+/* node offsets from a sorted batch vector: graph_ptr[g] = first i with batch[i] >= g. */
+int tsg_batch_to_ptr(const int64_t* batch, int64_t num_nodes, int64_t num_graphs,
+                     int64_t* graph_ptr, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K5b  filter_adj: relabel by perm, keep edges whose both ends survive, order preserving.
+ *   replaces: PyG topk_pool.filter_adj as called from Code/sag/layers.py:23.
+ *   inv_perm[num_nodes] (int32 out): position of node in perm or -1.  Survivors are written to
+ *   out_row/out_col (capacity num_edges); *out_num_edges_dev receives the count.
+ * ------------------------------------------------------------------------------------------ */
+size_t tsg_filter_adj_workspace_bytes(int64_t num_edges);
+int tsg_filter_adj(const int64_t* row, const int64_t* col, int64_t num_edges,
+                   const int64_t* num_edges_dev /*nullable*/,
+                   const int64_t* perm, int64_t num_perm, int64_t num_nodes,
+                   int32_t* inv_perm, int64_t* out_row, int64_t* out_col,
+                   int64_t* out_num_edges_dev,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* gated gather  xo[i,:] = x[perm[i],:] * tanh(score[perm[i]])   (Code/sag/layers.py:21)
+ * also emits batch_out[i] = batch[perm[i]] (layers.py:22) when batch != NULL. */
+int tsg_gate_gather_fwd(const float* x, const float* score, const int64_t* perm,
+                        const int64_t* batch /*nullable*/, float* xo, int64_t* batch_out,
+                        int64_t num_perm, int64_t feat, void* stream);
+/* dx[j,:] = inv_perm[j] >= 0 ? dxo[inv_perm[j],:] * tanh(score[j]) : 0
+ * dscore[j] = inv_perm[j] >= 0 ? sum_f(dxo[m,f] * x[j,f]) * (1 - tanh^2(score[j])) : 0 */
+int tsg_gate_gather_bwd(const float* dxo, const float* x, const float* score,
+                        const int32_t* inv_perm, float* dx, float* dscore,
+                        int64_t num_nodes, int64_t feat, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K6  per-graph readout: out[g, 0:F] = max_i x[i,:], out[g, F:2F] = mean_i x[i,:]
+ *   replaces: torch.cat([gmp(x,batch), gap(x,batch)],1) of Code/sag/network.py:36,40,44 and the
+ *   `torch.max(x, dim=1)` readouts of the dense directories (encoders.py:183,190,197).
+ *   argmax[g,f] (int32) = global row of the FIRST maximum (-1 for an empty graph => output 0).
+ *   mode bit0: emit max, bit1: emit mean, bit2: emit sum instead of mean.
+ * ------------------------------------------------------------------------------------------ */
+#define TSG_READOUT_MAX 1
+#define TSG_READOUT_MEAN 2
+#define TSG_READOUT_SUM 4
+int tsg_readout_fwd(const float* x, const int64_t* graph_ptr, int64_t num_graphs, int64_t feat,
+                    int mode, float* out, int64_t out_stride, int32_t* argmax, void* stream);
+/* dx[i,f] = (argmax[g,f]==i) * dout[g,f] + dout[g,F+f]/n_g ; g found from graph_ptr. */
+int tsg_readout_bwd(const float* dout, int64_t dout_stride, const int32_t* argmax,
+                    const int64_t* graph_ptr, int64_t num_graphs, int64_t num_nodes, int64_t feat,
+                    int mode, float* dx, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K9  triplet distances + margin ranking loss
+ *   replaces: F.pairwise_distance x2 (Code/sag/tripletnet.py:21-22) + MarginRankingLoss with
+ *   target -1 (Code/sag/train_triplet.py:196,208-211):
+ *   d(a,b) = || e_a - e_b + 1e-6 ||_2 ; loss = mean_t max(0, d_ap - d_an + margin).
+ *   triplets[T,3] int64 index rows of emb[M,D].  bwd is deterministic: per embedding row the
+ *   contributions are summed in triplet order via an inverted index built on the device.
+ *   tsg_pairdist_matrix writes the full [M,M] matrix (hard-negative mining / kNN evaluation).
+ * ------------------------------------------------------------------------------------------ */
+size_t tsg_triplet_workspace_bytes(int64_t num_triplets, int64_t num_rows, int64_t dim);
+int tsg_triplet_fwd(const float* emb, const int64_t* triplets, int64_t num_triplets,
+                    int64_t num_rows, int64_t dim, float margin, float eps,
+                    float* dist_pos, float* dist_neg, float* loss,
+                    void* workspace, size_t workspace_bytes, void* stream);
+int tsg_triplet_bwd(const float* emb, const int64_t* triplets, int64_t num_triplets,
+                    int64_t num_rows, int64_t dim, float margin, float eps,
+                    const float* dist_pos, const float* dist_neg, const float* dloss,
+                    float* demb, void* workspace, size_t workspace_bytes, void* stream);
+int tsg_pairdist_matrix(const float* emb, int64_t num_rows, int64_t dim, float eps,
+                        float* dist, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TSG_H_ */

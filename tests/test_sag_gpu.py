@@ -1,0 +1,314 @@
+"""Parity tests proper for the SAGPool path (BASELINE config 2): CUDA kernels through the C ABI
+versus the CPU oracle on identical seeded inputs.  Integer outputs bit-exact (torch.equal); fp32
+tensors within 1e-5 relative (L_inf over L_inf), the tolerance north_star states."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+from oracle import pyg_ref as R
+from tsg import synth
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def _batch(shape, G, seed=11):
+    c = synth.make_corpus(shape, G, seed=seed)
+    b = synth.pack(c)
+    return (torch.from_numpy(b["x"]), torch.from_numpy(b["edge_index"]), torch.from_numpy(b["batch"]),
+            b["node_ptr"])
+
+
+# ------------------------------------------------------------------ K1
+@pytest.mark.parametrize("shape,G", [("PROTEINS", 7), ("DD", 3), ("JANY", 2)])
+def test_csr_bit_exact(cuda, shape, G):
+    from tsg import ops
+    x, ei, batch, _ = _batch(shape, G)
+    n = x.size(0)
+    ei = torch.cat([ei, torch.tensor([[0, 3, 3], [0, 3, 3]])], dim=1)     # pre-existing self loops
+    csr = ops.build_csr(ops.EdgeList.from_edge_index(ei.to(cuda)), n, want_eid=True)
+    ei2, norm = R.gcn_norm(ei, None, n)
+    keep = (ei[0] != ei[1]).nonzero().flatten()
+    E = ei.size(1)
+    orig = torch.cat([keep, E + torch.arange(n)]).to(torch.int32)         # augmented position -> eid
+    for by, (rp, ci, v, eid) in (("dst", (csr.rowptr, csr.colidx, csr.val, csr.eid)),
+                                 ("src", (csr.t_rowptr, csr.t_colidx, csr.t_val, csr.t_eid))):
+        o_rp, o_ci, o_v, o_ord = R.csr_from_coo(ei2, norm, n, by)
+        nnz = int(o_rp[-1])
+        assert torch.equal(rp.cpu(), o_rp)
+        assert torch.equal(ci.cpu()[:nnz], o_ci)
+        assert torch.equal(eid.cpu()[:nnz], orig[o_ord.long()])
+        assert torch.equal(v.cpu()[:nnz].view(torch.int32), o_v.view(torch.int32)), "norm not bit-exact"
+
+
+def test_csr_raw_mode_and_device_count(cuda):
+    from tsg import ops
+    x, ei, batch, _ = _batch("PROTEINS", 5)
+    n, E = x.size(0), ei.size(1)
+    # capacity buffer twice as long as the valid prefix; only the device count says where it ends
+    pad = torch.cat([ei, torch.zeros(2, E, dtype=torch.int64)], dim=1).to(cuda)
+    el = ops.EdgeList(pad[0], pad[1], 2 * E, torch.tensor([E], device=cuda))
+    csr = ops.build_csr(el, n, mode=ops.CSR_RAW)
+    o = R.csr_from_coo(ei, torch.ones(E), n, "dst")
+    assert torch.equal(csr.rowptr.cpu(), o[0]) and torch.equal(csr.colidx.cpu()[:E], o[1])
+    assert torch.equal(csr.val.cpu()[:E], o[2])
+
+
+def test_csr_edge_weight(cuda):
+    from tsg import ops
+    x, ei, batch, _ = _batch("PROTEINS", 4)
+    n = x.size(0)
+    ei = torch.cat([ei, torch.tensor([[2, 2], [2, 2]])], dim=1)
+    w = torch.rand(ei.size(1), generator=torch.Generator().manual_seed(5)) + 0.5
+    csr = ops.build_csr(ops.EdgeList.from_edge_index(ei.to(cuda)), n, edge_weight=w.to(cuda))
+    ei2, norm = R.gcn_norm(ei, w, n)
+    o = R.csr_from_coo(ei2, norm, n, "dst")
+    nnz = int(o[0][-1])
+    assert torch.equal(csr.colidx.cpu()[:nnz], o[1])
+    assert torch.equal(csr.val.cpu()[:nnz].view(torch.int32), o[2].view(torch.int32))
+
+
+# ------------------------------------------------------------------ K2
+@pytest.mark.parametrize("F", [1, 7, 32, 89, 128, 160])
+def test_spmm_bit_exact(cuda, F):
+    from tsg import ops
+    x, ei, batch, _ = _batch("DD", 4)
+    n = x.size(0)
+    g = torch.Generator().manual_seed(F)
+    h = torch.randn(n, F, generator=g)
+    bias = torch.randn(F, generator=g)
+    csr = ops.build_csr(ops.EdgeList.from_edge_index(ei.to(cuda)), n)
+    ei2, norm = R.gcn_norm(ei, None, n)
+    ref = R.spmm_coo_edge_order(ei2, norm, h, n)
+    y = ops.spmm_raw(csr.rowptr, csr.colidx, csr.val, h.to(cuda))
+    assert torch.equal(y.cpu(), ref), "SpMM must reproduce index_add_ order bit for bit"
+    y2 = ops.spmm_raw(csr.rowptr, csr.colidx, csr.val, h.to(cuda), bias.to(cuda), relu=True)
+    assert torch.equal(y2.cpu(), torch.relu(ref + bias))
+    # transposed operator == A^T
+    yt = ops.spmm_raw(csr.t_rowptr, csr.t_colidx, csr.t_val, h.to(cuda))
+    ref_t = torch.zeros(n, F).index_add_(0, ei2[0], norm.view(-1, 1) * h[ei2[1]])
+    assert torch.equal(yt.cpu(), ref_t)
+
+
+@pytest.mark.parametrize("fin,fout", [(89, 32), (32, 1), (32, 128)])
+def test_gcn_conv_fwd_bwd(cuda, fin, fout):
+    from tsg import ops
+    x, ei, batch, _ = _batch("DD", 3)
+    n = x.size(0)
+    g = torch.Generator().manual_seed(7)
+    xin = torch.randn(n, fin, generator=g)
+    w = (torch.rand(fin, fout, generator=g) - 0.5)
+    b = torch.randn(fout, generator=g) * 0.1
+    dy = torch.randn(n, fout, generator=g)
+    ro = [t.clone().requires_grad_(True) for t in (xin, w, b)]
+    out_o = torch.relu(R.gcn_conv(ro[0], ei, ro[1], ro[2]))
+    out_o.backward(dy)
+    rg = [t.clone().to(cuda).requires_grad_(True) for t in (xin, w, b)]
+    csr = ops.build_csr(ops.EdgeList.from_edge_index(ei.to(cuda)), n)
+    out_g = ops.gcn_conv(rg[0], csr, rg[1], rg[2], relu=True)
+    out_g.backward(dy.to(cuda))
+    assert rel_err(out_g, out_o) <= TOL
+    for a, o in zip(rg, ro):
+        assert rel_err(a.grad, o.grad) <= TOL
+
+
+# ------------------------------------------------------------------ K5a
+@pytest.mark.parametrize("ratio", [0.5, 0.8, 0.25, 1.0])
+@pytest.mark.parametrize("shape,G", [("PROTEINS", 40), ("DD", 6)])
+def test_topk_bit_exact(cuda, ratio, shape, G):
+    from tsg import ops
+    x, ei, batch, ptr = _batch(shape, G)
+    n = x.size(0)
+    g = torch.Generator().manual_seed(13)
+    score = torch.randn(n, generator=g)
+    score[::5] = score[0]; score[1::11] = 0.25            # heavy ties
+    score[2] = float("nan"); score[7] = float("nan")
+    score[4] = -0.0; score[9] = 0.0; score[10] = float("inf"); score[12] = float("-inf")
+    ref = R.topk(score, ratio, batch)
+    gptr = ops.batch_to_ptr(batch.to(cuda), G)
+    assert torch.equal(gptr.cpu(), torch.from_numpy(ptr))
+    kptr = ops.topk_sizes(gptr, ratio)
+    K = int(kptr[-1])
+    assert K == ref.numel()
+    perm = ops.topk(score.to(cuda), gptr, kptr, K)
+    assert torch.equal(perm.cpu(), ref)
+
+
+def test_topk_single_node_graphs_and_big_graph(cuda):
+    from tsg import ops
+    sizes = [1, 1, 2, 9000, 1, 3]        # 9000 > the shared-memory key budget -> global path
+    batch = torch.repeat_interleave(torch.arange(len(sizes)), torch.tensor(sizes))
+    score = torch.randn(batch.numel(), generator=torch.Generator().manual_seed(3))
+    score[100:4000:3] = 0.5
+    ref = R.topk(score, 0.5, batch)
+    gptr = ops.batch_to_ptr(batch.to(cuda), len(sizes))
+    kptr = ops.topk_sizes(gptr, 0.5)
+    perm = ops.topk(score.to(cuda), gptr, kptr, int(kptr[-1]))
+    assert torch.equal(perm.cpu(), ref)
+
+
+# ------------------------------------------------------------------ K5b
+@pytest.mark.parametrize("shape,G,ratio", [("PROTEINS", 30, 0.5), ("DD", 5, 0.5), ("DD", 4, 0.1)])
+def test_filter_adj_bit_exact(cuda, shape, G, ratio):
+    from tsg import ops
+    x, ei, batch, _ = _batch(shape, G)
+    n = x.size(0)
+    score = torch.randn(n, generator=torch.Generator().manual_seed(17))
+    perm = R.topk(score, ratio, batch)
+    ref, _ = R.filter_adj(ei, None, perm, n)
+    el, inv = ops.filter_adj(ops.EdgeList.from_edge_index(ei.to(cuda)), perm.to(cuda), n)
+    assert int(el.count) == ref.size(1)
+    assert torch.equal(el.edge_index().cpu(), ref)
+    m = torch.full((n,), -1, dtype=torch.int32); m[perm] = torch.arange(perm.numel(), dtype=torch.int32)
+    assert torch.equal(inv.cpu(), m)
+
+
+def test_filter_adj_empty_result(cuda):
+    from tsg import ops
+    ei = torch.tensor([[0, 1, 2, 3], [1, 0, 3, 2]])
+    perm = torch.tensor([0, 2])
+    el, inv = ops.filter_adj(ops.EdgeList.from_edge_index(ei.to(cuda)), perm.to(cuda), 4)
+    assert int(el.count) == 0 and el.edge_index().shape == (2, 0)
+    # and the next level's CSR of an empty edge set is just the self loops
+    csr = ops.build_csr(el, 2)
+    assert csr.rowptr.cpu().tolist() == [0, 1, 2] and csr.val.cpu()[:2].tolist() == [1.0, 1.0]
+
+
+# ------------------------------------------------------------------ gate
+@pytest.mark.parametrize("F", [32, 128, 5])
+def test_gate_gather_fwd_bwd(cuda, F):
+    from tsg import ops
+    x, ei, batch, _ = _batch("DD", 3)
+    n = x.size(0)
+    g = torch.Generator().manual_seed(19)
+    h = torch.randn(n, F, generator=g); s = torch.randn(n, generator=g)
+    perm = R.topk(s, 0.5, batch)
+    dxo = torch.randn(perm.numel(), F, generator=g)
+    ho, so = h.clone().requires_grad_(True), s.clone().requires_grad_(True)
+    (ho[perm] * torch.tanh(so[perm]).view(-1, 1)).backward(dxo)
+    inv = torch.full((n,), -1, dtype=torch.int32); inv[perm] = torch.arange(perm.numel(), dtype=torch.int32)
+    hg, sg = h.to(cuda).requires_grad_(True), s.to(cuda).requires_grad_(True)
+    xo = ops.gate_gather(hg, sg, perm.to(cuda), inv.to(cuda))
+    xo.backward(dxo.to(cuda))
+    assert rel_err(xo, h[perm] * torch.tanh(s[perm]).view(-1, 1)) <= TOL
+    assert rel_err(hg.grad, ho.grad) <= TOL and rel_err(sg.grad, so.grad) <= TOL
+
+
+# ------------------------------------------------------------------ K6
+@pytest.mark.parametrize("F", [32, 128, 6, 256])
+def test_readout_fwd_bwd(cuda, F):
+    from tsg import ops
+    x, ei, batch, ptr = _batch("PROTEINS", 12)
+    n, G = x.size(0), 12
+    g = torch.Generator().manual_seed(23)
+    h = torch.randn(n, F, generator=g)
+    h[1] = h[0]                               # a tie on every column: gradient must go to row 0
+    dout = torch.randn(G, 2 * F, generator=g)
+    ho = h.clone().requires_grad_(True)
+    ref = torch.cat([R.global_max_pool(ho, batch, G), R.global_mean_pool(ho, batch, G)], 1)
+    ref.backward(dout)
+    hg = h.to(cuda).requires_grad_(True)
+    out = ops.readout(hg, torch.from_numpy(ptr).to(cuda))
+    out.backward(dout.to(cuda))
+    assert torch.equal(out[:, :F].cpu(), ref[:, :F].detach())           # max is exact
+    assert rel_err(out[:, F:], ref[:, F:]) <= TOL
+    assert rel_err(hg.grad, ho.grad) <= TOL
+
+
+# ------------------------------------------------------------------ K9
+def test_triplet_fwd_bwd(cuda):
+    from tsg import ops
+    g = torch.Generator().manual_seed(29)
+    M, D, T = 40, 32, 64
+    emb = torch.randn(M, D, generator=g)
+    trip = torch.randint(0, M, (T, 3), generator=g)
+    trip[5] = torch.tensor([3, 3, 3])           # degenerate: identical rows (d = eps * sqrt(D))
+    eo = emb.clone().requires_grad_(True)
+    lo, dpo, dno = R.triplet_margin_loss(eo[trip[:, 0]], eo[trip[:, 1]], eo[trip[:, 2]], 1.5)
+    lo.backward()
+    eg = emb.to(cuda).requires_grad_(True)
+    lg, dp, dn = ops.triplet_loss(eg, trip.to(cuda), 1.5)
+    lg.backward()
+    assert rel_err(dp, dpo) <= TOL and rel_err(dn, dno) <= TOL and rel_err(lg, lo) <= TOL
+    assert rel_err(eg.grad, eo.grad) <= TOL
+    dm = ops.pairdist_matrix(emb.to(cuda))
+    ref = torch.sqrt(((emb[:, None, :] - emb[None, :, :] + 1e-6) ** 2).sum(-1))
+    assert rel_err(dm, ref) <= TOL
+
+
+# ------------------------------------------------------------------ end to end
+@pytest.mark.parametrize("shape,G,nhid", [("PROTEINS", 24, 32), ("DD", 8, 32), ("DD", 6, 128)])
+def test_packed_sag_net_matches_oracle(cuda, shape, G, nhid):
+    """Whole Net forward + backward on a packed batch vs the oracle: same perms / filtered edges at
+    every level (bit-exact), embeddings, loss and every parameter gradient within 1e-5."""
+    from tsg import nn as tnn
+    x, ei, batch, ptr = _batch(shape, G, seed=777)
+    C = 16
+    params = R.init_sag_params(x.size(1), nhid, C, seed=777)
+    po = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    trip = torch.from_numpy(synth.sample_triplets(np.arange(G) % 2, G, seed=1))
+    emb_o, aux_o = R.sag_net_forward(po, x, ei, batch, 0.5, return_aux=True)
+    loss_o, _, _ = R.triplet_margin_loss(emb_o[trip[:, 0]], emb_o[trip[:, 1]], emb_o[trip[:, 2]], 1.5)
+    loss_o.backward()
+
+    net = tnn.PackedSAGNet(x.size(1), nhid, C, 0.5, 0.5).to(cuda)
+    net.load_state_dict({k: v for k, v in params.items()})
+    net.eval()                                   # dropout off (oracle runs without a mask)
+    emb_g, aux_g = net(x.to(cuda), ei.to(cuda), ptr, return_aux=True)
+    loss_g, _, _ = __import__("tsg.ops", fromlist=["x"]).triplet_loss(emb_g, trip.to(cuda), 1.5)
+    loss_g.backward()
+    for lvl in range(3):
+        assert torch.equal(aux_g["perm"][lvl].cpu(), aux_o["perm"][lvl]), f"perm differs at level {lvl}"
+        assert torch.equal(aux_g["edges"][lvl].edge_index().cpu(), aux_o["edge_index"][lvl])
+        assert rel_err(aux_g["score"][lvl], aux_o["score"][lvl]) <= TOL
+    assert rel_err(emb_g, emb_o) <= TOL
+    assert rel_err(loss_g, loss_o) <= TOL
+    for k, p in net.named_parameters():
+        assert rel_err(p.grad, po[k].grad) <= 2e-5, k
+
+
+def test_full_size_properties(cuda):
+    """BASELINE-size batch (1,168 DD-shape graphs): size-independent properties."""
+    from tsg import ops
+    c = synth.make_corpus("DD", 1168, seed=777)
+    b = synth.pack(c, one_hot=False)
+    ei = torch.from_numpy(b["edge_index"]).to(cuda)
+    ptr = torch.from_numpy(b["node_ptr"]).to(cuda)
+    n = int(b["node_ptr"][-1])
+    csr = ops.build_csr(ops.EdgeList.from_edge_index(ei), n, want_eid=True)
+    rp = csr.rowptr.long()
+    assert int(rp[-1]) == ei.size(1) + n
+    deg = (rp[1:] - rp[:-1])
+    assert int(deg.min()) >= 2                                     # connected + self loop
+    # rows keep COO order: eids strictly increase inside every row
+    eid = csr.eid.long()
+    rowid = torch.repeat_interleave(torch.arange(n, device=cuda), deg)
+    same = rowid[1:] == rowid[:-1]
+    assert bool(((eid[1:] > eid[:-1]) | ~same).all())
+    # A_hat is symmetric with unit spectral bound: A_hat 1-weighted rows: sum_j norm_ij*sqrt(d_j) = sqrt(d_i)
+    sq = deg.float().sqrt().view(-1, 1)
+    y = ops.spmm_raw(csr.rowptr, csr.colidx, csr.val, sq.contiguous())
+    assert rel_err(y, sq) <= 1e-5
+    yt = ops.spmm_raw(csr.t_rowptr, csr.t_colidx, csr.t_val, sq.contiguous())
+    assert torch.equal(y, yt)                                       # symmetric graph: same rows, same order
+    # top-k: scores of the kept nodes are sorted descending per graph, and nothing better was dropped
+    score = torch.randn(n, device=cuda, generator=torch.Generator(device=cuda).manual_seed(1))
+    kptr = ops.topk_sizes(ptr, 0.5)
+    perm = ops.topk(score, ptr, kptr, int(kptr[-1]))
+    ks = (kptr[1:] - kptr[:-1])
+    gid = torch.repeat_interleave(torch.arange(1168, device=cuda), ks)
+    s = score[perm]
+    same = gid[1:] == gid[:-1]
+    assert bool(((s[1:] <= s[:-1]) | ~same).all())
+    kept = torch.zeros(n, dtype=torch.bool, device=cuda); kept[perm] = True
+    assert int(kept.sum()) == perm.numel()                          # a permutation prefix: no duplicates
+    node_g = torch.repeat_interleave(torch.arange(1168, device=cuda), ptr[1:] - ptr[:-1])
+    min_kept = torch.full((1168,), float("inf"), device=cuda).scatter_reduce(0, gid, s, "amin")
+    assert bool((score[~kept] <= min_kept[node_g[~kept]]).all())
+    # filter_adj: survivors == both ends kept, count matches, relabelling is a bijection
+    el, inv = ops.filter_adj(ops.EdgeList.from_edge_index(ei), perm, n)
+    both = kept[ei[0]] & kept[ei[1]]
+    assert int(el.count) == int(both.sum())
+    out = el.edge_index()
+    assert torch.equal(perm[out[0]], ei[0][both]) and torch.equal(perm[out[1]], ei[1][both])

@@ -1,0 +1,232 @@
+// K2 -- CSR segment-sum SpMM   Y[r,:] = sum_p val[p] * H[colidx[p],:] (+bias) (ReLU)
+//
+// Replaces the gather -> mul -> scatter_add of PyG GCNConv.propagate (Code/sag/network.py:34,
+// 38,42; Code/sag/layers.py:18) and torch.matmul(adj, x) of the dense GraphConv
+// (Code/sage+gat+diffpool/encoders.py:33; Code/eigengcn/encoders.py:31) on a block-diagonal CSR.
+//
+// HBM-bound gather kernel, no tensor cores (AI ~ 0.5 flop/B).  Design:
+//   * a group of LPR lanes owns one destination row; each lane carries 4 consecutive features in
+//     a float4 (128-bit loads/stores); LPR = F/4 rounded up to a power of two (8 lanes at F=32, 32
+//     lanes at F=128) so one warp covers 32/LPR rows and every gathered row is one or more
+//     fully-used 128-byte lines;
+//   * the per-row loop is sequential in CSR order with the product rounded before the add
+//     (__fmul_rn / __fadd_rn, no FMA contraction): bit-identical to index_add_ in COO order and
+//     independent of the launch geometry; loads are issued 4 neighbours ahead for MLP;
+//   * neighbours of a row live in the same small graph block, so the gathers hit L1/L2 and DRAM
+//     sees ~compulsory traffic (H once, Y once, CSR once);
+//   * rows with more than HUB_DEG entries are split across the 32 lanes of a warp (warp per
+//     segment) in a second pass and combined in a fixed order.
+#include "common.cuh"
+
+namespace tsg {
+
+constexpr int SPMM_THREADS = 256;
+
+template <int LPR, bool HAS_VAL>
+__global__ void __launch_bounds__(SPMM_THREADS)
+k_spmm_vec4(const int* __restrict__ rowptr, const int* __restrict__ colidx,
+            const float* __restrict__ val, const float4* __restrict__ H,
+            const float4* __restrict__ bias, float4* __restrict__ Y,
+            int num_rows, int F4, int relu) {
+  const int lane_in_row = threadIdx.x % LPR;
+  const int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
+  const int64_t num_groups = ((int64_t)gridDim.x * blockDim.x) / LPR;
+  for (int64_t r = group; r < num_rows; r += num_groups) {
+    const int s = __ldg(rowptr + r), t = __ldg(rowptr + r + 1);
+    for (int f = lane_in_row; f < F4; f += LPR) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      int p = s;
+      for (; p + 4 <= t; p += 4) {
+        int c0 = __ldg(colidx + p), c1 = __ldg(colidx + p + 1);
+        int c2 = __ldg(colidx + p + 2), c3 = __ldg(colidx + p + 3);
+        float v0 = 1.f, v1 = 1.f, v2 = 1.f, v3 = 1.f;
+        if (HAS_VAL) { v0 = __ldg(val + p); v1 = __ldg(val + p + 1); v2 = __ldg(val + p + 2); v3 = __ldg(val + p + 3); }
+        float4 h0 = __ldg(H + (int64_t)c0 * F4 + f);
+        float4 h1 = __ldg(H + (int64_t)c1 * F4 + f);
+        float4 h2 = __ldg(H + (int64_t)c2 * F4 + f);
+        float4 h3 = __ldg(H + (int64_t)c3 * F4 + f);
+#define TSG_ACC(h, v)                                   \
+        acc.x = __fadd_rn(acc.x, __fmul_rn(v, h.x));    \
+        acc.y = __fadd_rn(acc.y, __fmul_rn(v, h.y));    \
+        acc.z = __fadd_rn(acc.z, __fmul_rn(v, h.z));    \
+        acc.w = __fadd_rn(acc.w, __fmul_rn(v, h.w));
+        TSG_ACC(h0, v0) TSG_ACC(h1, v1) TSG_ACC(h2, v2) TSG_ACC(h3, v3)
+      }
+      for (; p < t; ++p) {
+        int c0 = __ldg(colidx + p);
+        float v0 = HAS_VAL ? __ldg(val + p) : 1.f;
+        float4 h0 = __ldg(H + (int64_t)c0 * F4 + f);
+        TSG_ACC(h0, v0)
+      }
+#undef TSG_ACC
+      if (bias != nullptr) {
+        float4 b = __ldg(bias + f);
+        acc.x = __fadd_rn(acc.x, b.x); acc.y = __fadd_rn(acc.y, b.y);
+        acc.z = __fadd_rn(acc.z, b.z); acc.w = __fadd_rn(acc.w, b.w);
+      }
+      if (relu) {
+        acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f);
+        acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f);
+      }
+      Y[(int64_t)r * F4 + f] = acc;
+    }
+  }
+}
+
+// scalar-feature variant (F not a multiple of 4, or F == 1 where LPR == 1 => thread per row)
+template <int LPR, bool HAS_VAL>
+__global__ void __launch_bounds__(SPMM_THREADS)
+k_spmm_scalar(const int* __restrict__ rowptr, const int* __restrict__ colidx,
+              const float* __restrict__ val, const float* __restrict__ H,
+              const float* __restrict__ bias, float* __restrict__ Y,
+              int num_rows, int F, int relu) {
+  const int lane_in_row = threadIdx.x % LPR;
+  const int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
+  const int64_t num_groups = ((int64_t)gridDim.x * blockDim.x) / LPR;
+  for (int64_t r = group; r < num_rows; r += num_groups) {
+    const int s = __ldg(rowptr + r), t = __ldg(rowptr + r + 1);
+    for (int f = lane_in_row; f < F; f += LPR) {
+      float acc = 0.f;
+      int p = s;
+      for (; p + 4 <= t; p += 4) {
+        int c0 = __ldg(colidx + p), c1 = __ldg(colidx + p + 1);
+        int c2 = __ldg(colidx + p + 2), c3 = __ldg(colidx + p + 3);
+        float v0 = 1.f, v1 = 1.f, v2 = 1.f, v3 = 1.f;
+        if (HAS_VAL) { v0 = __ldg(val + p); v1 = __ldg(val + p + 1); v2 = __ldg(val + p + 2); v3 = __ldg(val + p + 3); }
+        float h0 = __ldg(H + (int64_t)c0 * F + f), h1 = __ldg(H + (int64_t)c1 * F + f);
+        float h2 = __ldg(H + (int64_t)c2 * F + f), h3 = __ldg(H + (int64_t)c3 * F + f);
+        acc = __fadd_rn(acc, __fmul_rn(v0, h0));
+        acc = __fadd_rn(acc, __fmul_rn(v1, h1));
+        acc = __fadd_rn(acc, __fmul_rn(v2, h2));
+        acc = __fadd_rn(acc, __fmul_rn(v3, h3));
+      }
+      for (; p < t; ++p) {
+        float v0 = HAS_VAL ? __ldg(val + p) : 1.f;
+        acc = __fadd_rn(acc, __fmul_rn(v0, __ldg(H + (int64_t)__ldg(colidx + p) * F + f)));
+      }
+      if (bias != nullptr) acc = __fadd_rn(acc, __ldg(bias + f));
+      if (relu) acc = fmaxf(acc, 0.f);
+      Y[(int64_t)r * F + f] = acc;
+    }
+  }
+}
+
+template <bool HAS_VAL>
+static int launch_spmm(const int* rowptr, const int* colidx, const float* val, const float* H,
+                       const float* bias, float* Y, int64_t N, int64_t F, int relu, cudaStream_t st) {
+  bool vec = (F % 4 == 0) && (((uintptr_t)H & 15) == 0) && (((uintptr_t)Y & 15) == 0) &&
+             (bias == nullptr || ((uintptr_t)bias & 15) == 0);
+  if (vec) {
+    int F4 = (int)(F / 4);
+    int lpr = 1; while (lpr < F4 && lpr < 32) lpr <<= 1;
+    int rows_per_block = SPMM_THREADS / lpr;
+    int grid = grid_for(N, rows_per_block, 32);
+#define TSG_GO(L) k_spmm_vec4<L, HAS_VAL><<<grid, SPMM_THREADS, 0, st>>>(rowptr, colidx, val, (const float4*)H, (const float4*)bias, (float4*)Y, (int)N, F4, relu)
+    switch (lpr) {
+      case 1: TSG_GO(1); break; case 2: TSG_GO(2); break; case 4: TSG_GO(4); break;
+      case 8: TSG_GO(8); break; case 16: TSG_GO(16); break; default: TSG_GO(32); break;
+    }
+#undef TSG_GO
+  } else {
+    int lpr = 1; while (lpr < F && lpr < 32) lpr <<= 1;
+    int rows_per_block = SPMM_THREADS / lpr;
+    int grid = grid_for(N, rows_per_block, 32);
+#define TSG_GO(L) k_spmm_scalar<L, HAS_VAL><<<grid, SPMM_THREADS, 0, st>>>(rowptr, colidx, val, H, bias, Y, (int)N, (int)F, relu)
+    switch (lpr) {
+      case 1: TSG_GO(1); break; case 2: TSG_GO(2); break; case 4: TSG_GO(4); break;
+      case 8: TSG_GO(8); break; case 16: TSG_GO(16); break; default: TSG_GO(32); break;
+    }
+#undef TSG_GO
+  }
+  return check_launch("spmm");
+}
+
+// ------------------------------------------------------------------------------------------
+// ReLU backward + bias gradient (column sum), deterministic two-stage reduction.
+//   stage 1: block b sums rows [b*RPB, (b+1)*RPB) per feature column into part[b, F]
+//   stage 2: one block sums part[:, f] sequentially in block order.
+// ------------------------------------------------------------------------------------------
+constexpr int CS_THREADS = 256;
+constexpr int CS_MAX_BLOCKS = TSG_NUM_SMS * 8;
+
+__global__ void __launch_bounds__(CS_THREADS)
+k_relu_bwd_colsum(const float* __restrict__ dY, const float* __restrict__ Y, float* __restrict__ dYm,
+                  float* __restrict__ part, int64_t N, int F, int64_t rows_per_block) {
+  // thread layout: column f = threadIdx.x % Fp, row lane = threadIdx.x / Fp  (Fp = cols per pass)
+  extern __shared__ float sm[];
+  int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  int64_t r1 = r0 + rows_per_block; if (r1 > N) r1 = N;
+  int cols = F < CS_THREADS ? F : CS_THREADS;
+  int rl = CS_THREADS / cols;             // row lanes
+  for (int fb = 0; fb < F; fb += cols) {
+    int f = fb + threadIdx.x % cols;
+    int lane_r = threadIdx.x / cols;
+    float acc = 0.f;
+    if (lane_r < rl && f < F) {
+      for (int64_t r = r0 + lane_r; r < r1; r += rl) {
+        float g = dY[r * F + f];
+        if (Y != nullptr && !(Y[r * F + f] > 0.f)) g = 0.f;
+        if (dYm != nullptr) dYm[r * F + f] = g;
+        acc += g;
+      }
+    }
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.x < cols && fb + threadIdx.x < F) {
+      float s = 0.f;
+      for (int k = 0; k < rl; ++k) s += sm[k * cols + threadIdx.x];
+      part[(int64_t)blockIdx.x * F + fb + threadIdx.x] = s;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void k_colsum_final(const float* __restrict__ part, float* __restrict__ out, int nb, int F) {
+  int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= F) return;
+  float s = 0.f;
+  for (int b = 0; b < nb; ++b) s += part[(int64_t)b * F + f];
+  out[f] = s;
+}
+
+}  // namespace tsg
+
+using namespace tsg;
+
+extern "C" int tsg_spmm(const int32_t* rowptr, const int32_t* colidx, const float* val,
+                        const float* H, const float* bias, float* Y,
+                        int64_t num_rows, int64_t feat, int flags, void* stream) {
+  TSG_REQUIRE(num_rows >= 0 && feat > 0, "spmm: bad shape rows=%lld feat=%lld", (long long)num_rows, (long long)feat);
+  TSG_REQUIRE(num_rows < (int64_t)0x7fffffff, "spmm: too many rows");
+  if (num_rows == 0) return TSG_OK;
+  TSG_REQUIRE(rowptr && colidx && H && Y, "spmm: null pointer");
+  int relu = (flags & TSG_SPMM_RELU) ? 1 : 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  return val ? launch_spmm<true>(rowptr, colidx, val, H, bias, Y, num_rows, feat, relu, st)
+             : launch_spmm<false>(rowptr, colidx, val, H, bias, Y, num_rows, feat, relu, st);
+}
+
+static int colsum_blocks(int64_t N) {
+  int64_t nb = (N + 255) / 256;
+  if (nb > CS_MAX_BLOCKS) nb = CS_MAX_BLOCKS;
+  if (nb < 1) nb = 1;
+  return (int)nb;
+}
+
+extern "C" size_t tsg_colsum_workspace_bytes(int64_t N, int64_t F) {
+  return ws_bytes((size_t)colsum_blocks(N) * (size_t)F, 4) + 256;
+}
+
+extern "C" int tsg_relu_bwd_colsum(const float* dY, const float* Y, float* dYm, float* dbias,
+                                   int64_t N, int64_t F, void* workspace, size_t workspace_bytes,
+                                   void* stream) {
+  TSG_REQUIRE(N >= 0 && F > 0 && dY && dbias, "relu_bwd_colsum: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (workspace_bytes < tsg_colsum_workspace_bytes(N, F)) { set_error("relu_bwd_colsum: workspace too small"); return TSG_EWORKSPACE; }
+  float* part = (float*)workspace;
+  int nb = colsum_blocks(N);
+  int64_t rpb = (N + nb - 1) / nb; if (rpb < 1) rpb = 1;
+  k_relu_bwd_colsum<<<nb, CS_THREADS, CS_THREADS * sizeof(float), st>>>(dY, Y, dYm, part, N, (int)F, rpb);
+  k_colsum_final<<<(int)((F + 127) / 128), 128, 0, st>>>(part, dbias, nb, (int)F);
+  return check_launch("relu_bwd_colsum");
+}

@@ -1,0 +1,287 @@
+// K5 -- SAGPooling selection: per-graph top-k, filter_adj edge compaction, gated gather.
+//
+// Replaces PyG 1.6.3 `topk` / `filter_adj` (called from Code/sag/layers.py:20,23) and the gate
+// x[perm] * tanh(score[perm]) (Code/sag/layers.py:21).  Integer outputs are deterministic and
+// bit-exact: the ordering is a strict total order on (score descending, node id ascending), NaN
+// first, -0.0 == +0.0, i.e. what torch's stable CPU sort produces.
+//
+// top-k = rank selection, one CTA per graph: the graph's keys are staged in shared memory as
+// order-preserving uint32, every thread owns a node and counts the keys that precede its own
+// (broadcast shared-memory reads, no barriers in the hot loop, no atomics).  n_g is ~10^2..10^3,
+// so the O(n^2) compares (72k for a DD graph) cost less than the barriers of a sorting network.
+#include "common.cuh"
+
+namespace tsg {
+
+// order-preserving map: larger key <=> earlier in a descending sort. NaN -> max, -0 -> +0.
+__device__ __forceinline__ uint32_t score_key(float s) {
+  if (s != s) return 0xFFFFFFFFu;
+  if (s == 0.f) s = 0.f;                       // canonicalise -0.0
+  uint32_t b = __float_as_uint(s);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+struct KofN {
+  const int64_t* gptr; float ratio;
+  __device__ int operator()(int64_t g) const {
+    float n = (float)(gptr[g + 1] - gptr[g]);
+    return (int)ceilf(__fmul_rn(ratio, n));
+  }
+};
+
+constexpr int TOPK_THREADS = 128;
+constexpr int TOPK_SMEM_KEYS = 8192;   // 32 KB of keys; larger graphs read keys from global
+
+__global__ void __launch_bounds__(TOPK_THREADS)
+k_topk_rank(const float* __restrict__ score, const int64_t* __restrict__ gptr,
+            const int64_t* __restrict__ kptr, int64_t* __restrict__ perm, uint32_t* __restrict__ gkeys) {
+  __shared__ uint32_t skeys[TOPK_SMEM_KEYS];
+  const int g = blockIdx.x;
+  const int64_t base = gptr[g];
+  const int n = (int)(gptr[g + 1] - base);
+  const int64_t obase = kptr[g];
+  const int k = (int)(kptr[g + 1] - obase);
+  if (n == 0 || k == 0) return;
+  const bool in_smem = n <= TOPK_SMEM_KEYS;
+  uint32_t* keys = in_smem ? skeys : (gkeys + base);
+  for (int i = threadIdx.x; i < n; i += TOPK_THREADS) keys[i] = score_key(score[base + i]);
+  __syncthreads();    // (global path: writes by this block, read by this block after the barrier)
+  for (int i = threadIdx.x; i < n; i += TOPK_THREADS) {
+    const uint32_t ki = keys[i];
+    int rank = 0;
+    int j = 0;
+    for (; j + 4 <= n; j += 4) {
+      uint32_t a = keys[j], b = keys[j + 1], c = keys[j + 2], d = keys[j + 3];
+      rank += (a > ki) || (a == ki && j < i);
+      rank += (b > ki) || (b == ki && j + 1 < i);
+      rank += (c > ki) || (c == ki && j + 2 < i);
+      rank += (d > ki) || (d == ki && j + 3 < i);
+    }
+    for (; j < n; ++j) { uint32_t a = keys[j]; rank += (a > ki) || (a == ki && j < i); }
+    if (rank < k) perm[obase + rank] = base + i;
+  }
+}
+
+__global__ void k_batch_to_ptr(const int64_t* __restrict__ batch, int64_t n, int64_t G, int64_t* __restrict__ gptr) {
+  // graph_ptr[g] = first i with batch[i] >= g ; batch sorted ascending
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t prev = i == 0 ? -1 : batch[i - 1];
+    int64_t cur = i == n ? G : batch[i];
+    if (cur > G) cur = G;
+    for (int64_t g = prev + 1; g <= cur; ++g) gptr[g] = i;
+  }
+}
+
+// ---------------------------------- filter_adj -------------------------------------------
+constexpr int FA_THREADS = 256;
+constexpr int FA_ITEMS = 8;
+constexpr int FA_TILE = FA_THREADS * FA_ITEMS;
+
+__global__ void k_inv_perm(const int64_t* __restrict__ perm, int64_t k, int* __restrict__ inv) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < k;
+       i += (int64_t)gridDim.x * blockDim.x)
+    inv[perm[i]] = (int)i;
+}
+
+// pass 1: per-tile survivor count.  pass 2 (WRITE): order-preserving compaction.
+template <bool WRITE>
+__global__ void __launch_bounds__(FA_THREADS)
+k_filter_adj(const int64_t* __restrict__ row, const int64_t* __restrict__ col, int64_t E_cap,
+             const int64_t* __restrict__ E_dev, const int* __restrict__ inv,
+             int* __restrict__ tile_cnt, const int* __restrict__ tile_off,
+             int64_t* __restrict__ out_row, int64_t* __restrict__ out_col) {
+  __shared__ int wcnt[FA_ITEMS][FA_THREADS / 32];
+  __shared__ int woff[FA_ITEMS][FA_THREADS / 32];
+  const int64_t E = dev_count(E_cap, E_dev);
+  const int64_t base = (int64_t)blockIdx.x * FA_TILE;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int nr[FA_ITEMS], nc[FA_ITEMS];
+  unsigned ball[FA_ITEMS];
+#pragma unroll
+  for (int k = 0; k < FA_ITEMS; ++k) {
+    int64_t e = base + k * FA_THREADS + threadIdx.x;
+    int r = -1, c = -1;
+    if (e < E) { r = inv[row[e]]; c = inv[col[e]]; }
+    bool keep = (r >= 0) && (c >= 0);
+    nr[k] = r; nc[k] = c;
+    ball[k] = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) wcnt[k][w] = __popc(ball[k]);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int s = 0;
+    for (int k = 0; k < FA_ITEMS; ++k)
+      for (int ww = 0; ww < FA_THREADS / 32; ++ww) { woff[k][ww] = s; s += wcnt[k][ww]; }
+    if (!WRITE) tile_cnt[blockIdx.x] = s;
+  }
+  if (!WRITE) return;
+  __syncthreads();
+  const int toff = tile_off[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < FA_ITEMS; ++k) {
+    if ((ball[k] >> lane) & 1u) {
+      int p = toff + woff[k][w] + __popc(ball[k] & ((1u << lane) - 1u));
+      out_row[p] = nr[k];
+      out_col[p] = nc[k];
+    }
+  }
+}
+
+struct TileCnt {
+  const int* c;
+  __device__ int operator()(int64_t i) const { return c[i]; }
+};
+
+__global__ void k_store_count(const int* src, int64_t* dst) { *dst = (int64_t)*src; }
+
+// ---------------------------------- gated gather -----------------------------------------
+template <int VEC>
+__global__ void __launch_bounds__(256)
+k_gate_gather_fwd(const float* __restrict__ x, const float* __restrict__ score,
+                  const int64_t* __restrict__ perm, const int64_t* __restrict__ batch,
+                  float* __restrict__ xo, int64_t* __restrict__ batch_out, int64_t K, int F) {
+  const int FV = F / VEC;
+  const int64_t total = K * FV;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    int64_t i = idx / FV; int f = (int)(idx - i * FV);
+    int64_t j = perm[i];
+    float t = tanhf(score[j]);
+    if (VEC == 4) {
+      float4 v = __ldg(reinterpret_cast<const float4*>(x) + j * FV + f);
+      v.x *= t; v.y *= t; v.z *= t; v.w *= t;
+      reinterpret_cast<float4*>(xo)[i * FV + f] = v;
+    } else {
+      xo[i * FV + f] = x[j * FV + f] * t;
+    }
+    if (f == 0 && batch != nullptr) batch_out[i] = batch[j];
+  }
+}
+
+// one group of LPR lanes per source node j; writes every row of dx (zeros for dropped nodes)
+template <int LPR>
+__global__ void __launch_bounds__(256)
+k_gate_gather_bwd(const float* __restrict__ dxo, const float* __restrict__ x,
+                  const float* __restrict__ score, const int* __restrict__ inv,
+                  float* __restrict__ dx, float* __restrict__ dscore, int64_t N, int F) {
+  const int l = threadIdx.x % LPR;
+  const int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
+  const int64_t ngroups = ((int64_t)gridDim.x * blockDim.x) / LPR;
+  // shuffles name only the LPR lanes of this group, which always iterate together
+  const unsigned gmask = LPR == 32 ? 0xffffffffu
+                                   : (((1u << LPR) - 1u) << (((threadIdx.x & 31) / LPR) * LPR));
+  for (int64_t j = group; j < N; j += ngroups) {
+    int m = inv[j];
+    float dot = 0.f;
+    float t = 0.f;
+    if (m >= 0) t = tanhf(score[j]);
+    for (int f = l; f < F; f += LPR) {
+      float g = 0.f;
+      if (m >= 0) {
+        float go = dxo[(int64_t)m * F + f];
+        dot += go * x[j * F + f];
+        g = go * t;
+      }
+      dx[j * F + f] = g;
+    }
+#pragma unroll
+    for (int d = LPR / 2; d > 0; d >>= 1) dot += __shfl_xor_sync(gmask, dot, d);
+    if (l == 0) dscore[j] = m >= 0 ? dot * (1.f - t * t) : 0.f;
+  }
+}
+
+}  // namespace tsg
+
+using namespace tsg;
+
+extern "C" size_t tsg_topk_workspace_bytes(int64_t N, int64_t G) {
+  return ws_bytes(scan_ws_ints(G), 4) + ws_bytes((size_t)N + 1, 4) + 512;
+}
+
+extern "C" int tsg_topk_sizes(const int64_t* gptr, int64_t G, float ratio, int64_t* kptr,
+                              void* workspace, size_t workspace_bytes, void* stream) {
+  TSG_REQUIRE(G >= 0 && gptr && kptr, "topk_sizes: bad arguments");
+  if (workspace_bytes < tsg_topk_workspace_bytes(0, G)) { set_error("topk_sizes: workspace too small"); return TSG_EWORKSPACE; }
+  return exclusive_scan(KofN{gptr, ratio}, G, kptr, (int*)workspace, (cudaStream_t)stream);
+}
+
+extern "C" int tsg_topk(const float* score, const int64_t* gptr, const int64_t* kptr, int64_t G,
+                        int64_t N, int64_t* perm, void* workspace, size_t workspace_bytes, void* stream) {
+  TSG_REQUIRE(G >= 0 && N >= 0, "topk: bad sizes");
+  if (G == 0 || N == 0) return TSG_OK;
+  TSG_REQUIRE(score && gptr && kptr && perm, "topk: null pointer");
+  if (workspace_bytes < tsg_topk_workspace_bytes(N, G)) { set_error("topk: workspace too small"); return TSG_EWORKSPACE; }
+  Workspace ws(workspace, workspace_bytes);
+  ws.take<int>(scan_ws_ints(G));
+  uint32_t* gkeys = ws.take<uint32_t>(N + 1);
+  TSG_REQUIRE(G < (int64_t)0x7fffffff, "topk: too many graphs");
+  k_topk_rank<<<(int)G, TOPK_THREADS, 0, (cudaStream_t)stream>>>(score, gptr, kptr, perm, gkeys);
+  return check_launch("topk");
+}
+
+extern "C" int tsg_batch_to_ptr(const int64_t* batch, int64_t N, int64_t G, int64_t* gptr, void* stream) {
+  TSG_REQUIRE(N >= 0 && G >= 0 && gptr && (N == 0 || batch), "batch_to_ptr: bad arguments");
+  k_batch_to_ptr<<<grid_for(N + 1, 256), 256, 0, (cudaStream_t)stream>>>(batch, N, G, gptr);
+  return check_launch("batch_to_ptr");
+}
+
+extern "C" size_t tsg_filter_adj_workspace_bytes(int64_t E) {
+  size_t tiles = (size_t)((E + FA_TILE - 1) / FA_TILE) + 1;
+  return 2 * ws_bytes(tiles + 1, 4) + ws_bytes(scan_ws_ints((int64_t)tiles), 4) + 512;
+}
+
+extern "C" int tsg_filter_adj(const int64_t* row, const int64_t* col, int64_t E, const int64_t* E_dev,
+                              const int64_t* perm, int64_t K, int64_t N, int32_t* inv,
+                              int64_t* out_row, int64_t* out_col, int64_t* out_E_dev,
+                              void* workspace, size_t workspace_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  TSG_REQUIRE(E >= 0 && K >= 0 && N >= 0 && inv && out_E_dev, "filter_adj: bad arguments");
+  TSG_REQUIRE(E < (int64_t)0x7fffffff && N < (int64_t)0x7fffffff, "filter_adj: sizes must stay below 2^31");
+  if (workspace_bytes < tsg_filter_adj_workspace_bytes(E)) { set_error("filter_adj: workspace too small"); return TSG_EWORKSPACE; }
+  int tiles = (int)((E + FA_TILE - 1) / FA_TILE);
+  Workspace ws(workspace, workspace_bytes);
+  int* tile_cnt = ws.take<int>(tiles + 2);
+  int* tile_off = ws.take<int>(tiles + 2);
+  int* scan_ws = ws.take<int>(scan_ws_ints(tiles + 1));
+  if (N > 0) cudaMemsetAsync(inv, 0xFF, (size_t)N * 4, st);
+  if (K > 0) k_inv_perm<<<grid_for(K, 256), 256, 0, st>>>(perm, K, inv);
+  if (tiles == 0) { cudaMemsetAsync(out_E_dev, 0, 8, st); return check_launch("filter_adj(empty)"); }
+  k_filter_adj<false><<<tiles, FA_THREADS, 0, st>>>(row, col, E, E_dev, inv, tile_cnt, nullptr, nullptr, nullptr);
+  int rc = exclusive_scan(TileCnt{tile_cnt}, tiles, tile_off, scan_ws, st);
+  if (rc) return rc;
+  k_store_count<<<1, 1, 0, st>>>(tile_off + tiles, out_E_dev);
+  k_filter_adj<true><<<tiles, FA_THREADS, 0, st>>>(row, col, E, E_dev, inv, nullptr, tile_off, out_row, out_col);
+  return check_launch("filter_adj");
+}
+
+extern "C" int tsg_gate_gather_fwd(const float* x, const float* score, const int64_t* perm,
+                                   const int64_t* batch, float* xo, int64_t* batch_out,
+                                   int64_t K, int64_t F, void* stream) {
+  TSG_REQUIRE(K >= 0 && F > 0, "gate_gather_fwd: bad shape");
+  if (K == 0) return TSG_OK;
+  TSG_REQUIRE(x && score && perm && xo, "gate_gather_fwd: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  bool vec = F % 4 == 0 && (((uintptr_t)x | (uintptr_t)xo) & 15) == 0;
+  if (vec) k_gate_gather_fwd<4><<<grid_for(K * (F / 4), 256), 256, 0, st>>>(x, score, perm, batch, xo, batch_out, K, (int)F);
+  else k_gate_gather_fwd<1><<<grid_for(K * F, 256), 256, 0, st>>>(x, score, perm, batch, xo, batch_out, K, (int)F);
+  return check_launch("gate_gather_fwd");
+}
+
+extern "C" int tsg_gate_gather_bwd(const float* dxo, const float* x, const float* score,
+                                   const int32_t* inv, float* dx, float* dscore,
+                                   int64_t N, int64_t F, void* stream) {
+  TSG_REQUIRE(N >= 0 && F > 0, "gate_gather_bwd: bad shape");
+  if (N == 0) return TSG_OK;
+  TSG_REQUIRE(dxo && x && score && inv && dx && dscore, "gate_gather_bwd: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  int lpr = 1; while (lpr < F && lpr < 32) lpr <<= 1;
+  int grid = grid_for(N, 256 / lpr);
+#define TSG_GO(L) k_gate_gather_bwd<L><<<grid, 256, 0, st>>>(dxo, x, score, inv, dx, dscore, N, (int)F)
+  switch (lpr) {
+    case 1: TSG_GO(1); break; case 2: TSG_GO(2); break; case 4: TSG_GO(4); break;
+    case 8: TSG_GO(8); break; case 16: TSG_GO(16); break; default: TSG_GO(32); break;
+  }
+#undef TSG_GO
+  return check_launch("gate_gather_bwd");
+}

@@ -1,0 +1,93 @@
+"""ctypes binding of libtsg.so (the C ABI declared in /include/tsg.h).
+
+There is deliberately NO fallback: if the shared library is missing or an entry point fails,
+importing / calling raises.  Tensors cross the boundary as raw device pointers.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "libtsg.so")
+
+P, I64, SZ, I, F32 = c_void_p, c_int64, c_size_t, c_int, c_float
+
+# name -> (restype, argtypes); mirrors include/tsg.h line by line
+_PROTOTYPES = {
+    "tsg_abi_version": (I, []),
+    "tsg_last_error": (c_char_p, []),
+    "tsg_check_device": (I, []),
+    "tsg_csr_build_workspace_bytes": (SZ, [I64, I64]),
+    "tsg_csr_build": (I, [P, P, P, I64, P, I64, I, P, P, P, P, P, P, P, P, P, SZ, P]),
+    "tsg_spmm": (I, [P, P, P, P, P, P, I64, I64, I, P]),
+    "tsg_colsum_workspace_bytes": (SZ, [I64, I64]),
+    "tsg_relu_bwd_colsum": (I, [P, P, P, P, I64, I64, P, SZ, P]),
+    "tsg_topk_workspace_bytes": (SZ, [I64, I64]),
+    "tsg_topk_sizes": (I, [P, I64, F32, P, P, SZ, P]),
+    "tsg_topk": (I, [P, P, P, I64, I64, P, P, SZ, P]),
+    "tsg_batch_to_ptr": (I, [P, I64, I64, P, P]),
+    "tsg_filter_adj_workspace_bytes": (SZ, [I64]),
+    "tsg_filter_adj": (I, [P, P, I64, P, P, I64, I64, P, P, P, P, P, SZ, P]),
+    "tsg_gate_gather_fwd": (I, [P, P, P, P, P, P, I64, I64, P]),
+    "tsg_gate_gather_bwd": (I, [P, P, P, P, P, P, I64, I64, P]),
+    "tsg_readout_fwd": (I, [P, P, I64, I64, I, P, I64, P, P]),
+    "tsg_readout_bwd": (I, [P, I64, P, P, I64, I64, I64, I, P, P]),
+    "tsg_triplet_workspace_bytes": (SZ, [I64, I64, I64]),
+    "tsg_triplet_fwd": (I, [P, P, I64, I64, I64, F32, F32, P, P, P, P, SZ, P]),
+    "tsg_triplet_bwd": (I, [P, P, I64, I64, I64, F32, F32, P, P, P, P, P, SZ, P]),
+    "tsg_pairdist_matrix": (I, [P, I64, I64, F32, P, P]),
+}
+
+EXPORTS = tuple(_PROTOTYPES)
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+        "(or `make -C two-stage-gnn_b200/csrc`). tsg has no CPU or eager fallback.")
+
+lib = ctypes.CDLL(LIB_PATH)
+for _name, (_res, _args) in _PROTOTYPES.items():
+    _fn = getattr(lib, _name)          # AttributeError here = header/library mismatch
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+if lib.tsg_abi_version() != 1:
+    raise ImportError(f"libtsg ABI version {lib.tsg_abi_version()} != 1")
+
+# number of libtsg entry points that enqueue GPU work, counted since import (bench.py reports it)
+launch_calls = 0
+
+
+def last_error() -> str:
+    return lib.tsg_last_error().decode()
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL). Refuses CPU tensors: no fallback."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("tsg: expected a CUDA tensor (there is no CPU path)")
+    if not t.is_contiguous():
+        raise RuntimeError("tsg: expected a contiguous tensor")
+    return t.data_ptr()
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name: str, *args) -> None:
+    global launch_calls
+    rc = getattr(lib, name)(*args)
+    launch_calls += 1
+    if rc != 0:
+        raise RuntimeError(f"{name} failed ({rc}): {last_error()}")
+
+
+def workspace(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)

@@ -1,0 +1,165 @@
+"""Modules mirroring the reference's operator/plugin surface for the SAGPool path.
+
+* `GCNConv`   -- same constructor, parameter names/shapes/initialisers and forward signature as
+  PyG 1.6.3's GCNConv as used in Code/sag/network.py:19-23 and Code/sag/layers.py:12, so the
+  reference's `state_dict` keys (`conv1.weight` [in,out], `pool1.score_layer.bias`, ...) round-trip.
+* `PackedSAGNet` -- Code/sag/network.py:9-53 `Net` with the `batch` vector the reference's
+  commented-out line (network.py:31) would have passed: one forward over a block-diagonal packed
+  batch of many graphs instead of one graph per call.  Same parameters, same arithmetic per graph.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import ops
+from .ops import CSR, EdgeList
+
+
+def _glorot_(t: torch.Tensor) -> None:
+    a = math.sqrt(6.0 / (t.size(-2) + t.size(-1)))
+    with torch.no_grad():
+        t.uniform_(-a, a)
+
+
+class _CsrCache:
+    """conv_k and pool_k.score_layer receive the SAME edge_index tensor (Code/sag/network.py:34-35,
+    layers.py:18): build K1's CSR once per pooling level and reuse it.  Keyed on the tensor object
+    (held alive so its storage cannot be recycled) plus its version counter."""
+
+    def __init__(self, slots: int = 4):
+        self.slots, self.items = slots, []
+
+    def get(self, edge_index: torch.Tensor, num_nodes: int) -> CSR:
+        for ei, ver, n, csr in self.items:
+            if ei is edge_index and ver == edge_index._version and n == num_nodes:
+                return csr
+        csr = ops.build_csr(EdgeList.from_edge_index(edge_index), num_nodes)
+        self.items.append((edge_index, edge_index._version, num_nodes, csr))
+        if len(self.items) > self.slots:
+            self.items.pop(0)
+        return csr
+
+
+_GLOBAL_CSR_CACHE = _CsrCache()
+
+
+class GCNConv(torch.nn.Module):
+    """Drop-in for torch_geometric.nn.GCNConv (defaults improved=False, cached=False,
+    add_self_loops=True, normalize=True, bias=True)."""
+
+    def __init__(self, in_channels: int, out_channels: int, improved: bool = False,
+                 cached: bool = False, add_self_loops: bool = True, normalize: bool = True,
+                 bias: bool = True, **kwargs):
+        super().__init__()
+        if improved or not add_self_loops or not normalize:
+            raise NotImplementedError("tsg.GCNConv implements the configuration the reference uses: "
+                                      "improved=False, add_self_loops=True, normalize=True")
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.weight = torch.nn.Parameter(torch.empty(in_channels, out_channels))
+        self.bias = torch.nn.Parameter(torch.empty(out_channels)) if bias else None
+        self.reset_parameters()
+
+    def reset_parameters(self) -> None:
+        _glorot_(self.weight)
+        if self.bias is not None:
+            torch.nn.init.zeros_(self.bias)
+
+    def forward(self, x: torch.Tensor, edge_index, edge_weight: Optional[torch.Tensor] = None,
+                relu: bool = False) -> torch.Tensor:
+        if isinstance(edge_index, CSR):
+            csr = edge_index
+        elif edge_weight is not None:
+            csr = ops.build_csr(EdgeList.from_edge_index(edge_index), x.size(0), edge_weight=edge_weight)
+        else:
+            csr = _GLOBAL_CSR_CACHE.get(edge_index, x.size(0))
+        return ops.gcn_conv(x, csr, self.weight, self.bias, relu=relu)
+
+    def __repr__(self):
+        return f"{self.__class__.__name__}({self.in_channels}, {self.out_channels})"
+
+
+class _ScoreLayerHolder(torch.nn.Module):
+    """Keeps the reference's module path `poolK.score_layer.{weight,bias}` (Code/sag/layers.py:12)."""
+
+    def __init__(self, in_channels: int):
+        super().__init__()
+        self.score_layer = GCNConv(in_channels, 1)
+
+
+def host_level_ptrs(node_ptr: np.ndarray, ratio: float, levels: int = 3) -> np.ndarray:
+    """Node offsets of every pooling level, computed on the host from the graph sizes exactly as
+    PyG's topk does on the device: k = ceil(float32(ratio) * float32(n)).  int64 [levels+1, G+1]."""
+    n = np.diff(node_ptr).astype(np.int64)
+    out = np.zeros((levels + 1, n.shape[0] + 1), np.int64)
+    out[0, 1:] = np.cumsum(n)
+    for l in range(1, levels + 1):
+        n = np.ceil(np.float32(ratio) * n.astype(np.float32)).astype(np.int64)
+        out[l, 1:] = np.cumsum(n)
+    return out
+
+
+class PackedSAGNet(torch.nn.Module):
+    """Code/sag/network.py `Net` over a packed batch.  Three levels of
+    GCNConv -> ReLU -> SAGPool(score GCNConv, top-k, gate, filter_adj) -> [gmp || gap],
+    summed, then lin1/ReLU/dropout/lin2/ReLU/lin3/log_softmax."""
+
+    def __init__(self, num_features: int, nhid: int, num_classes: int, pooling_ratio: float,
+                 dropout_ratio: float):
+        super().__init__()
+        self.num_features, self.nhid, self.num_classes = num_features, nhid, num_classes
+        self.pooling_ratio, self.dropout_ratio = pooling_ratio, dropout_ratio
+        self.conv1 = GCNConv(num_features, nhid); self.pool1 = _ScoreLayerHolder(nhid)
+        self.conv2 = GCNConv(nhid, nhid); self.pool2 = _ScoreLayerHolder(nhid)
+        self.conv3 = GCNConv(nhid, nhid); self.pool3 = _ScoreLayerHolder(nhid)
+        self.lin1 = torch.nn.Linear(nhid * 2, nhid)
+        self.lin2 = torch.nn.Linear(nhid, nhid // 2)
+        self.lin3 = torch.nn.Linear(nhid // 2, num_classes)
+
+    def forward(self, x: torch.Tensor, edge_index, node_ptr_host: np.ndarray,
+                return_aux: bool = False):
+        """x [sum n, F] f32, edge_index int64 [2, sum E] (or an EdgeList), node_ptr_host int64 [G+1]
+        on the HOST (graph sizes are known where the batch was packed, so every level's sizes are
+        computed without a device round trip)."""
+        dev = x.device
+        edges = edge_index if isinstance(edge_index, EdgeList) else EdgeList.from_edge_index(edge_index)
+        plan = host_level_ptrs(np.asarray(node_ptr_host), self.pooling_ratio)
+        ptrs = torch.from_numpy(plan).pin_memory().to(dev, non_blocking=True)
+        aux = {"perm": [], "edges": [], "score": []}
+        outs = []
+        for lvl, (conv, pool) in enumerate(((self.conv1, self.pool1), (self.conv2, self.pool2),
+                                            (self.conv3, self.pool3))):
+            n_l, k_l = int(plan[lvl, -1]), int(plan[lvl + 1, -1])
+            csr = ops.build_csr(edges, n_l)
+            h = conv(x, csr, relu=True)                                   # network.py:34
+            score = pool.score_layer(h, csr).view(-1)                     # layers.py:18
+            perm = ops.topk(score, ptrs[lvl], ptrs[lvl + 1], k_l)         # layers.py:20
+            edges, inv = ops.filter_adj(edges, perm, n_l)                 # layers.py:23
+            x = ops.gate_gather(h, score, perm, inv)                      # layers.py:21
+            outs.append(ops.readout(x, ptrs[lvl + 1]))                    # network.py:36
+            if return_aux:
+                aux["perm"].append(perm); aux["edges"].append(edges); aux["score"].append(score)
+        z = outs[0] + outs[1] + outs[2]                                   # network.py:46
+        z = F.relu(self.lin1(z))
+        z = F.dropout(z, p=self.dropout_ratio, training=self.training)
+        z = F.relu(self.lin2(z))
+        z = F.log_softmax(self.lin3(z), dim=-1)
+        return (z, aux) if return_aux else z
+
+
+class PackedTripletNet(torch.nn.Module):
+    """Code/sag/tripletnet.py over packed batches: ONE forward over all graphs of the step, then
+    K9 on index triplets.  Returns (loss, dist_p, dist_n, embeddings)."""
+
+    def __init__(self, model: torch.nn.Module, margin: float = 1.5):
+        super().__init__()
+        self.model, self.margin = model, margin
+
+    def forward(self, x, edge_index, node_ptr_host, triplets: torch.Tensor):
+        emb = self.model(x, edge_index, node_ptr_host)
+        loss, dp, dn = ops.triplet_loss(emb, triplets, self.margin)
+        return loss, dp, dn, emb

@@ -1,0 +1,300 @@
+"""Host-side operator layer over libtsg.so: torch.autograd.Function wrappers whose forward and
+backward are hand-written sm_100a kernels reached through the C ABI (include/tsg.h).
+
+PyTorch is plumbing here (device memory, streams, autograd graph bookkeeping, the dense
+Linear/GEMM pieces); every message-passing / pooling / readout / triplet kernel is ours.
+There is no CPU path: CPU tensors raise.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import call, ptr, stream_ptr, workspace, lib
+
+CSR_GCN, CSR_RAW = 0, 1
+SPMM_RELU = 1
+READOUT_MAX, READOUT_MEAN, READOUT_SUM = 1, 2, 4
+
+
+# --------------------------------------------------------------------------------------------
+# containers
+# --------------------------------------------------------------------------------------------
+@dataclass
+class EdgeList:
+    """COO edge list; `count` (device int64 scalar) overrides `cap` when the number of valid
+    edges is data dependent (after filter_adj) so no host sync is needed."""
+    row: torch.Tensor
+    col: torch.Tensor
+    cap: int
+    count: Optional[torch.Tensor] = None
+
+    @staticmethod
+    def from_edge_index(edge_index: torch.Tensor) -> "EdgeList":
+        if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.size(0) != 2:
+            raise RuntimeError("edge_index must be int64 [2, E]")
+        ei = edge_index.contiguous()
+        return EdgeList(ei[0], ei[1], int(ei.size(1)))
+
+    def edge_index(self) -> torch.Tensor:
+        """Exact-shape PyG edge_index [2, E'] (synchronises once if the count is on the device)."""
+        e = self.cap if self.count is None else int(self.count.item())
+        return torch.stack([self.row[:e], self.col[:e]])
+
+
+@dataclass
+class CSR:
+    rowptr: torch.Tensor
+    colidx: torch.Tensor
+    val: torch.Tensor
+    eid: Optional[torch.Tensor]
+    t_rowptr: Optional[torch.Tensor]
+    t_colidx: Optional[torch.Tensor]
+    t_val: Optional[torch.Tensor]
+    t_eid: Optional[torch.Tensor]
+    num_nodes: int
+
+
+def build_csr(edges: EdgeList, num_nodes: int, mode: int = CSR_GCN, transposed: bool = True,
+              edge_weight: Optional[torch.Tensor] = None, want_eid: bool = False) -> CSR:
+    """K1: stable counting sort of the (self-loop augmented) COO list into dst-major (+ src-major)
+    CSR with GCN normalisation.  Reference: PyG gcn_norm via Code/sag/network.py:34."""
+    dev = edges.row.device
+    E, N = edges.cap, int(num_nodes)
+    cap = E + (N if mode == CSR_GCN else 0)
+    i32 = dict(dtype=torch.int32, device=dev)
+    rowptr = torch.empty(N + 1, **i32)
+    colidx = torch.empty(cap, **i32)
+    val = torch.empty(cap, dtype=torch.float32, device=dev)
+    eid = torch.empty(cap, **i32) if want_eid else None
+    if transposed:
+        t_rowptr = torch.empty(N + 1, **i32)
+        t_colidx = torch.empty(cap, **i32)
+        t_val = torch.empty(cap, dtype=torch.float32, device=dev)
+        t_eid = torch.empty(cap, **i32) if want_eid else None
+    else:
+        t_rowptr = t_colidx = t_val = t_eid = None
+    wsb = lib.tsg_csr_build_workspace_bytes(E, N)
+    ws = workspace(wsb, dev)
+    call("tsg_csr_build", ptr(edges.row), ptr(edges.col), ptr(edge_weight), E, ptr(edges.count), N,
+         mode, ptr(rowptr), ptr(colidx), ptr(val), ptr(eid), ptr(t_rowptr), ptr(t_colidx),
+         ptr(t_val), ptr(t_eid), ptr(ws), wsb, stream_ptr())
+    return CSR(rowptr, colidx, val, eid, t_rowptr, t_colidx, t_val, t_eid, N)
+
+
+def spmm_raw(rowptr, colidx, val, H: torch.Tensor, bias=None, relu: bool = False) -> torch.Tensor:
+    n = rowptr.numel() - 1
+    H = H.contiguous()
+    Y = torch.empty(n, H.size(1), dtype=torch.float32, device=H.device)
+    call("tsg_spmm", ptr(rowptr), ptr(colidx), ptr(val), ptr(H), ptr(bias), ptr(Y), n, H.size(1),
+         SPMM_RELU if relu else 0, stream_ptr())
+    return Y
+
+
+def relu_bwd_colsum(dY: torch.Tensor, Y: Optional[torch.Tensor], want_masked: bool):
+    """dYm = dY * (Y > 0) and dbias = column sums of dYm in one pass (deterministic)."""
+    dY = dY.contiguous()
+    n, f = dY.shape
+    dYm = torch.empty_like(dY) if want_masked else None
+    db = torch.empty(f, dtype=torch.float32, device=dY.device)
+    wsb = lib.tsg_colsum_workspace_bytes(n, f)
+    ws = workspace(wsb, dY.device)
+    call("tsg_relu_bwd_colsum", ptr(dY), ptr(Y), ptr(dYm), ptr(db), n, f, ptr(ws), wsb, stream_ptr())
+    return dYm, db
+
+
+class _SpMM(torch.autograd.Function):
+    """Y = A_hat H (+ bias) (ReLU);  dH = A_hat^T dY' via the src-major CSR (K2 both ways)."""
+
+    @staticmethod
+    def forward(ctx, H, bias, csr: CSR, relu: bool):
+        Y = spmm_raw(csr.rowptr, csr.colidx, csr.val, H, bias, relu)
+        ctx.csr, ctx.relu, ctx.has_bias = csr, relu, bias is not None
+        ctx.save_for_backward(Y if relu else None)
+        return Y
+
+    @staticmethod
+    def backward(ctx, dY):
+        (Y,) = ctx.saved_tensors
+        csr = ctx.csr
+        if csr.t_rowptr is None:
+            raise RuntimeError("tsg: CSR was built without the transposed orientation")
+        dY = dY.contiguous()
+        db = None
+        if ctx.relu or ctx.has_bias:
+            dYm, db = relu_bwd_colsum(dY, Y, want_masked=ctx.relu)
+            if ctx.relu:
+                dY = dYm
+            if not ctx.has_bias:
+                db = None
+        dH = spmm_raw(csr.t_rowptr, csr.t_colidx, csr.t_val, dY) if ctx.needs_input_grad[0] else None
+        return dH, db, None, None
+
+
+def spmm(csr: CSR, H: torch.Tensor, bias: Optional[torch.Tensor] = None, relu: bool = False):
+    return _SpMM.apply(H, bias, csr, relu)
+
+
+def gcn_conv(x: torch.Tensor, csr: CSR, weight: torch.Tensor, bias: Optional[torch.Tensor],
+             relu: bool = False) -> torch.Tensor:
+    """PyG GCNConv.forward (Code/sag/network.py:34): (A_hat (X W)) + b, CSR prebuilt by K1."""
+    return spmm(csr, x @ weight, bias, relu)
+
+
+# --------------------------------------------------------------------------------------------
+# top-k / filter_adj / gate
+# --------------------------------------------------------------------------------------------
+def batch_to_ptr(batch: torch.Tensor, num_graphs: int) -> torch.Tensor:
+    gptr = torch.empty(num_graphs + 1, dtype=torch.int64, device=batch.device)
+    call("tsg_batch_to_ptr", ptr(batch.contiguous()), batch.numel(), num_graphs, ptr(gptr), stream_ptr())
+    return gptr
+
+
+def topk_sizes(graph_ptr: torch.Tensor, ratio: float) -> torch.Tensor:
+    G = graph_ptr.numel() - 1
+    kptr = torch.empty(G + 1, dtype=torch.int64, device=graph_ptr.device)
+    wsb = lib.tsg_topk_workspace_bytes(0, G)
+    ws = workspace(wsb, graph_ptr.device)
+    call("tsg_topk_sizes", ptr(graph_ptr), G, float(ratio), ptr(kptr), ptr(ws), wsb, stream_ptr())
+    return kptr
+
+
+def topk(score: torch.Tensor, graph_ptr: torch.Tensor, k_ptr: torch.Tensor, num_selected: int
+         ) -> torch.Tensor:
+    """K5a. perm [num_selected] int64, graph-major, score-descending, ties -> lower id."""
+    score = score.detach().contiguous()
+    G, N = graph_ptr.numel() - 1, score.numel()
+    perm = torch.empty(num_selected, dtype=torch.int64, device=score.device)
+    wsb = lib.tsg_topk_workspace_bytes(N, G)
+    ws = workspace(wsb, score.device)
+    call("tsg_topk", ptr(score), ptr(graph_ptr), ptr(k_ptr), G, N, ptr(perm), ptr(ws), wsb, stream_ptr())
+    return perm
+
+
+def filter_adj(edges: EdgeList, perm: torch.Tensor, num_nodes: int) -> Tuple[EdgeList, torch.Tensor]:
+    """K5b. Returns the relabelled surviving edges (capacity buffers + device count) and inv_perm."""
+    dev = perm.device
+    E = edges.cap
+    inv = torch.empty(num_nodes, dtype=torch.int32, device=dev)
+    out = torch.empty(2, max(E, 1), dtype=torch.int64, device=dev)
+    cnt = torch.empty(1, dtype=torch.int64, device=dev)
+    wsb = lib.tsg_filter_adj_workspace_bytes(E)
+    ws = workspace(wsb, dev)
+    call("tsg_filter_adj", ptr(edges.row), ptr(edges.col), E, ptr(edges.count), ptr(perm),
+         perm.numel(), num_nodes, ptr(inv), ptr(out[0]), ptr(out[1]), ptr(cnt), ptr(ws), wsb,
+         stream_ptr())
+    return EdgeList(out[0], out[1], E, cnt), inv
+
+
+class _GateGather(torch.autograd.Function):
+    """xo = x[perm] * tanh(score[perm])  (Code/sag/layers.py:21)."""
+
+    @staticmethod
+    def forward(ctx, x, score, perm, inv_perm):
+        x = x.contiguous(); score = score.contiguous()
+        K, F = perm.numel(), x.size(1)
+        xo = torch.empty(K, F, dtype=torch.float32, device=x.device)
+        call("tsg_gate_gather_fwd", ptr(x), ptr(score), ptr(perm), None, ptr(xo), None, K, F, stream_ptr())
+        ctx.save_for_backward(x, score, inv_perm)
+        return xo
+
+    @staticmethod
+    def backward(ctx, dxo):
+        x, score, inv = ctx.saved_tensors
+        dxo = dxo.contiguous()
+        dx = torch.empty_like(x)
+        ds = torch.empty_like(score)
+        call("tsg_gate_gather_bwd", ptr(dxo), ptr(x), ptr(score), ptr(inv), ptr(dx), ptr(ds),
+             x.size(0), x.size(1), stream_ptr())
+        return dx, ds, None, None
+
+
+def gate_gather(x, score, perm, inv_perm):
+    return _GateGather.apply(x, score, perm, inv_perm)
+
+
+def gather_batch(batch: torch.Tensor, perm: torch.Tensor) -> torch.Tensor:
+    return batch[perm]
+
+
+# --------------------------------------------------------------------------------------------
+# readout
+# --------------------------------------------------------------------------------------------
+class _Readout(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, graph_ptr, mode):
+        x = x.contiguous()
+        G, F = graph_ptr.numel() - 1, x.size(1)
+        width = F * (bool(mode & READOUT_MAX) + bool(mode & (READOUT_MEAN | READOUT_SUM)))
+        out = torch.empty(G, width, dtype=torch.float32, device=x.device)
+        am = torch.empty(G, F, dtype=torch.int32, device=x.device) if mode & READOUT_MAX else None
+        call("tsg_readout_fwd", ptr(x), ptr(graph_ptr), G, F, mode, ptr(out), width, ptr(am), stream_ptr())
+        ctx.mode, ctx.n, ctx.f = mode, x.size(0), F
+        ctx.save_for_backward(graph_ptr, am)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        gptr, am = ctx.saved_tensors
+        dout = dout.contiguous()
+        # contract: graph_ptr covers every row (graph_ptr[G] == N), so the kernel writes all of dx
+        dx = torch.empty(ctx.n, ctx.f, dtype=torch.float32, device=dout.device)
+        call("tsg_readout_bwd", ptr(dout), dout.size(1), ptr(am), ptr(gptr), gptr.numel() - 1, ctx.n,
+             ctx.f, ctx.mode, ptr(dx), stream_ptr())
+        return dx, None, None
+
+
+def readout(x: torch.Tensor, graph_ptr: torch.Tensor, mode: int = READOUT_MAX | READOUT_MEAN):
+    """K6: [gmp || gap] per graph (Code/sag/network.py:36)."""
+    return _Readout.apply(x, graph_ptr, mode)
+
+
+# --------------------------------------------------------------------------------------------
+# triplet loss
+# --------------------------------------------------------------------------------------------
+class _TripletLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, emb, triplets, margin, eps):
+        emb = emb.contiguous(); triplets = triplets.contiguous()
+        T, (M, D) = triplets.size(0), emb.shape
+        dev = emb.device
+        dp = torch.empty(T, dtype=torch.float32, device=dev)
+        dn = torch.empty(T, dtype=torch.float32, device=dev)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        wsb = lib.tsg_triplet_workspace_bytes(T, M, D)
+        ws = workspace(wsb, dev)
+        call("tsg_triplet_fwd", ptr(emb), ptr(triplets), T, M, D, float(margin), float(eps), ptr(dp),
+             ptr(dn), ptr(loss), ptr(ws), wsb, stream_ptr())
+        ctx.margin, ctx.eps = float(margin), float(eps)
+        ctx.save_for_backward(emb, triplets, dp, dn)
+        ctx.mark_non_differentiable(dp, dn)
+        return loss, dp, dn
+
+    @staticmethod
+    def backward(ctx, dloss, _ddp, _ddn):
+        emb, triplets, dp, dn = ctx.saved_tensors
+        T, (M, D) = triplets.size(0), emb.shape
+        demb = torch.empty_like(emb)
+        wsb = lib.tsg_triplet_workspace_bytes(T, M, D)
+        ws = workspace(wsb, emb.device)
+        dloss = dloss.contiguous().view(1)
+        call("tsg_triplet_bwd", ptr(emb), ptr(triplets), T, M, D, ctx.margin, ctx.eps, ptr(dp), ptr(dn),
+             ptr(dloss), ptr(demb), ptr(ws), wsb, stream_ptr())
+        return demb, None, None, None
+
+
+def triplet_loss(emb: torch.Tensor, triplets: torch.Tensor, margin: float, eps: float = 1e-6):
+    """K9: (loss, d_pos, d_neg) for index triplets [T,3] into emb [M,D]
+    (Code/sag/tripletnet.py:21-22 + train_triplet.py:196,208-211)."""
+    return _TripletLoss.apply(emb, triplets, margin, eps)
+
+
+def pairdist_matrix(emb: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
+    emb = emb.detach().contiguous()
+    M, D = emb.shape
+    out = torch.empty(M, M, dtype=torch.float32, device=emb.device)
+    call("tsg_pairdist_matrix", ptr(emb), M, D, float(eps), ptr(out), stream_ptr())
+    return out
