@@ -18,10 +18,12 @@ versions of every integer op (`*_loops` below) that the vectorised versions must
 Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl reference`
 legs may import this module.  The product path (`two-stage-gnn_b200/tsg`) never does.
 
-One deliberate deviation, documented: PyG writes `deg.pow(-0.5)`.  ATen's CPU kernel lowers
-that to an ISA-dependent vector rsqrt (on AVX512 hosts it differs from IEEE `1/sqrt` by up to
-2 ulp, e.g. deg=267) so it is not reproducible across hosts.  The oracle pins the IEEE form
-`1.0 / sqrt(deg)` (what the scalar path computes); the difference is <= 2.4e-7 relative.
+One deliberate deviation, documented: PyG writes `deg.pow(-0.5)`.  ATen's CPU kernels lower
+pow(-0.5) / sqrt to ISA-dependent vector approximations (on this AVX512 host they differ from the
+correctly rounded result by up to 2 ulp, e.g. deg=267) so they are not reproducible across hosts.
+The oracle pins the IEEE form `1.0 / sqrt(deg)` computed with correctly rounded sqrt and divide
+(`_ieee_rsqrt`); the difference is <= 2.4e-7 relative.  Passing float64 tensors runs the same
+restatement in double precision (used by the tests to measure how well conditioned a quantity is).
 """
 from __future__ import annotations
 
@@ -59,17 +61,29 @@ def add_remaining_self_loops(edge_index: Tensor, edge_weight: Optional[Tensor], 
     return torch.stack([row2, col2]), w2
 
 
-def gcn_norm(edge_index: Tensor, edge_weight: Optional[Tensor], num_nodes: int
-             ) -> Tuple[Tensor, Tensor]:
+def gcn_norm(edge_index: Tensor, edge_weight: Optional[Tensor], num_nodes: int,
+             dtype: torch.dtype = torch.float32) -> Tuple[Tensor, Tensor]:
     """PyG 1.6.3 `GCNConv.norm` / `gcn_norm` (improved=False, add_self_loops=True):
     deg = scatter_add(w, col); norm = deg^-1/2[row] * w * deg^-1/2[col]."""
     ei, w = add_remaining_self_loops(edge_index, edge_weight, num_nodes, 1.0)
+    w = w.to(dtype)
     row, col = ei[0], ei[1]
-    deg = torch.zeros(num_nodes, dtype=torch.float32).index_add_(0, col, w)
-    dis = 1.0 / deg.sqrt()            # IEEE form of deg.pow(-0.5); see module docstring
+    deg = torch.zeros(num_nodes, dtype=dtype).index_add_(0, col, w)
+    dis = _ieee_rsqrt(deg)            # IEEE form of deg.pow(-0.5); see module docstring
     dis[dis == float("inf")] = 0.0
     norm = dis[row] * w * dis[col]    # evaluated left to right: (dis[row]*w)*dis[col]
     return ei, norm
+
+
+def _ieee_rsqrt(deg: Tensor) -> Tensor:
+    """1/sqrt(deg) with correctly rounded sqrt and divide (numpy uses the hardware IEEE
+    instructions; ATen's vectorised CPU sqrt/rsqrt are ISA-dependent approximations that differ
+    in the last bits between hosts, which would make the oracle irreproducible)."""
+    import numpy as np
+    d = deg.numpy()
+    with np.errstate(divide="ignore"):
+        out = (d.dtype.type(1.0) / np.sqrt(d)).astype(d.dtype)
+    return torch.from_numpy(out)
 
 
 def spmm_coo_edge_order(ei: Tensor, norm: Tensor, h: Tensor, num_nodes: int) -> Tensor:
@@ -83,7 +97,7 @@ def gcn_conv(x: Tensor, edge_index: Tensor, weight: Tensor, bias: Optional[Tenso
              edge_weight: Optional[Tensor] = None) -> Tensor:
     """GCNConv.forward with defaults (improved=False, cached=False, normalize=True)."""
     n = x.size(0)
-    ei, norm = gcn_norm(edge_index, edge_weight, n)
+    ei, norm = gcn_norm(edge_index, edge_weight, n, dtype=x.dtype)   # float64 = conditioning probe
     h = x @ weight
     out = spmm_coo_edge_order(ei, norm, h, n)
     if bias is not None:

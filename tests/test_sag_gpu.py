@@ -124,7 +124,9 @@ def test_topk_bit_exact(cuda, ratio, shape, G):
     score = torch.randn(n, generator=g)
     score[::5] = score[0]; score[1::11] = 0.25            # heavy ties
     score[2] = float("nan"); score[7] = float("nan")
-    score[4] = -0.0; score[9] = 0.0; score[10] = float("inf"); score[12] = float("-inf")
+    score[4] = -0.0; score[9] = 0.0; score[10] = float("inf")
+    # (-inf is left out here: PyG pads its dense [G, max_n] table with finfo.min, so a real -inf
+    #  score sorts BEHIND the padding upstream -- see test_topk_minus_inf for our behaviour)
     ref = R.topk(score, ratio, batch)
     gptr = ops.batch_to_ptr(batch.to(cuda), G)
     assert torch.equal(gptr.cpu(), torch.from_numpy(ptr))
@@ -238,34 +240,80 @@ def test_triplet_fwd_bwd(cuda):
 
 
 # ------------------------------------------------------------------ end to end
+def test_topk_minus_inf(cuda):
+    """-inf scores sort last (the brute-force total order); upstream PyG is undefined here."""
+    from tsg import ops
+    batch = torch.repeat_interleave(torch.arange(3), torch.tensor([5, 4, 6]))
+    score = torch.tensor([1., float("-inf"), 3., float("-inf"), 2.,  0., 1., float("-inf"), -1.,
+                          float("-inf"), 5., float("nan"), 4., 3., 2.])
+    gptr = ops.batch_to_ptr(batch.to(cuda), 3)
+    kptr = ops.topk_sizes(gptr, 1.0)
+    perm = ops.topk(score.to(cuda), gptr, kptr, int(kptr[-1]))
+    assert torch.equal(perm.cpu(), R.topk_loops(score, 1.0, batch))
+
+
+def _sag_case(shape, G, nhid, C=16):
+    x, ei, batch, ptr = _batch(shape, G, seed=777)
+    params = R.init_sag_params(x.size(1), nhid, C, seed=777)
+    return x, ei, batch, ptr, params
+
+
 @pytest.mark.parametrize("shape,G,nhid", [("PROTEINS", 24, 32), ("DD", 8, 32), ("DD", 6, 128)])
 def test_packed_sag_net_matches_oracle(cuda, shape, G, nhid):
     """Whole Net forward + backward on a packed batch vs the oracle: same perms / filtered edges at
-    every level (bit-exact), embeddings, loss and every parameter gradient within 1e-5."""
+    every level (bit-exact), scores, embeddings and every parameter gradient within 1e-5.  The
+    backward is driven by a random cotangent on the embeddings (a well-conditioned functional; the
+    triplet hinge at random init is not -- see test_packed_triplet_step)."""
     from tsg import nn as tnn
-    x, ei, batch, ptr = _batch(shape, G, seed=777)
     C = 16
-    params = R.init_sag_params(x.size(1), nhid, C, seed=777)
+    x, ei, batch, ptr, params = _sag_case(shape, G, nhid, C)
     po = {k: v.clone().requires_grad_(True) for k, v in params.items()}
-    trip = torch.from_numpy(synth.sample_triplets(np.arange(G) % 2, G, seed=1))
+    cot = torch.randn(G, C, generator=torch.Generator().manual_seed(5))
     emb_o, aux_o = R.sag_net_forward(po, x, ei, batch, 0.5, return_aux=True)
-    loss_o, _, _ = R.triplet_margin_loss(emb_o[trip[:, 0]], emb_o[trip[:, 1]], emb_o[trip[:, 2]], 1.5)
-    loss_o.backward()
+    (emb_o * cot).sum().backward()
 
     net = tnn.PackedSAGNet(x.size(1), nhid, C, 0.5, 0.5).to(cuda)
-    net.load_state_dict({k: v for k, v in params.items()})
+    net.load_state_dict(params)
     net.eval()                                   # dropout off (oracle runs without a mask)
     emb_g, aux_g = net(x.to(cuda), ei.to(cuda), ptr, return_aux=True)
-    loss_g, _, _ = __import__("tsg.ops", fromlist=["x"]).triplet_loss(emb_g, trip.to(cuda), 1.5)
-    loss_g.backward()
+    (emb_g * cot.to(cuda)).sum().backward()
     for lvl in range(3):
         assert torch.equal(aux_g["perm"][lvl].cpu(), aux_o["perm"][lvl]), f"perm differs at level {lvl}"
         assert torch.equal(aux_g["edges"][lvl].edge_index().cpu(), aux_o["edge_index"][lvl])
         assert rel_err(aux_g["score"][lvl], aux_o["score"][lvl]) <= TOL
     assert rel_err(emb_g, emb_o) <= TOL
-    assert rel_err(loss_g, loss_o) <= TOL
     for k, p in net.named_parameters():
-        assert rel_err(p.grad, po[k].grad) <= 2e-5, k
+        assert rel_err(p.grad, po[k].grad) <= TOL, (k, rel_err(p.grad, po[k].grad))
+
+
+def test_packed_triplet_step(cuda):
+    """One 2stg step (triplet hinge over packed embeddings).  At random init all graphs embed to
+    nearly the same log-softmax vector, so d_p ~ d_n and the hinge gradient is a difference of
+    nearly equal unit vectors: the REFERENCE's own fp32 arithmetic is only accurate to ~1e-3 there
+    (measured against the float64 run of the same oracle).  The gate is therefore: loss within
+    1e-5, and every gradient at least as close to the float64 result as 3x the fp32 oracle is."""
+    from tsg import nn as tnn, ops
+    G, nhid, C = 8, 32, 16
+    x, ei, batch, ptr, params = _sag_case("DD", G, nhid, C)
+    trip = torch.from_numpy(synth.sample_triplets(np.arange(G) % 2, G, seed=1))
+
+    def oracle(dtype):
+        po = {k: v.clone().to(dtype).requires_grad_(True) for k, v in params.items()}
+        emb = R.sag_net_forward(po, x.to(dtype), ei, batch, 0.5)
+        loss, _, _ = R.triplet_margin_loss(emb[trip[:, 0]], emb[trip[:, 1]], emb[trip[:, 2]], 1.5)
+        loss.backward()
+        return loss, po
+    l32, p32 = oracle(torch.float32)
+    l64, p64 = oracle(torch.float64)
+    net = tnn.PackedSAGNet(x.size(1), nhid, C, 0.5, 0.5).to(cuda)
+    net.load_state_dict(params); net.eval()
+    tn = tnn.PackedTripletNet(net, 1.5)
+    loss, dp, dn, emb = tn(x.to(cuda), ei.to(cuda), ptr, trip.to(cuda))
+    loss.backward()
+    assert rel_err(loss, l32) <= TOL
+    for k, p in net.named_parameters():
+        noise = rel_err(p32[k].grad, p64[k].grad)
+        assert rel_err(p.grad, p64[k].grad) <= max(TOL, 3 * noise), (k, noise)
 
 
 def test_full_size_properties(cuda):

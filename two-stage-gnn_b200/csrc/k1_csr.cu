@@ -155,7 +155,7 @@ extern "C" size_t tsg_csr_build_workspace_bytes(int64_t E, int64_t N) {
   size_t b = 0;
   b += 5 * ws_bytes((size_t)N + 1, 4);      // cnt_dst, cnt_src, fill_dst, fill_src, loop_eid
   b += ws_bytes((size_t)N + 1, 4);          // dis
-  b += 2 * ws_bytes((size_t)E + 1, 4);      // tmp_dst, tmp_src
+  b += 2 * ws_bytes((size_t)E + (size_t)N + 1, 4);   // tmp_dst, tmp_src (indexed by rowptr slots)
   b += 2 * ws_bytes((size_t)E + (size_t)N + 1, 4);   // eid scratch when caller passes NULL eid
   b += ws_bytes(scan_ws_ints(N), 4);
   return b + 1024;
@@ -185,8 +185,8 @@ extern "C" int tsg_csr_build(const int64_t* row, const int64_t* col, const float
   int* fill_src = ws.take<int>(N + 1);
   int* loop_eid = ws.take<int>(N + 1);
   float* dis = ws.take<float>(N + 1);
-  int* tmp_dst = ws.take<int>(E + 1);
-  int* tmp_src = ws.take<int>(E + 1);
+  int* tmp_dst = ws.take<int>(E + N + 1);
+  int* tmp_src = ws.take<int>(E + N + 1);
   int* eid_s = ws.take<int>(E + N + 1);
   int* t_eid_s = ws.take<int>(E + N + 1);
   int* scan_ws = ws.take<int>(scan_ws_ints(N));
