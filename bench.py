@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py -- train graphs/sec (fwd+bwd+Adam) of the SAGPool 2stg step on synthetic DD-shape graphs.
+
+Workload (BASELINE.json configs[1]): Code/sag `Net(89, nhid=32, final_dim=32, ratio=0.5, dropout=0.5)`
+(the run_examples.txt command), 2stg triplet step over the 1,168-graph DD-shape corpus: every graph is
+the anchor of one triplet, so one step = 1,168 triplets = 3,504 graph forward+backward passes packed
+into ONE block-diagonal batch (~0.94 M nodes, ~4.7 M directed edges), then MarginRankingLoss(1.5),
+backward, Adam step.  Per rank (weak scaling): each rank owns its own corpus shard and step batch;
+embeddings are all-gathered for the loss and gradients all-reduced (NCCL).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          our arm
+  python bench.py --impl reference ...                         reference CPU arm (oracle port, B=1)
+
+One JSON line on stdout (rank 0).  `value` = graphs/s with inputs resident in HBM; `e2e` = same step
+through TripletTrainer.step_from_host with pinned HOST buffers (H2D of x / edge_index / triplets and
+the loss read back inside the timed region); `roofline` = the level-1 GCN aggregation (K2 SpMM)
+timed alone with CUDA events, algorithmic bytes / measured HBM peak; `cpu_baseline` = the oracle
+port of the reference path timed on this box's host cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "two-stage-gnn_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+METRIC = "train graphs/sec (fwd+bwd)"
+UNIT = "graphs/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="tsg", choices=["tsg", "reference"])
+    ap.add_argument("--corpus", type=int, default=1168, help="graphs in the DD-shape corpus (per rank)")
+    ap.add_argument("--triplets", type=int, default=1168, help="triplets per step (per rank)")
+    ap.add_argument("--nhid", type=int, default=32)
+    ap.add_argument("--final-dim", type=int, default=32)
+    ap.add_argument("--ref-triplets", type=int, default=8, help="triplets per reference-arm step")
+    ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--breakdown", action="store_true", help="print per-entry-point device time shares to stderr")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"SAGPool 2stg triplet step, DD-shape corpus {a.corpus} graphs, {a.triplets} triplets/step "
+            f"(3x{a.triplets} graphs packed), Net(89,{a.nhid},{a.final_dim},ratio 0.5,dropout 0.5)")
+
+
+# ------------------------------------------------------------------------------------------ data
+def make_step_batches(a, rank: int, num_batches: int):
+    from tsg import synth
+    corpus = synth.make_corpus("DD", a.corpus, seed=777 + 1_000_003 * rank)
+    out = []
+    for b in range(num_batches):
+        trip = synth.sample_triplets(corpus.y, a.triplets, seed=1000 * rank + b)
+        ids = np.concatenate([trip[:, 0], trip[:, 1], trip[:, 2]])
+        pk = synth.pack(corpus, ids)
+        T = a.triplets
+        tidx = np.stack([np.arange(T), T + np.arange(T), 2 * T + np.arange(T)], 1).astype(np.int64)
+        out.append(dict(x=torch.from_numpy(pk["x"]).pin_memory(),
+                        edge_index=torch.from_numpy(pk["edge_index"]).pin_memory(),
+                        node_ptr=pk["node_ptr"], triplets=torch.from_numpy(tidx).pin_memory()))
+    return corpus, out
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler(threading.Thread):
+    def __init__(self, index: int, period: float = 0.2):
+        super().__init__(daemon=True)
+        self.index, self.period, self.samples, self.reasons, self.max_mhz = index, period, [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    NAMES = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+             0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+             0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def run(self):
+        if not self.ok:
+            return
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(int(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+                r = int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                for bit, name in self.NAMES.items():
+                    if r & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop_evt.wait(self.period)
+
+    def finish(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons)}
+
+
+# ------------------------------------------------------------------------------------------ CPU reference
+class CpuReference:
+    """The reference's stage-1 loop (Code/sag/train_triplet.py:203-214) on the host cores through the
+    oracle port: per triplet three SINGLE-graph forwards (the scripts' effective batch size),
+    pairwise distances, MarginRankingLoss, backward, Adam step."""
+
+    def __init__(self, a, n_graphs: int = 64):
+        from oracle import pyg_ref as R
+        from tsg import synth
+        self.R, self.a = R, a
+        torch.set_num_threads(os.cpu_count() or 1)
+        n_graphs = min(a.corpus, n_graphs)
+        corpus = synth.make_corpus("DD", n_graphs, seed=777)
+        self.graphs = []
+        for g in range(n_graphs):
+            pk = synth.pack(corpus, [g])
+            self.graphs.append((torch.from_numpy(pk["x"]), torch.from_numpy(pk["edge_index"]),
+                                torch.zeros(pk["x"].shape[0], dtype=torch.long)))
+        self.trip = synth.sample_triplets(corpus.y, 4096, seed=0)
+        self.params = {k: v.clone().requires_grad_(True)
+                       for k, v in R.init_sag_params(corpus.num_node_labels, a.nhid, a.final_dim, 777).items()}
+        self.opt = torch.optim.Adam(list(self.params.values()), lr=5e-4, weight_decay=1e-4)
+        self.gen = torch.Generator().manual_seed(0)
+        self.t = 0
+
+    def triplet(self):
+        R, a = self.R, self.a
+        embs = []
+        for gid in self.trip[self.t % len(self.trip)]:
+            x, ei, batch = self.graphs[int(gid)]
+            mask = (torch.rand(1, a.nhid, generator=self.gen) >= 0.5).float() * 2.0     # dropout p=0.5
+            embs.append(R.sag_net_forward(self.params, x, ei, batch, 0.5, dropout_mask=mask))
+        loss, _, _ = R.triplet_margin_loss(embs[0], embs[1], embs[2], 1.5)
+        self.opt.zero_grad(); loss.backward(); self.opt.step()
+        self.t += 1
+
+    def rate(self, seconds: float, max_triplets: int):
+        self.triplet()   # warm-up
+        done, t0 = 0, time.perf_counter()
+        while done < max_triplets and (time.perf_counter() - t0) < seconds:
+            self.triplet(); done += 1
+        el = time.perf_counter() - t0
+        return 3 * done / el, 3 * done, el
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    ref = CpuReference(a)
+    for _ in range(max(a.warmup, 0)):
+        ref.triplet()
+    t0 = time.perf_counter()
+    for s in range(a.steps):
+        for _ in range(a.ref_triplets):
+            ref.triplet()
+    el = time.perf_counter() - t0
+    graphs = 3 * a.ref_triplets * a.steps
+    rate = graphs / el
+    sample = (f"{a.ref_triplets} triplets/step x 3 single-graph forwards (B=1 as shipped), DD-shape, oracle port "
+              f"of PyG ops under torch CPU, {cores} threads")
+    line = {"metric": METRIC, "value": rate, "unit": UNIT, "impl": "reference", "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": 1000 * el / max(a.steps, 1), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(a), "reference_step": sample},
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+        return
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: tsg has no CPU path")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from tsg import _lib, nn as tnn, ops
+    from tsg.train import TripletTrainer
+    assert _lib.lib.tsg_check_device() == 0, _lib.last_error()
+
+    corpus, batches = make_step_batches(a, rank, num_batches=2)
+    dev_batches = [dict(x=b["x"].to(dev), edge_index=b["edge_index"].to(dev), node_ptr=b["node_ptr"],
+                        triplets=b["triplets"].to(dev)) for b in batches]
+    torch.manual_seed(777)
+    model = tnn.PackedSAGNet(corpus.num_node_labels, a.nhid, a.final_dim, 0.5, 0.5).to(dev)
+    if world > 1:
+        for p in model.parameters():
+            dist.broadcast(p.data, 0)
+    trainer = TripletTrainer(model, lr=5e-4, weight_decay=1e-4, margin=1.5)
+    graphs_per_step = 3 * a.triplets
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for i in range(steps):
+            fn(i)
+        e.record()
+        barrier()
+        ms = torch.tensor([s.elapsed_time(e)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def step_resident(i):
+        b = dev_batches[i % len(dev_batches)]
+        trainer.step(b["x"], b["edge_index"], b["node_ptr"], b["triplets"])
+
+    def step_e2e(i):
+        b = batches[i % len(batches)]
+        trainer.step_from_host(b["x"], b["edge_index"], b["node_ptr"], b["triplets"], dev)
+
+    # ---- device-resident throughput (value)
+    for i in range(max(a.warmup, 3)):
+        step_resident(i)
+    cvd = [v for v in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if v.strip().isdigit()]
+    sampler = ClockSampler(int(cvd[local_rank]) if local_rank < len(cvd) else local_rank)
+    sampler.start()
+    k0 = _lib.kernel_launches
+    ms = timed(step_resident, a.steps)
+    launches = _lib.kernel_launches - k0
+    clocks = sampler.finish()
+    value = world * graphs_per_step * a.steps / (ms / 1000.0)
+
+    # ---- end to end with host buffers
+    for i in range(2):
+        step_e2e(i)
+    ms_e2e = timed(step_e2e, a.steps)
+    e2e_val = world * graphs_per_step * a.steps / (ms_e2e / 1000.0)
+    b0 = batches[0]
+    h2d = b0["x"].numel() * 4 + b0["edge_index"].numel() * 8 + b0["triplets"].numel() * 8 + 4 * 8 * (graphs_per_step + 1)
+
+    # ---- roofline of the dominant kernel: level-1 aggregation (K2 SpMM, F = nhid), timed alone
+    b = dev_batches[0]
+    N = int(b["node_ptr"][-1]); E = int(b["edge_index"].size(1)); Fh = a.nhid
+    csr = ops.build_csr(ops.EdgeList.from_edge_index(b["edge_index"]), N)
+    H = torch.randn(N, Fh, device=dev)
+    bias = torch.zeros(Fh, device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
+    durs = []
+    for it in range(3 + 10):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        ops.spmm_raw(csr.rowptr, csr.colidx, csr.val, H, bias, relu=True)
+        e.record()
+        torch.cuda.synchronize()
+        if it >= 3:
+            durs.append(s.elapsed_time(e))
+    nnz = E + N
+    alg_bytes = 4 * (N * Fh + N * Fh) + 4 * (N + 1) + 8 * nnz       # H once, Y once, CSR once
+    spmm_ms = sum(durs) / len(durs)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = alg_bytes / (spmm_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": f"k_spmm_vec4 (level-1 GCN aggregation, N={N}, nnz={nnz}, F={Fh})",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
+                "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": spmm_ms, "traffic": None}
+
+    # ---- optional per-entry-point breakdown (device time shares; not part of any reported number)
+    if a.breakdown and rank == 0:
+        _lib.profile = {}
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(); step_resident(0); e.record(); torch.cuda.synchronize()
+        total = s.elapsed_time(e)
+        rows = sorted(((sum(x.elapsed_time(y) for x, y in v), k, len(v)) for k, v in _lib.profile.items()), reverse=True)
+        _lib.profile = None
+        print(f"[breakdown] one step {total:.3f} ms", file=sys.stderr)
+        for t, k, n in rows:
+            print(f"[breakdown] {k:28s} calls={n:3d} {t:8.3f} ms  {100 * t / total:5.1f}%", file=sys.stderr)
+
+    # ---- CPU baseline (rank 0, N=1 only)
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        rate, g, el = CpuReference(a).rate(a.cpu_baseline_seconds, 10_000)
+        cpu_baseline = {"value": rate, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                        "sample": f"{g} single-graph fwd+bwd ({g // 3} triplets, B=1 as shipped, Adam step each) in {el:.1f} s"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+                "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload_name(a), "graphs_per_step_per_gpu": graphs_per_step,
+                           "nodes_per_step": N, "directed_edges_per_step": E,
+                           "l2_policy": "inputs larger than L2 (x alone is %.0f MB), 2 alternating batches" % (N * corpus.num_node_labels * 4 / 1e6),
+                           "parallelism": f"dp{world}: shard by graph, all-gather embeddings, all-reduce grads"},
+                "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": ms_e2e / a.steps,
+                        "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+                "cpu_baseline": cpu_baseline}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

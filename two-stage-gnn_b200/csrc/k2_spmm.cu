@@ -29,9 +29,12 @@ k_spmm_vec4(const int* __restrict__ rowptr, const int* __restrict__ colidx,
             const float4* __restrict__ bias, float4* __restrict__ Y,
             int num_rows, int F4, int relu) {
   const int lane_in_row = threadIdx.x % LPR;
-  const int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
-  const int64_t num_groups = ((int64_t)gridDim.x * blockDim.x) / LPR;
-  for (int64_t r = group; r < num_rows; r += num_groups) {
+  // blocked assignment: CTA b owns rows [b*rpc, (b+1)*rpc) so the rows of one small graph (whose
+  // neighbours are each other) are gathered through the same SM's L1
+  const int rpc = (num_rows + gridDim.x - 1) / gridDim.x;
+  const int r_begin = blockIdx.x * rpc;
+  const int r_end = min(num_rows, r_begin + rpc);
+  for (int r = r_begin + threadIdx.x / LPR; r < r_end; r += SPMM_THREADS / LPR) {
     const int s = __ldg(rowptr + r), t = __ldg(rowptr + r + 1);
     for (int f = lane_in_row; f < F4; f += LPR) {
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -81,9 +84,12 @@ k_spmm_scalar(const int* __restrict__ rowptr, const int* __restrict__ colidx,
               const float* __restrict__ bias, float* __restrict__ Y,
               int num_rows, int F, int relu) {
   const int lane_in_row = threadIdx.x % LPR;
-  const int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
-  const int64_t num_groups = ((int64_t)gridDim.x * blockDim.x) / LPR;
-  for (int64_t r = group; r < num_rows; r += num_groups) {
+  // blocked assignment: CTA b owns rows [b*rpc, (b+1)*rpc) so the rows of one small graph (whose
+  // neighbours are each other) are gathered through the same SM's L1
+  const int rpc = (num_rows + gridDim.x - 1) / gridDim.x;
+  const int r_begin = blockIdx.x * rpc;
+  const int r_end = min(num_rows, r_begin + rpc);
+  for (int r = r_begin + threadIdx.x / LPR; r < r_end; r += SPMM_THREADS / LPR) {
     const int s = __ldg(rowptr + r), t = __ldg(rowptr + r + 1);
     for (int f = lane_in_row; f < F; f += LPR) {
       float acc = 0.f;

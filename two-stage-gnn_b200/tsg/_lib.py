@@ -58,8 +58,16 @@ for _name, (_res, _args) in _PROTOTYPES.items():
 if lib.tsg_abi_version() != 1:
     raise ImportError(f"libtsg ABI version {lib.tsg_abi_version()} != 1")
 
-# number of libtsg entry points that enqueue GPU work, counted since import (bench.py reports it)
-launch_calls = 0
+# kernels each entry point enqueues (memsets not counted); bench.py reports the sum as gpu_launches
+KERNELS_PER_CALL = {
+    "tsg_csr_build": 12, "tsg_spmm": 1, "tsg_relu_bwd_colsum": 2, "tsg_topk_sizes": 3, "tsg_topk": 1,
+    "tsg_batch_to_ptr": 1, "tsg_filter_adj": 7, "tsg_gate_gather_fwd": 1, "tsg_gate_gather_bwd": 1,
+    "tsg_readout_fwd": 1, "tsg_readout_bwd": 1, "tsg_triplet_fwd": 2, "tsg_triplet_bwd": 9,
+    "tsg_pairdist_matrix": 1,
+}
+launch_calls = 0        # libtsg entry points called since import
+kernel_launches = 0     # kernels enqueued by them
+profile = None          # set to {} to record (start, end) CUDA events per entry point
 
 
 def last_error() -> str:
@@ -82,9 +90,17 @@ def stream_ptr() -> int:
 
 
 def call(name: str, *args) -> None:
-    global launch_calls
-    rc = getattr(lib, name)(*args)
+    global launch_calls, kernel_launches
+    if profile is not None:
+        s = torch.cuda.Event(enable_timing=True); e = torch.cuda.Event(enable_timing=True)
+        s.record()
+        rc = getattr(lib, name)(*args)
+        e.record()
+        profile.setdefault(name, []).append((s, e))
+    else:
+        rc = getattr(lib, name)(*args)
     launch_calls += 1
+    kernel_launches += KERNELS_PER_CALL.get(name, 1)
     if rc != 0:
         raise RuntimeError(f"{name} failed ({rc}): {last_error()}")
 

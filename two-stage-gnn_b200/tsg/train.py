@@ -1,0 +1,98 @@
+"""2stg training step over packed batches: the public call a user of this framework makes.
+
+Mirrors the loop of Code/sag/train_triplet.py:198-214 (TNet forward -> MarginRankingLoss ->
+backward -> Adam step) with two differences that are the point of this framework: the step runs
+ONE packed forward over all 3T graphs of T triplets instead of 3 single-graph forwards per
+triplet, and it is data-parallel: every rank embeds its own graphs, embeddings are all-gathered
+(NCCL) so the triplet loss sees the global batch, parameter gradients are all-reduced in one flat
+bucket.  Graphs are independent, so there is no other exchange step.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+
+class _AllGatherRows(torch.autograd.Function):
+    """emb_local [M, D] -> emb_global [world*M, D].  Every rank evaluates the SAME global loss on
+    the gathered matrix, so d(loss)/d(emb_global) is complete on every rank and the backward is a
+    slice (no reduce-scatter needed)."""
+
+    @staticmethod
+    def forward(ctx, emb, group):
+        world = dist.get_world_size(group)
+        ctx.rank, ctx.m = dist.get_rank(group), emb.size(0)
+        out = torch.empty(world * emb.size(0), emb.size(1), dtype=emb.dtype, device=emb.device)
+        dist.all_gather_into_tensor(out, emb.contiguous(), group=group)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g[ctx.rank * ctx.m:(ctx.rank + 1) * ctx.m].contiguous(), None
+
+
+def all_gather_rows(emb: torch.Tensor, group=None) -> torch.Tensor:
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return emb
+    return _AllGatherRows.apply(emb, group)
+
+
+def all_reduce_grads(params, group=None) -> None:
+    """One flat-bucket all-reduce(SUM) of every parameter gradient (33-361 KB: latency bound)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    off = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[off:off + n].view_as(g)); off += n
+
+
+class TripletTrainer:
+    """model: tsg.nn.PackedSAGNet (or any module with the same forward signature)."""
+
+    def __init__(self, model: torch.nn.Module, lr: float = 5e-4, weight_decay: float = 1e-4,
+                 margin: float = 1.5, group=None):
+        self.model, self.margin, self.group = model, margin, group
+        # Code/sag/train_triplet.py:191
+        self.opt = torch.optim.Adam(model.parameters(), lr=lr, weight_decay=weight_decay)
+
+    def step(self, x: torch.Tensor, edge_index: torch.Tensor, node_ptr_host: np.ndarray,
+             triplets: torch.Tensor) -> torch.Tensor:
+        """x/edge_index/triplets on the device.  `triplets` [T,3] index rows of THIS rank's
+        embedding matrix; with world > 1 they are offset into the gathered matrix and every rank's
+        triplets are gathered too, so the loss is the mean over the global batch."""
+        self.model.train()
+        emb = self.model(x, edge_index, node_ptr_host)
+        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        if world > 1:
+            rank = dist.get_rank(self.group)
+            emb_all = all_gather_rows(emb, self.group)
+            trip_local = (triplets + rank * emb.size(0)).contiguous()
+            trip_all = torch.empty(world * triplets.size(0), 3, dtype=triplets.dtype, device=triplets.device)
+            dist.all_gather_into_tensor(trip_all, trip_local, group=self.group)
+        else:
+            emb_all, trip_all = emb, triplets
+        loss, _, _ = ops.triplet_loss(emb_all, trip_all, self.margin)
+        self.opt.zero_grad(set_to_none=True)
+        loss.backward()
+        all_reduce_grads(list(self.model.parameters()), self.group)
+        self.opt.step()
+        return loss.detach()
+
+    def step_from_host(self, x_host: torch.Tensor, edge_index_host: torch.Tensor,
+                       node_ptr_host: np.ndarray, triplets_host: torch.Tensor, device) -> float:
+        """End-to-end call with (pinned) HOST buffers: H2D copies, the step, and the loss read back."""
+        x = x_host.to(device, non_blocking=True)
+        ei = edge_index_host.to(device, non_blocking=True)
+        tr = triplets_host.to(device, non_blocking=True)
+        return float(self.step(x, ei, node_ptr_host, tr).item())
