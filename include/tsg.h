@@ -94,6 +94,53 @@ int tsg_relu_bwd_colsum(const float* dY, const float* Y /*nullable*/, float* dY_
                         void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * K3  tall-skinny row-local dense products (N ~ 10^6 rows, K and M <= 128 columns), fp32 FFMA,
+ *     exact zeros of X skipped (one-hot node-label features).
+ *   tsg_linear_fwd: Y = epilogue(X[N,K] . Wop + bias), Wop = W[K,M] (w_transposed=0) or W[M,K]^T.
+ *     replaces `x @ weight` of PyG GCNConv (Code/sag/network.py:34) and, with the epilogue flags,
+ *     `torch.matmul(y, self.weight) + self.bias` -> F.normalize(dim=2) (Code/sage+gat+diffpool/
+ *     encoders.py:36-40) -> self.act (ReLU, :177) -> apply_bn (:134-138: fresh BatchNorm1d(N) =
+ *     per-node statistics over the feature axis, biased variance, eps 1e-5, no affine).
+ *     The input gradient dX = dY . W^T is the same call with w_transposed=1.
+ *   tsg_dense_epilogue_bwd: dU (gradient at X.W+b) from dO, recomputing the forward from X.
+ *   tsg_linear_bwd_weight: dW[K,M] = X^T . dY and db[M] = colsum(dY), deterministic two-stage.
+ * ------------------------------------------------------------------------------------------ */
+#define TSG_LIN_NORMALIZE 1
+#define TSG_LIN_RELU 2
+#define TSG_LIN_NODEBN 4
+int tsg_linear_fwd(const float* X, const float* W, const float* bias /*nullable*/, float* Y,
+                   int64_t num_rows, int64_t in_feat, int64_t out_feat, int w_transposed, int flags,
+                   void* stream);
+int tsg_dense_epilogue_bwd(const float* X, const float* W, const float* bias /*nullable*/,
+                           const float* dO, float* dU, int64_t num_rows, int64_t in_feat,
+                           int64_t out_feat, int flags, void* stream);
+size_t tsg_linear_bwd_weight_workspace_bytes(int64_t in_feat, int64_t out_feat);
+int tsg_linear_bwd_weight(const float* X, const float* dY, float* dW /*nullable*/,
+                          float* db /*nullable*/, int64_t num_rows, int64_t in_feat, int64_t out_feat,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Dense wire-format adapters (dense directories)
+ *   tsg_dense_to_coo: non-zeros of zero-padded dense matrices M[B,R,C] (adjacency
+ *     Code/sage+gat+diffpool/cross_val.py:163-184; pooled adjacency / eigen-pooling operators
+ *     Code/eigengcn/graph_sampler.py:185-241) in row-major order as COO triplets
+ *     (row_off[b] + r, col_off[b] + c, M[b,r,c]) for r < nrows[b], c < ncols[b]; feed to
+ *     tsg_csr_build(TSG_CSR_RAW).  capacity >= number of non-zeros; count returned on the device.
+ *   tsg_nodebn_{fwd,bwd}: `apply_bn` (encoders.py:134-138) on x[B,N,F]: statistics per node over
+ *     (B,F), biased variance, eps 1e-5, no affine.  fwd also returns mean[N], rstd[N].
+ * ------------------------------------------------------------------------------------------ */
+size_t tsg_dense_to_coo_workspace_bytes(int64_t B, int64_t R);
+int tsg_dense_to_coo(const float* M, int64_t B, int64_t R, int64_t C,
+                     const int64_t* nrows, const int64_t* ncols,
+                     const int64_t* row_off, const int64_t* col_off,
+                     int64_t* out_r, int64_t* out_c, float* out_w, int64_t capacity,
+                     int64_t* out_count_dev, void* workspace, size_t workspace_bytes, void* stream);
+int tsg_nodebn_fwd(const float* x, float* y, float* mean, float* rstd,
+                   int64_t B, int64_t N, int64_t F, void* stream);
+int tsg_nodebn_bwd(const float* dy, const float* y, const float* rstd, float* dx,
+                   int64_t B, int64_t N, int64_t F, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * K5a  per-graph top-k (deterministic: descending score, ties -> lower node id, NaN first)
  *   replaces: PyG topk_pool.topk as called from Code/sag/layers.py:20.
  *   graph_ptr[G+1] are node offsets of the (sorted) batch vector; k_g = ceil(ratio * n_g) in

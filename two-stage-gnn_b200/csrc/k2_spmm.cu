@@ -14,8 +14,6 @@
 //     independent of the launch geometry; loads are issued 4 neighbours ahead for MLP;
 //   * neighbours of a row live in the same small graph block, so the gathers hit L1/L2 and DRAM
 //     sees ~compulsory traffic (H once, Y once, CSR once);
-//   * rows with more than HUB_DEG entries are split across the 32 lanes of a warp (warp per
-//     segment) in a second pass and combined in a fixed order.
 #include "common.cuh"
 
 namespace tsg {
@@ -187,14 +185,6 @@ k_relu_bwd_colsum(const float* __restrict__ dY, const float* __restrict__ Y, flo
   }
 }
 
-__global__ void k_colsum_final(const float* __restrict__ part, float* __restrict__ out, int nb, int F) {
-  int f = blockIdx.x * blockDim.x + threadIdx.x;
-  if (f >= F) return;
-  float s = 0.f;
-  for (int b = 0; b < nb; ++b) s += part[(int64_t)b * F + f];
-  out[f] = s;
-}
-
 }  // namespace tsg
 
 using namespace tsg;
@@ -233,6 +223,6 @@ extern "C" int tsg_relu_bwd_colsum(const float* dY, const float* Y, float* dYm, 
   int nb = colsum_blocks(N);
   int64_t rpb = (N + nb - 1) / nb; if (rpb < 1) rpb = 1;
   k_relu_bwd_colsum<<<nb, CS_THREADS, CS_THREADS * sizeof(float), st>>>(dY, Y, dYm, part, N, (int)F, rpb);
-  k_colsum_final<<<(int)((F + 127) / 128), 128, 0, st>>>(part, dbias, nb, (int)F);
+  launch_partial_sum_final(part, dbias, (int)F, nullptr, nb, (int)F, st);
   return check_launch("relu_bwd_colsum");
 }

@@ -26,6 +26,14 @@ _PROTOTYPES = {
     "tsg_spmm": (I, [P, P, P, P, P, P, I64, I64, I, P]),
     "tsg_colsum_workspace_bytes": (SZ, [I64, I64]),
     "tsg_relu_bwd_colsum": (I, [P, P, P, P, I64, I64, P, SZ, P]),
+    "tsg_linear_fwd": (I, [P, P, P, P, I64, I64, I64, I, I, P]),
+    "tsg_dense_epilogue_bwd": (I, [P, P, P, P, P, I64, I64, I64, I, P]),
+    "tsg_linear_bwd_weight_workspace_bytes": (SZ, [I64, I64]),
+    "tsg_linear_bwd_weight": (I, [P, P, P, P, I64, I64, I64, P, SZ, P]),
+    "tsg_dense_to_coo_workspace_bytes": (SZ, [I64, I64]),
+    "tsg_dense_to_coo": (I, [P, I64, I64, I64, P, P, P, P, P, P, P, I64, P, P, SZ, P]),
+    "tsg_nodebn_fwd": (I, [P, P, P, P, I64, I64, I64, P]),
+    "tsg_nodebn_bwd": (I, [P, P, P, P, I64, I64, I64, P]),
     "tsg_topk_workspace_bytes": (SZ, [I64, I64]),
     "tsg_topk_sizes": (I, [P, I64, F32, P, P, SZ, P]),
     "tsg_topk": (I, [P, P, P, I64, I64, P, P, SZ, P]),
@@ -63,7 +71,8 @@ KERNELS_PER_CALL = {
     "tsg_csr_build": 12, "tsg_spmm": 1, "tsg_relu_bwd_colsum": 2, "tsg_topk_sizes": 3, "tsg_topk": 1,
     "tsg_batch_to_ptr": 1, "tsg_filter_adj": 7, "tsg_gate_gather_fwd": 1, "tsg_gate_gather_bwd": 1,
     "tsg_readout_fwd": 1, "tsg_readout_bwd": 1, "tsg_triplet_fwd": 2, "tsg_triplet_bwd": 9,
-    "tsg_pairdist_matrix": 1,
+    "tsg_pairdist_matrix": 1, "tsg_linear_fwd": 1, "tsg_dense_epilogue_bwd": 1, "tsg_linear_bwd_weight": 2,
+    "tsg_dense_to_coo": 6, "tsg_nodebn_fwd": 1, "tsg_nodebn_bwd": 1,
 }
 launch_calls = 0        # libtsg entry points called since import
 kernel_launches = 0     # kernels enqueued by them

@@ -18,6 +18,7 @@ from ._lib import call, ptr, stream_ptr, workspace, lib
 CSR_GCN, CSR_RAW = 0, 1
 SPMM_RELU = 1
 READOUT_MAX, READOUT_MEAN, READOUT_SUM = 1, 2, 4
+LIN_NORMALIZE, LIN_RELU, LIN_NODEBN = 1, 2, 4
 
 
 # --------------------------------------------------------------------------------------------
@@ -138,10 +139,67 @@ def spmm(csr: CSR, H: torch.Tensor, bias: Optional[torch.Tensor] = None, relu: b
     return _SpMM.apply(H, bias, csr, relu)
 
 
+# --------------------------------------------------------------------------------------------
+# K3 row-local dense products
+# --------------------------------------------------------------------------------------------
+def linear_raw(x: torch.Tensor, w: torch.Tensor, bias=None, transposed: bool = False, flags: int = 0):
+    x = x.contiguous(); w = w.contiguous()
+    n, k = x.shape
+    m = w.size(0) if transposed else w.size(1)
+    if (w.size(1) if transposed else w.size(0)) != k:
+        raise RuntimeError(f"tsg.linear: shape mismatch x{tuple(x.shape)} w{tuple(w.shape)} T={transposed}")
+    y = torch.empty(n, m, dtype=torch.float32, device=x.device)
+    call("tsg_linear_fwd", ptr(x), ptr(w), ptr(bias), ptr(y), n, k, m, int(transposed), flags, stream_ptr())
+    return y
+
+
+def linear_bwd_weight(x: torch.Tensor, dy: torch.Tensor, want_bias: bool):
+    x = x.contiguous(); dy = dy.contiguous()
+    n, k = x.shape; m = dy.size(1)
+    dw = torch.empty(k, m, dtype=torch.float32, device=x.device)
+    db = torch.empty(m, dtype=torch.float32, device=x.device) if want_bias else None
+    wsb = lib.tsg_linear_bwd_weight_workspace_bytes(k, m)
+    ws = workspace(wsb, x.device)
+    call("tsg_linear_bwd_weight", ptr(x), ptr(dy), ptr(dw), ptr(db), n, k, m, ptr(ws), wsb, stream_ptr())
+    return dw, db
+
+
+class _Linear(torch.autograd.Function):
+    """Y = epilogue(X W + b).  flags = 0: plain product (PyG GCNConv's `x @ weight`);
+    flags = NORMALIZE|RELU|NODEBN: the dense GraphConv epilogue (encoders.py:36-40,177,134-138)."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, flags: int):
+        y = linear_raw(x, w, bias, False, flags)
+        ctx.flags = flags
+        ctx.save_for_backward(x, w, bias)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, bias = ctx.saved_tensors
+        dy = dy.contiguous()
+        if ctx.flags:
+            du = torch.empty_like(dy)
+            n, k = x.shape
+            call("tsg_dense_epilogue_bwd", ptr(x), ptr(w), ptr(bias), ptr(dy), ptr(du), n, k, dy.size(1),
+                 ctx.flags, stream_ptr())
+            dy = du
+        dx = linear_raw(dy, w, None, True) if ctx.needs_input_grad[0] else None
+        dw = db = None
+        if ctx.needs_input_grad[1] or (bias is not None and ctx.needs_input_grad[2]):
+            dw, db = linear_bwd_weight(x, dy, bias is not None)
+        return dx, dw, db, None
+
+
+def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, flags: int = 0):
+    return _Linear.apply(x, w, bias, flags)
+
+
 def gcn_conv(x: torch.Tensor, csr: CSR, weight: torch.Tensor, bias: Optional[torch.Tensor],
              relu: bool = False) -> torch.Tensor:
     """PyG GCNConv.forward (Code/sag/network.py:34): (A_hat (X W)) + b, CSR prebuilt by K1."""
-    return spmm(csr, x @ weight, bias, relu)
+    return spmm(csr, linear(x, weight), bias, relu)
 
 
 # --------------------------------------------------------------------------------------------
