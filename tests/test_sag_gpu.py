@@ -254,6 +254,13 @@ def test_topk_minus_inf(cuda):
 
 def _sag_case(shape, G, nhid, C=16):
     x, ei, batch, ptr = _batch(shape, G, seed=777)
+    if shape == "PROTEINS":
+        # 3 one-hot node labels on ~39-node graphs give many nodes with IDENTICAL receptive fields:
+        # their scores are equal in exact arithmetic and the fp32 tie-break then depends on the
+        # summation order of the dense product (MKL vs any other GEMM, the reference's own CPU vs GPU
+        # runs included).  The bit-exact claim is "same scores in => same perm out" (operator tests
+        # above); the end-to-end comparison needs non-degenerate scores, so use dense random features.
+        x = torch.randn(x.size(0), 8, generator=torch.Generator().manual_seed(777))
     params = R.init_sag_params(x.size(1), nhid, C, seed=777)
     return x, ei, batch, ptr, params
 
