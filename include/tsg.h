@@ -141,6 +141,28 @@ int tsg_nodebn_bwd(const float* dy, const float* y, const float* rstd, float* dx
                    int64_t B, int64_t N, int64_t F, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * K4  dense-GAT head on the packed CSR (all heads of a layer at once)
+ *   replaces DGATHead.forward (Code/sage+gat+diffpool/encoders_GAT.py:29-49):
+ *     e_ij = LeakyReLU(s1_i + s2_j) on edges adj[i,j] > 0, softmax over i for every column j
+ *     (dim=1 of the broadcast [1,N,N] tensor), h'_i = sum_j att_ij h_j.
+ *   h [n, heads*F], s1 = h.a[:F], s2 = h.a[F:] as [n, heads].  (rowptr, colidx, eid) is the
+ *   dst-major CSR (row i lists its columns j), t_* the src-major one (column j lists its rows i);
+ *   both from tsg_csr_build(TSG_CSR_RAW) with eids.  fwd also returns the per-column softmax
+ *   statistics mx, zs [n, heads].  Columns without any edge are not touched (host-side correction).
+ * ------------------------------------------------------------------------------------------ */
+int tsg_gat_fwd(const int32_t* rowptr, const int32_t* colidx, const int32_t* t_rowptr,
+                const int32_t* t_colidx, const float* h, const float* s1, const float* s2,
+                int64_t num_nodes, int64_t heads, int64_t feat, float slope,
+                float* mx, float* zs, float* hp, void* stream);
+size_t tsg_gat_bwd_workspace_bytes(int64_t nnz, int64_t heads);
+int tsg_gat_bwd(const int32_t* rowptr, const int32_t* eid, const int32_t* t_rowptr,
+                const int32_t* t_colidx, const int32_t* t_eid, const float* h, const float* s1,
+                const float* s2, const float* mx, const float* zs, const float* dhp,
+                int64_t num_nodes, int64_t nnz, int64_t heads, int64_t feat, float slope,
+                float* dh, float* ds1, float* ds2,
+                void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * K5a  per-graph top-k (deterministic: descending score, ties -> lower node id, NaN first)
  *   replaces: PyG topk_pool.topk as called from Code/sag/layers.py:20.
  *   graph_ptr[G+1] are node offsets of the (sorted) batch vector; k_g = ceil(ratio * n_g) in

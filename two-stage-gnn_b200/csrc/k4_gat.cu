@@ -1,0 +1,190 @@
+// K4 -- dense-GAT head on the packed CSR: edge score, segmented edge-softmax, weighted aggregation.
+//
+// Replaces DGATHead.forward (Code/sage+gat+diffpool/encoders_GAT.py:29-49), which materialises an
+// [N*N, 2F] tensor (244 MiB per head at N = 1000) to evaluate
+//     e_ij = LeakyReLU(a[:F].h_i + a[F:].h_j)   masked to adj[i,j] > 0,
+//     att  = softmax(e, dim=1)   -- over the ROW index i for every column j (adj [1,N,N] broadcasts),
+//     h'_i = sum_j att_ij h_j.
+// On the CSR only the edges exist: per column j the softmax runs over its in-list (src-major CSR),
+// per row i the aggregation runs over its out-list (dst-major CSR).  Masked entries contribute exactly
+// 0 upstream (exp(-9e15 - max) == 0), so the sparse form is exact for every column that has an edge;
+// columns without any edge (isolated / padded nodes: uniform 1/N upstream) are handled by the host
+// layer as a per-graph correction vector (tsg/gat.py).
+//
+// Forward : k_gat_colstats (per column: max and sum of exp)  +  k_gat_aggregate (per row gather).
+// Backward: k_gat_bwd_col (per column: d_alpha, softmax backward, dh_j, ds2_j, dz per edge in COO
+//           order)  +  k_gat_bwd_row (per row: ds1_i).  Sequential per segment: deterministic, no atomics.
+// HBM-bound gathers; scores are 4-byte scattered reads that stay in L2 (the whole graph block is ~100 KB).
+#include "common.cuh"
+#include <float.h>
+
+namespace tsg {
+
+__device__ __forceinline__ float lrelu(float x, float slope) { return x > 0.f ? x : slope * x; }
+
+// one thread per (column j, head): online max / sum over the column's entries (src-major CSR)
+__global__ void __launch_bounds__(256)
+k_gat_colstats(const int* __restrict__ t_rowptr, const int* __restrict__ t_colidx,
+               const float* __restrict__ s1, const float* __restrict__ s2, int n, int heads, float slope,
+               float* __restrict__ mx, float* __restrict__ zs) {
+  const int64_t total = (int64_t)n * heads;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(idx / heads), hd = (int)(idx - (int64_t)j * heads);
+    const int p0 = t_rowptr[j], p1 = t_rowptr[j + 1];
+    const float sj = s2[idx];
+    float m = -FLT_MAX;
+    for (int p = p0; p < p1; ++p) m = fmaxf(m, lrelu(s1[(int64_t)t_colidx[p] * heads + hd] + sj, slope));
+    float z = 0.f;
+    for (int p = p0; p < p1; ++p) z += expf(lrelu(s1[(int64_t)t_colidx[p] * heads + hd] + sj, slope) - m);
+    mx[idx] = m; zs[idx] = z;
+  }
+}
+
+// LPR lanes per row i, each lane owns columns f = l, l+LPR, ... of the heads*F wide feature row.
+template <int LPR>
+__global__ void __launch_bounds__(256)
+k_gat_aggregate(const int* __restrict__ rowptr, const int* __restrict__ colidx, const float* __restrict__ h,
+                const float* __restrict__ s1, const float* __restrict__ s2, const float* __restrict__ mx,
+                const float* __restrict__ zs, int n, int heads, int F, float slope, float* __restrict__ hp) {
+  const int l = threadIdx.x % LPR;
+  const int W = heads * F;
+  const int rpc = (n + gridDim.x - 1) / gridDim.x;
+  const int r_begin = blockIdx.x * rpc, r_end = min(n, r_begin + rpc);
+  for (int i = r_begin + threadIdx.x / LPR; i < r_end; i += 256 / LPR) {
+    const int p0 = rowptr[i], p1 = rowptr[i + 1];
+    for (int f = l; f < W; f += LPR) {
+      const int hd = f / F;
+      const float si = s1[(int64_t)i * heads + hd];
+      float acc = 0.f;
+      for (int p = p0; p < p1; ++p) {
+        const int j = colidx[p];
+        const int64_t jh = (int64_t)j * heads + hd;
+        const float a = expf(lrelu(si + s2[jh], slope) - mx[jh]) / zs[jh];
+        acc = fmaf(a, h[(int64_t)j * W + f], acc);
+      }
+      hp[(int64_t)i * W + f] = acc;
+    }
+  }
+}
+
+// warp per column j.  Two sweeps over the column's entries; d_alpha kept per (slot, head) in `dal`.
+__global__ void __launch_bounds__(256)
+k_gat_bwd_col(const int* __restrict__ t_rowptr, const int* __restrict__ t_colidx, const int* __restrict__ t_eid,
+              const float* __restrict__ h, const float* __restrict__ s1, const float* __restrict__ s2,
+              const float* __restrict__ mx, const float* __restrict__ zs, const float* __restrict__ dhp,
+              int n, int heads, int F, float slope, float* __restrict__ dal, float* __restrict__ dz_coo,
+              float* __restrict__ dh, float* __restrict__ ds2) {
+  const int lane = threadIdx.x & 31;
+  const int W = heads * F;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t j = warp; j < n; j += nwarps) {
+    const int p0 = t_rowptr[j], p1 = t_rowptr[j + 1];
+    for (int hd = 0; hd < heads; ++hd) {
+      const int64_t jh = j * heads + hd;
+      const float sj = s2[jh], m = mx[jh], z = zs[jh];
+      // sweep 1: d_alpha_ij = dhp_i[hd] . h_j[hd] ;  t = sum_i alpha_ij d_alpha_ij
+      float t = 0.f;
+      for (int p = p0; p < p1; ++p) {
+        const int i = t_colidx[p];
+        float part = 0.f;
+        for (int f = lane; f < F; f += 32) part += dhp[(int64_t)i * W + hd * F + f] * h[j * W + hd * F + f];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        const float a = expf(lrelu(s1[(int64_t)i * heads + hd] + sj, slope) - m) / z;
+        t += a * part;
+        if (lane == 0) dal[(int64_t)p * heads + hd] = part;
+      }
+      __syncwarp();
+      // sweep 2: dz_ij, ds2_j, and the transposed aggregation dh_j += alpha_ij dhp_i
+      float dsum = 0.f;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};          // F <= 128: up to 4 columns per lane
+      for (int p = p0; p < p1; ++p) {
+        const int i = t_colidx[p];
+        const float pre = s1[(int64_t)i * heads + hd] + sj;
+        const float a = expf(lrelu(pre, slope) - m) / z;
+        const float de = a * (dal[(int64_t)p * heads + hd] - t);
+        const float dzv = de * (pre > 0.f ? 1.f : slope);
+        dsum += dzv;
+        if (lane == 0) dz_coo[(int64_t)t_eid[p] * heads + hd] = dzv;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int f = lane + 32 * q;
+          if (f < F) acc[q] = fmaf(a, dhp[(int64_t)i * W + hd * F + f], acc[q]);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int f = lane + 32 * q;
+        if (f < F) dh[j * W + hd * F + f] = acc[q];
+      }
+      if (lane == 0) ds2[jh] = dsum;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_gat_bwd_row(const int* __restrict__ rowptr, const int* __restrict__ eid, const float* __restrict__ dz_coo,
+              int n, int heads, float* __restrict__ ds1) {
+  const int64_t total = (int64_t)n * heads;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(idx / heads), hd = (int)(idx - (int64_t)i * heads);
+    float s = 0.f;
+    for (int p = rowptr[i]; p < rowptr[i + 1]; ++p) s += dz_coo[(int64_t)eid[p] * heads + hd];
+    ds1[idx] = s;
+  }
+}
+
+}  // namespace tsg
+
+using namespace tsg;
+
+extern "C" int tsg_gat_fwd(const int32_t* rowptr, const int32_t* colidx, const int32_t* t_rowptr,
+                           const int32_t* t_colidx, const float* h, const float* s1, const float* s2,
+                           int64_t n, int64_t heads, int64_t F, float slope,
+                           float* mx, float* zs, float* hp, void* stream) {
+  TSG_REQUIRE(n >= 0 && heads > 0 && F > 0, "gat_fwd: bad shape");
+  TSG_REQUIRE(n * heads * F < (int64_t)0x7fffffff, "gat_fwd: too large");
+  if (n == 0) return TSG_OK;
+  TSG_REQUIRE(rowptr && colidx && t_rowptr && t_colidx && h && s1 && s2 && mx && zs && hp, "gat_fwd: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  k_gat_colstats<<<grid_for(n * heads, 256), 256, 0, st>>>(t_rowptr, t_colidx, s1, s2, (int)n, (int)heads, slope, mx, zs);
+  int W = (int)(heads * F);
+  int lpr = 1; while (lpr < W && lpr < 32) lpr <<= 1;
+  int grid = grid_for(n, 256 / lpr, 32);
+#define TSG_GO(L) k_gat_aggregate<L><<<grid, 256, 0, st>>>(rowptr, colidx, h, s1, s2, mx, zs, (int)n, (int)heads, (int)F, slope, hp)
+  switch (lpr) {
+    case 1: TSG_GO(1); break; case 2: TSG_GO(2); break; case 4: TSG_GO(4); break;
+    case 8: TSG_GO(8); break; case 16: TSG_GO(16); break; default: TSG_GO(32); break;
+  }
+#undef TSG_GO
+  return check_launch("gat_fwd");
+}
+
+extern "C" size_t tsg_gat_bwd_workspace_bytes(int64_t nnz, int64_t heads) {
+  return 2 * ws_bytes((size_t)(nnz + 1) * (size_t)heads, 4) + 512;
+}
+
+extern "C" int tsg_gat_bwd(const int32_t* rowptr, const int32_t* eid, const int32_t* t_rowptr,
+                           const int32_t* t_colidx, const int32_t* t_eid, const float* h, const float* s1,
+                           const float* s2, const float* mx, const float* zs, const float* dhp,
+                           int64_t n, int64_t nnz, int64_t heads, int64_t F, float slope,
+                           float* dh, float* ds1, float* ds2,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+  TSG_REQUIRE(n >= 0 && heads > 0 && F > 0 && nnz >= 0, "gat_bwd: bad shape");
+  TSG_REQUIRE(F <= 128, "gat_bwd: per-head width %lld > 128 not supported", (long long)F);
+  if (n == 0) return TSG_OK;
+  TSG_REQUIRE(rowptr && eid && t_rowptr && t_colidx && t_eid && h && s1 && s2 && mx && zs && dhp && dh && ds1 && ds2,
+              "gat_bwd: null pointer");
+  if (workspace_bytes < tsg_gat_bwd_workspace_bytes(nnz, heads)) { set_error("gat_bwd: workspace too small"); return TSG_EWORKSPACE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  Workspace ws(workspace, workspace_bytes);
+  float* dal = ws.take<float>((nnz + 1) * heads);
+  float* dz = ws.take<float>((nnz + 1) * heads);
+  k_gat_bwd_col<<<grid_for(n, 8), 256, 0, st>>>(t_rowptr, t_colidx, t_eid, h, s1, s2, mx, zs, dhp, (int)n, (int)heads,
+                                                (int)F, slope, dal, dz, dh, ds2);
+  k_gat_bwd_row<<<grid_for(n * heads, 256), 256, 0, st>>>(rowptr, eid, dz, (int)n, (int)heads, ds1);
+  return check_launch("gat_bwd");
+}

@@ -33,7 +33,7 @@ from .ops import CSR, CSR_RAW, EdgeList, LIN_NODEBN, LIN_NORMALIZE, LIN_RELU, RE
 # adapters
 # ---------------------------------------------------------------------------------------------
 def dense_to_csr(mat: torch.Tensor, nrows: Sequence[int], ncols: Sequence[int], transpose: bool = False,
-                 packed: bool = True, capacity: Optional[int] = None):
+                 packed: bool = True, capacity: Optional[int] = None, want_eid: bool = False):
     """Zero-padded dense operators M[B,R,C] -> CSR of the block-diagonal packed operator.
 
     transpose=False: y[row_off+r] = sum_c M[r,c] x[col_off+c]      (adjacency: adj @ x)
@@ -67,15 +67,15 @@ def dense_to_csr(mat: torch.Tensor, nrows: Sequence[int], ncols: Sequence[int], 
     else:              # destination = matrix row, source = matrix column
         el = EdgeList(out_c[:nnz].contiguous(), out_r[:nnz].contiguous(), nnz)
         n_out, n_in = n_rows, n_cols
-    csr = build_rect_csr(el, out_w[:nnz].contiguous(), n_out, n_in)
+    csr = build_rect_csr(el, out_w[:nnz].contiguous(), n_out, n_in, want_eid)
     return csr, n_out, n_in
 
 
-def build_rect_csr(el: EdgeList, w: torch.Tensor, n_out: int, n_in: int) -> CSR:
+def build_rect_csr(el: EdgeList, w: torch.Tensor, n_out: int, n_in: int, want_eid: bool = False) -> CSR:
     """K1 in RAW mode for a rectangular operator (n_out x n_in): the forward CSR has n_out rows, the
     transposed one n_in rows; built over max(n_out, n_in) rows and trimmed."""
     n = max(n_out, n_in)
-    csr = ops.build_csr(el, n, mode=CSR_RAW, transposed=True, edge_weight=w)
+    csr = ops.build_csr(el, n, mode=CSR_RAW, transposed=True, edge_weight=w, want_eid=want_eid)
     csr.rowptr = csr.rowptr[:n_out + 1]
     csr.t_rowptr = csr.t_rowptr[:n_in + 1]
     csr.num_nodes = n_out
