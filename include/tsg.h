@@ -163,6 +163,24 @@ int tsg_gat_bwd(const int32_t* rowptr, const int32_t* eid, const int32_t* t_rowp
                 void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * K7  DiffPool per-graph dense contractions (packed layout)
+ *   replaces the batched dense matmuls of SoftPoolingGcnEncoder.forward
+ *   (Code/sage+gat+diffpool/encoders.py:374-375: x = S^T Z, adj = S^T adj S) and of the post-pool
+ *   tower on the dense K x K pooled adjacency (encoders.py:378).
+ *   tsg_seg_contract: C[g] (Kx x Ky) = sum_{r in graph g} X[r,:]^T Y[r,:], g = 0..G-1.
+ *     With Y = [Z | A.S] and X = S this is both products at once.  use_tensor_cores = 1 runs the
+ *     tcgen05 kernel (kind::tf32, 3xTF32 error-compensated split, TMEM accumulators; needs
+ *     Kx <= 128, Ky <= 256); 0 runs the fp32 SIMT kernel.  status_dev (int32, device, caller-zeroed)
+ *     is set to 1 if an MMA completion wait ever times out (hang guard; required for tcgen05).
+ *   tsg_seg_linear: Y[r,:] = X[r,:] . W[g] (Kin x M) (or W[g]^T stored M x Kin) for r in graph g.
+ * ------------------------------------------------------------------------------------------ */
+int tsg_seg_contract(const float* X, const float* Y, const int64_t* graph_ptr, int64_t num_graphs,
+                     int64_t Kx, int64_t Ky, float* C, int use_tensor_cores,
+                     int32_t* status_dev /*nullable unless tensor cores*/, void* stream);
+int tsg_seg_linear(const float* X, const float* W, const int64_t* graph_ptr, int64_t num_graphs,
+                   int64_t in_feat, int64_t out_feat, int w_transposed, float* Y, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * K5a  per-graph top-k (deterministic: descending score, ties -> lower node id, NaN first)
  *   replaces: PyG topk_pool.topk as called from Code/sag/layers.py:20.
  *   graph_ptr[G+1] are node offsets of the (sorted) batch vector; k_g = ceil(ratio * n_g) in

@@ -37,6 +37,8 @@ _PROTOTYPES = {
     "tsg_gat_fwd": (I, [P, P, P, P, P, P, P, I64, I64, I64, F32, P, P, P, P]),
     "tsg_gat_bwd_workspace_bytes": (SZ, [I64, I64]),
     "tsg_gat_bwd": (I, [P, P, P, P, P, P, P, P, P, P, P, I64, I64, I64, I64, F32, P, P, P, P, SZ, P]),
+    "tsg_seg_contract": (I, [P, P, P, I64, I64, I64, P, I, P, P]),
+    "tsg_seg_linear": (I, [P, P, P, I64, I64, I64, I, P, P]),
     "tsg_topk_workspace_bytes": (SZ, [I64, I64]),
     "tsg_topk_sizes": (I, [P, I64, F32, P, P, SZ, P]),
     "tsg_topk": (I, [P, P, P, I64, I64, P, P, SZ, P]),
@@ -75,7 +77,7 @@ KERNELS_PER_CALL = {
     "tsg_batch_to_ptr": 1, "tsg_filter_adj": 7, "tsg_gate_gather_fwd": 1, "tsg_gate_gather_bwd": 1,
     "tsg_readout_fwd": 1, "tsg_readout_bwd": 1, "tsg_triplet_fwd": 2, "tsg_triplet_bwd": 9,
     "tsg_pairdist_matrix": 1, "tsg_linear_fwd": 1, "tsg_dense_epilogue_bwd": 1, "tsg_linear_bwd_weight": 2,
-    "tsg_gat_fwd": 2, "tsg_gat_bwd": 2, "tsg_dense_to_coo": 6, "tsg_nodebn_fwd": 1, "tsg_nodebn_bwd": 1,
+    "tsg_seg_contract": 1, "tsg_seg_linear": 1, "tsg_gat_fwd": 2, "tsg_gat_bwd": 2, "tsg_dense_to_coo": 6, "tsg_nodebn_fwd": 1, "tsg_nodebn_bwd": 1,
 }
 launch_calls = 0        # libtsg entry points called since import
 kernel_launches = 0     # kernels enqueued by them

@@ -356,3 +356,72 @@ def pairdist_matrix(emb: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
     out = torch.empty(M, M, dtype=torch.float32, device=emb.device)
     call("tsg_pairdist_matrix", ptr(emb), M, D, float(eps), ptr(out), stream_ptr())
     return out
+
+
+# --------------------------------------------------------------------------------------------
+# K7 per-graph dense contractions (DiffPool)
+# --------------------------------------------------------------------------------------------
+USE_TCGEN05 = True      # tcgen05 (3xTF32, TMEM) kernel for the contraction; False = fp32 SIMT kernel
+
+
+def seg_contract_raw(x: torch.Tensor, y: torch.Tensor, graph_ptr: torch.Tensor,
+                     tensor_cores: Optional[bool] = None) -> torch.Tensor:
+    """C[g] = sum_{r in g} x[r,:]^T y[r,:]  -> [G, Kx, Ky]."""
+    x = x.contiguous(); y = y.contiguous()
+    G, kx, ky = graph_ptr.numel() - 1, x.size(1), y.size(1)
+    tc = USE_TCGEN05 if tensor_cores is None else tensor_cores
+    tc = bool(tc) and kx <= 128 and ky <= 256
+    c = torch.empty(G, kx, ky, dtype=torch.float32, device=x.device)
+    status = torch.zeros(1, dtype=torch.int32, device=x.device) if tc else None
+    call("tsg_seg_contract", ptr(x), ptr(y), ptr(graph_ptr), G, kx, ky, ptr(c), int(tc), ptr(status), stream_ptr())
+    return c
+
+
+def seg_linear_raw(x: torch.Tensor, w: torch.Tensor, graph_ptr: torch.Tensor, transposed: bool = False):
+    """y[r,:] = x[r,:] . w[g]  (w [G, Kin, M])  or  x[r,:] . w[g]^T  (w [G, M, Kin]) for r in graph g."""
+    x = x.contiguous(); w = w.contiguous()
+    G, kin = graph_ptr.numel() - 1, x.size(1)
+    m = w.size(1) if transposed else w.size(2)
+    if (w.size(2) if transposed else w.size(1)) != kin or w.size(0) != G:
+        raise RuntimeError(f"tsg.seg_linear: shape mismatch x{tuple(x.shape)} w{tuple(w.shape)} T={transposed}")
+    y = torch.empty(x.size(0), m, dtype=torch.float32, device=x.device)
+    call("tsg_seg_linear", ptr(x), ptr(w), ptr(graph_ptr), G, kin, m, int(transposed), ptr(y), stream_ptr())
+    return y
+
+
+class _SegContract(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, y, graph_ptr):
+        ctx.save_for_backward(x, y, graph_ptr)
+        return seg_contract_raw(x, y, graph_ptr)
+
+    @staticmethod
+    def backward(ctx, dc):
+        x, y, gptr = ctx.saved_tensors
+        dc = dc.contiguous()
+        dx = seg_linear_raw(y, dc, gptr, transposed=True) if ctx.needs_input_grad[0] else None   # Y dC^T
+        dy = seg_linear_raw(x, dc, gptr, transposed=False) if ctx.needs_input_grad[1] else None  # X dC
+        return dx, dy, None
+
+
+class _SegLinear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, graph_ptr):
+        ctx.save_for_backward(x, w, graph_ptr)
+        return seg_linear_raw(x, w, graph_ptr, False)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, gptr = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = seg_linear_raw(dy, w, gptr, transposed=True) if ctx.needs_input_grad[0] else None
+        dw = seg_contract_raw(x, dy, gptr) if ctx.needs_input_grad[1] else None
+        return dx, dw, None
+
+
+def seg_contract(x, y, graph_ptr):
+    return _SegContract.apply(x, y, graph_ptr)
+
+
+def seg_linear(x, w, graph_ptr):
+    return _SegLinear.apply(x, w, graph_ptr)
