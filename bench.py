@@ -280,13 +280,14 @@ def main():
     csr = ops.build_csr(ops.EdgeList.from_edge_index(b["edge_index"]), N)
     H = torch.randn(N, Fh, device=dev)
     bias = torch.zeros(Fh, device=dev)
+    tile_ptr = torch.from_numpy(ops.make_tiles(b["node_ptr"])).to(dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
     durs = []
     for it in range(3 + 10):
         flush.zero_()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
-        ops.spmm_raw(csr.rowptr, csr.colidx, csr.val, H, bias, relu=True)
+        ops.spmm_raw(csr.rowptr, csr.colidx, csr.val, H, bias, relu=True, tile_ptr=tile_ptr)
         e.record()
         torch.cuda.synchronize()
         if it >= 3:
@@ -308,16 +309,20 @@ def main():
 
     # ---- optional per-entry-point breakdown (device time shares; not part of any reported number)
     if a.breakdown and rank == 0:
+        step_resident(0)
         _lib.profile = {}
         torch.cuda.synchronize()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record(); step_resident(0); e.record(); torch.cuda.synchronize()
         total = s.elapsed_time(e)
-        rows = sorted(((sum(x.elapsed_time(y) for x, y in v), k, len(v)) for k, v in _lib.profile.items()), reverse=True)
+        prof = _lib.profile
+        rows = sorted(((sum(x.elapsed_time(y) for x, y in v), k, len(v)) for k, v in prof.items()), reverse=True)
         _lib.profile = None
         print(f"[breakdown] one step {total:.3f} ms", file=sys.stderr)
         for t, k, n in rows:
             print(f"[breakdown] {k:28s} calls={n:3d} {t:8.3f} ms  {100 * t / total:5.1f}%", file=sys.stderr)
+        for k in ("tsg_linear_bwd_weight", "tsg_linear_fwd", "tsg_spmm", "tsg_csr_build", "tsg_topk"):
+            print(f"[breakdown] {k} per call (ms): " + " ".join(f"{x.elapsed_time(y):.3f}" for x, y in prof.get(k, [])), file=sys.stderr)
 
     # ---- CPU baseline (rank 0, N=1 only)
     cpu_baseline = None

@@ -85,6 +85,15 @@ int tsg_spmm(const int32_t* rowptr, const int32_t* colidx, const float* val /*nu
              const float* H, const float* bias /*nullable*/, float* Y,
              int64_t num_rows, int64_t feat, int flags, void* stream);
 
+/* Tiled K2: `tile_ptr[T+1]` (int64, device) cuts the rows into runs whose neighbours all lie inside the
+ * same run (a packed batch is block diagonal: a tile = one or several whole graphs).  Each CTA stages
+ * its tile's H rows, CSR slice and rowptr slice in shared memory with bulk async copies and gathers
+ * from there; tiles that do not fit the staging buffers or are not self-contained (verified in the
+ * kernel) use the global-gather path.  Same arithmetic and order as tsg_spmm (bit-identical). */
+int tsg_spmm_tiled(const int32_t* rowptr, const int32_t* colidx, const float* val /*nullable => 1*/,
+                   const float* H, const float* bias /*nullable*/, float* Y, const int64_t* tile_ptr,
+                   int64_t num_tiles, int64_t num_rows, int64_t feat, int flags, void* stream);
+
 /* dY_masked = dY * (Y > 0): ReLU backward fused with the column sum that gives the bias gradient:
  * dbias[f] = sum_r dY_masked[r,f]  (deterministic two-stage reduction).  Y may be NULL (no ReLU).
  * workspace: tsg_colsum_workspace_bytes(num_rows, feat). */

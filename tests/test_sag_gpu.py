@@ -367,3 +367,32 @@ def test_full_size_properties(cuda):
     assert int(el.count) == int(both.sum())
     out = el.edge_index()
     assert torch.equal(perm[out[0]], ei[0][both]) and torch.equal(perm[out[1]], ei[1][both])
+
+
+# ------------------------------------------------------------------ K2 tiled (shared-memory staging)
+@pytest.mark.parametrize("F", [32, 128, 64])
+def test_spmm_tiled_bit_exact(cuda, F):
+    """Tiled kernel == untiled kernel == oracle, including tiles that fall back (too many rows, not
+    self-contained) and an empty tile."""
+    from tsg import ops
+    ops.USE_TILED_SPMM = True
+    c = synth.make_corpus("DD", 40, seed=5)
+    b = synth.pack(c)
+    ei = torch.from_numpy(b["edge_index"]); n = int(b["node_ptr"][-1])
+    h = torch.randn(n, F, generator=torch.Generator().manual_seed(F))
+    bias = torch.randn(F, generator=torch.Generator().manual_seed(1))
+    csr = ops.build_csr(ops.EdgeList.from_edge_index(ei.to(cuda)), n)
+    ei2, norm = R.gcn_norm(ei, None, n)
+    ref = torch.relu(R.spmm_coo_edge_order(ei2, norm, h, n) + bias)
+    tiles = ops.make_tiles(b["node_ptr"], 512)
+    assert tiles[0] == 0 and tiles[-1] == n and np.all(np.diff(tiles) > 0)
+    y = ops.spmm_raw(csr.rowptr, csr.colidx, csr.val, h.to(cuda), bias.to(cuda), True, torch.from_numpy(tiles).to(cuda))
+    assert torch.equal(y.cpu(), ref)
+    # adversarial tiling: cuts in the middle of graphs (not self-contained) + an empty tile
+    cut = np.unique(np.concatenate([[0, 100, 100 + 1, 777, n // 2, n], tiles[::3]])).astype(np.int64)
+    cut = np.concatenate([cut[:2], cut[1:]])          # duplicate => empty tile
+    y2 = ops.spmm_raw(csr.rowptr, csr.colidx, csr.val, h.to(cuda), bias.to(cuda), True, torch.from_numpy(np.sort(cut)).to(cuda))
+    assert torch.equal(y2.cpu(), ref)
+    yt = ops.spmm_raw(csr.t_rowptr, csr.t_colidx, csr.t_val, h.to(cuda), tile_ptr=torch.from_numpy(tiles).to(cuda))
+    assert torch.equal(yt.cpu(), ops.spmm_raw(csr.t_rowptr, csr.t_colidx, csr.t_val, h.to(cuda)).cpu())
+    ops.USE_TILED_SPMM = False

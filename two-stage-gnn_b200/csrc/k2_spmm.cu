@@ -115,6 +115,126 @@ k_spmm_scalar(const int* __restrict__ rowptr, const int* __restrict__ colidx,
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Tiled variant: shared-memory staging of the small per-graph blocks (north-star design).
+// A tile is a run of consecutive rows [tile_ptr[t], tile_ptr[t+1]) whose neighbours all lie inside
+// the same run (a packed batch is block diagonal: tiles = whole graphs).  The CTA bulk-copies the
+// tile's H rows (contiguous in memory: one coalesced cp.async stream), its CSR slice and rowptr
+// slice into shared memory, then every gather is a 30-cycle LDS instead of a dependent global load.
+// DRAM sees exactly the compulsory traffic; L2 sees H once.  The kernel VERIFIES containment
+// (min / max of the staged column ids); a tile that is too large for the staging buffers or not
+// self-contained takes the global-gather path, so correctness never depends on the caller's promise.
+// Accumulation order per row is unchanged => still bit-identical to index_add_ order.
+// ------------------------------------------------------------------------------------------
+constexpr int TILED_SMEM_BYTES = 112 * 1024;      // 2 CTAs / SM
+constexpr int TILED_MAX_NNZ = 3840;               // 30 KB of (colidx, val)
+constexpr int TILED_MAX_ROWS_RP = 704;            // rowptr slice entries
+
+__device__ __forceinline__ void cp_async_4(void* sdst, const void* gsrc) {
+  unsigned a = (unsigned)__cvta_generic_to_shared(sdst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(a), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_16(void* sdst, const void* gsrc) {
+  unsigned a = (unsigned)__cvta_generic_to_shared(sdst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(a), "l"(gsrc) : "memory");
+}
+
+constexpr int TILED_THREADS = 512;
+
+template <int LPR, bool HAS_VAL>
+__global__ void __launch_bounds__(TILED_THREADS, 2)
+k_spmm_tiled(const int* __restrict__ rowptr, const int* __restrict__ colidx, const float* __restrict__ val,
+             const float4* __restrict__ H, const float4* __restrict__ bias, float4* __restrict__ Y,
+             const int64_t* __restrict__ tile_ptr, int num_tiles, int F4, int max_rows, int relu) {
+  extern __shared__ __align__(16) unsigned char tsm[];
+  int* s_off = reinterpret_cast<int*>(tsm);                         // (col - r0) * F4, pre-scaled
+  float* s_val = reinterpret_cast<float*>(tsm + TILED_MAX_NNZ * 4);
+  int* s_rp = reinterpret_cast<int*>(tsm + TILED_MAX_NNZ * 8);
+  float4* s_H = reinterpret_cast<float4*>(tsm + TILED_MAX_NNZ * 8 + (TILED_MAX_ROWS_RP + 32) * 4);
+  __shared__ int s_flag;
+  const int lane_in_row = threadIdx.x % LPR;
+  // this lane's bias columns stay in registers for the whole kernel (F4 <= 2*LPR is the common case)
+  for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    const int r0 = (int)tile_ptr[t], r1 = (int)tile_ptr[t + 1];
+    const int rows = r1 - r0;
+    if (rows <= 0) continue;
+    const int p0 = __ldg(rowptr + r0), p1 = __ldg(rowptr + r1);
+    const int nnz = p1 - p0;
+    const bool fits = rows <= max_rows && rows <= TILED_MAX_ROWS_RP && nnz <= TILED_MAX_NNZ;
+    if (threadIdx.x == 0) s_flag = 1;
+    __syncthreads();                           // previous tile fully consumed; flag reset
+    if (fits) {
+      const float4* src = H + (size_t)r0 * F4;
+      for (int i = threadIdx.x; i < rows * F4; i += TILED_THREADS) cp_async_16(s_H + i, src + i);
+      if (HAS_VAL) for (int i = threadIdx.x; i < nnz; i += TILED_THREADS) cp_async_4(s_val + i, val + p0 + i);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      int bad = 0;
+      for (int i = threadIdx.x; i < nnz; i += TILED_THREADS) {
+        const int c = __ldg(colidx + p0 + i);
+        bad |= (c < r0) | (c >= r1);
+        s_off[i] = (c - r0) * F4;
+      }
+      for (int i = threadIdx.x; i <= rows; i += TILED_THREADS) s_rp[i] = __ldg(rowptr + r0 + i) - p0;
+      if (bad) s_flag = 0;
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();
+    }
+    const bool staged = fits && s_flag;
+    if (staged) {
+      for (int r = threadIdx.x / LPR; r < rows; r += TILED_THREADS / LPR) {
+        const int s = s_rp[r], e = s_rp[r + 1];
+        for (int f = lane_in_row; f < F4; f += LPR) {
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4* hb = s_H + f;
+          int p = s;
+#define TSG_TACC(h, v)                                                                          \
+          acc.x = __fadd_rn(acc.x, __fmul_rn(v, h.x)); acc.y = __fadd_rn(acc.y, __fmul_rn(v, h.y)); \
+          acc.z = __fadd_rn(acc.z, __fmul_rn(v, h.z)); acc.w = __fadd_rn(acc.w, __fmul_rn(v, h.w));
+          for (; p + 2 <= e; p += 2) {
+            const int o0 = s_off[p], o1 = s_off[p + 1];
+            const float v0 = HAS_VAL ? s_val[p] : 1.f, v1 = HAS_VAL ? s_val[p + 1] : 1.f;
+            const float4 h0 = hb[o0], h1 = hb[o1];
+            TSG_TACC(h0, v0) TSG_TACC(h1, v1)
+          }
+          if (p < e) {
+            const float v0 = HAS_VAL ? s_val[p] : 1.f;
+            const float4 h0 = hb[s_off[p]];
+            TSG_TACC(h0, v0)
+          }
+#undef TSG_TACC
+          if (bias != nullptr) {
+            float4 b = __ldg(bias + f);
+            acc.x = __fadd_rn(acc.x, b.x); acc.y = __fadd_rn(acc.y, b.y);
+            acc.z = __fadd_rn(acc.z, b.z); acc.w = __fadd_rn(acc.w, b.w);
+          }
+          if (relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
+          Y[(size_t)(r0 + r) * F4 + f] = acc;
+        }
+      }
+    } else {                                   // global-gather path (same arithmetic, same order)
+      for (int r = r0 + threadIdx.x / LPR; r < r1; r += TILED_THREADS / LPR) {
+        const int s = __ldg(rowptr + r), e = __ldg(rowptr + r + 1);
+        for (int f = lane_in_row; f < F4; f += LPR) {
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int p = s; p < e; ++p) {
+            const float v = HAS_VAL ? __ldg(val + p) : 1.f;
+            const float4 h = __ldg(H + (size_t)__ldg(colidx + p) * F4 + f);
+            acc.x = __fadd_rn(acc.x, __fmul_rn(v, h.x)); acc.y = __fadd_rn(acc.y, __fmul_rn(v, h.y));
+            acc.z = __fadd_rn(acc.z, __fmul_rn(v, h.z)); acc.w = __fadd_rn(acc.w, __fmul_rn(v, h.w));
+          }
+          if (bias != nullptr) {
+            float4 b = __ldg(bias + f);
+            acc.x = __fadd_rn(acc.x, b.x); acc.y = __fadd_rn(acc.y, b.y);
+            acc.z = __fadd_rn(acc.z, b.z); acc.w = __fadd_rn(acc.w, b.w);
+          }
+          if (relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
+          Y[(size_t)r * F4 + f] = acc;
+        }
+      }
+    }
+  }
+}
+
 template <bool HAS_VAL>
 static int launch_spmm(const int* rowptr, const int* colidx, const float* val, const float* H,
                        const float* bias, float* Y, int64_t N, int64_t F, int relu, cudaStream_t st) {
@@ -200,6 +320,36 @@ extern "C" int tsg_spmm(const int32_t* rowptr, const int32_t* colidx, const floa
   cudaStream_t st = (cudaStream_t)stream;
   return val ? launch_spmm<true>(rowptr, colidx, val, H, bias, Y, num_rows, feat, relu, st)
              : launch_spmm<false>(rowptr, colidx, val, H, bias, Y, num_rows, feat, relu, st);
+}
+
+
+extern "C" int tsg_spmm_tiled(const int32_t* rowptr, const int32_t* colidx, const float* val,
+                              const float* H, const float* bias, float* Y, const int64_t* tile_ptr,
+                              int64_t num_tiles, int64_t num_rows, int64_t feat, int flags, void* stream) {
+  TSG_REQUIRE(num_rows >= 0 && feat > 0 && num_tiles >= 0, "spmm_tiled: bad shape");
+  TSG_REQUIRE(num_rows < (int64_t)0x7fffffff && num_tiles < (int64_t)0x7fffffff, "spmm_tiled: too large");
+  if (num_rows == 0 || num_tiles == 0) return TSG_OK;
+  TSG_REQUIRE(rowptr && colidx && H && Y && tile_ptr, "spmm_tiled: null pointer");
+  bool vec = (feat % 4 == 0) && (((uintptr_t)H & 15) == 0) && (((uintptr_t)Y & 15) == 0) &&
+             (bias == nullptr || ((uintptr_t)bias & 15) == 0);
+  if (!vec) return tsg_spmm(rowptr, colidx, val, H, bias, Y, num_rows, feat, flags, stream);   // scalar widths: untiled kernel
+  cudaStream_t st = (cudaStream_t)stream;
+  int relu = (flags & TSG_SPMM_RELU) ? 1 : 0;
+  int F4 = (int)(feat / 4);
+  int lpr = 1; while (lpr < F4 && lpr < 32) lpr <<= 1;
+  size_t h_bytes = TILED_SMEM_BYTES - (size_t)TILED_MAX_NNZ * 8 - (TILED_MAX_ROWS_RP + 32) * 4;
+  int max_rows = (int)(h_bytes / ((size_t)F4 * 16));
+  int grid = (int)(num_tiles < TSG_NUM_SMS * 2 ? num_tiles : TSG_NUM_SMS * 2);
+#define TSG_GO(L, V)                                                                                         \
+  { cudaFuncSetAttribute(k_spmm_tiled<L, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILED_SMEM_BYTES);   \
+    k_spmm_tiled<L, V><<<grid, TILED_THREADS, TILED_SMEM_BYTES, st>>>(rowptr, colidx, val, (const float4*)H,    \
+        (const float4*)bias, (float4*)Y, tile_ptr, (int)num_tiles, F4, max_rows, relu); }
+#define TSG_SW(V) switch (lpr) { case 1: TSG_GO(1, V) break; case 2: TSG_GO(2, V) break; case 4: TSG_GO(4, V) break; \
+                                 case 8: TSG_GO(8, V) break; case 16: TSG_GO(16, V) break; default: TSG_GO(32, V) break; }
+  if (val) { TSG_SW(true) } else { TSG_SW(false) }
+#undef TSG_SW
+#undef TSG_GO
+  return check_launch("spmm_tiled");
 }
 
 static int colsum_blocks(int64_t N) {

@@ -25,6 +25,31 @@ constexpr int LIN_RPT = 2;                 // rows per thread
 constexpr float NORM_EPS = 1e-12f;         // F.normalize eps
 constexpr float BN_EPS = 1e-5f;            // BatchNorm1d eps
 
+
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N_> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N_) : "memory"); }
+
+// asynchronously stage rows [r0, r0+R) of X[N,K] into Xs[R][pitch] (rows past N are zero filled);
+// warp w copies rows w, w+8, ..., lanes run along K so every global request is a contiguous run.
+__device__ __forceinline__ void stage_rows_async(float* Xs, const float* __restrict__ X, int r0, int R,
+                                                 int N, int K, int pitch) {
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = w; r < R; r += LIN_THREADS / 32) {
+    float* dst = Xs + r * pitch;
+    if (r0 + r < N) {
+      const float* src = X + (size_t)(r0 + r) * K;
+      for (int k = lane; k < K; k += 32) cp_async4(dst + k, src + k);
+    } else {
+      for (int k = lane; k < K; k += 32) dst[k] = 0.f;
+    }
+  }
+  cp_async_commit();
+}
+
 template <int CG>
 __device__ __forceinline__ float group_sum(float v, unsigned mask) {
 #pragma unroll
@@ -93,26 +118,27 @@ k_linear_fwd(const float* __restrict__ X, const float* __restrict__ W, const flo
     b4[c] = (bias != nullptr && ok[c]) ? bias[cg * 4 + c] : 0.f;
   }
   const int num_tiles = (N + R - 1) / R;
+  int buf = 0;
+  if ((int)blockIdx.x < num_tiles) stage_rows_async(Xs, X, blockIdx.x * R, R, N, K, pitch);
   for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
     const int r0 = tile * R;
     const int rows = min(R, N - r0);
-    __syncthreads();                             // previous tile's Xs readers are done; Ws visible
-    {
-      const float* src = X + (size_t)r0 * K;
-      const int total = rows * K;
-      for (int i = threadIdx.x; i < R * K; i += LIN_THREADS) {
-        int r = i / K, k = i - r * K;
-        Xs[r * pitch + k] = i < total ? src[i] : 0.f;
-      }
+    const int next = tile + gridDim.x;
+    float* Xcur = Xs + (size_t)buf * R * pitch;
+    if (next < num_tiles) {                      // prefetch the next tile into the other buffer
+      stage_rows_async(Xs + (size_t)(buf ^ 1) * R * pitch, X, next * R, R, N, K, pitch);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
     }
-    __syncthreads();
+    __syncthreads();                             // this tile's rows (and Ws on the first pass) visible
     float acc[LIN_RPT][4];
 #pragma unroll
     for (int j = 0; j < LIN_RPT; ++j)
 #pragma unroll
       for (int c = 0; c < 4; ++c) acc[j][c] = 0.f;
-    const float* x0 = Xs + (rs)*pitch;
-    const float* x1 = Xs + (rs + RS) * pitch;
+    const float* x0 = Xcur + (rs)*pitch;
+    const float* x1 = Xcur + (rs + RS) * pitch;
     for (int k = 0; k < K; ++k) {
       float a0 = x0[k], a1 = x1[k];
       if (!__any_sync(0xffffffffu, (a0 != 0.f) | (a1 != 0.f))) continue;   // exact zeros contribute +0
@@ -138,6 +164,8 @@ k_linear_fwd(const float* __restrict__ X, const float* __restrict__ W, const flo
         }
       }
     }
+    __syncthreads();                             // everyone is done with Xcur before it is refilled
+    buf ^= 1;
   }
 }
 
@@ -169,26 +197,27 @@ k_dense_epilogue_bwd(const float* __restrict__ X, const float* __restrict__ W, c
     b4[c] = (bias != nullptr && ok[c]) ? bias[cg * 4 + c] : 0.f;
   }
   const int num_tiles = (N + R - 1) / R;
+  int buf = 0;
+  if ((int)blockIdx.x < num_tiles) stage_rows_async(Xs, X, blockIdx.x * R, R, N, K, pitch);
   for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
     const int r0 = tile * R;
     const int rows = min(R, N - r0);
-    __syncthreads();
-    {
-      const float* src = X + (size_t)r0 * K;
-      const int total = rows * K;
-      for (int i = threadIdx.x; i < R * K; i += LIN_THREADS) {
-        int r = i / K, k = i - r * K;
-        Xs[r * pitch + k] = i < total ? src[i] : 0.f;
-      }
+    const int next = tile + gridDim.x;
+    float* Xcur = Xs + (size_t)buf * R * pitch;
+    if (next < num_tiles) {                      // prefetch the next tile into the other buffer
+      stage_rows_async(Xs + (size_t)(buf ^ 1) * R * pitch, X, next * R, R, N, K, pitch);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
     }
-    __syncthreads();
+    __syncthreads();                             // this tile's rows (and Ws on the first pass) visible
     float u[LIN_RPT][4];
 #pragma unroll
     for (int j = 0; j < LIN_RPT; ++j)
 #pragma unroll
       for (int c = 0; c < 4; ++c) u[j][c] = 0.f;
-    const float* x0 = Xs + (rs)*pitch;
-    const float* x1 = Xs + (rs + RS) * pitch;
+    const float* x0 = Xcur + (rs)*pitch;
+    const float* x1 = Xcur + (rs + RS) * pitch;
     for (int k = 0; k < K; ++k) {
       float a0 = x0[k], a1 = x1[k];
       if (!__any_sync(0xffffffffu, (a0 != 0.f) | (a1 != 0.f))) continue;
@@ -264,91 +293,187 @@ k_dense_epilogue_bwd(const float* __restrict__ X, const float* __restrict__ W, c
         for (int c = 0; c < 4; ++c) if (ok[c]) dU[(size_t)(r0 + r) * M + cg * 4 + c] = g[c];
       }
     }
+    __syncthreads();
+    buf ^= 1;
   }
 }
 
 // ------------------------------------------------------------------------------------------
-// dW[K,M] = X^T . dY   and   db[M] = colsum(dY)   -- deterministic two-stage reduction.
-// A "unit" owns feature row k (k == K is the bias row with x == 1) x one 32-column chunk of M and
-// keeps 32 accumulators in registers; row groups split the tile's rows; exact zeros are skipped.
-// stage 1 writes part[cta][K+1][M]; stage 2 sums the CTAs in a fixed order.
+// dW[K,M] = X^T . dY  -- deterministic two-stage reduction that streams X and dY exactly once.
+// A warp owns rows r = w, w + W, ... of its CTA's contiguous row range.  Per row the lanes read
+// X[r, 32c + lane] (coalesced) for every 32-column chunk c of K and dY[r, m0 + lane] (coalesced);
+// all loads of U rows are issued before any is used (memory-level parallelism).  Non-zeros are
+// found with a ballot and applied one by one to the warp's PRIVATE accumulator tile acc[k][lane] in
+// shared memory (bank = lane: conflict free) -- with one-hot features that is one update per row.
+// Order: rows ascending inside a warp, warps combined in index order, CTAs (fixed grid) in index
+// order: bit-reproducible.  M is covered in passes of 32 columns.
+// db (when requested) is the deterministic column sum of dY (tsg_relu_bwd_colsum's kernels).
 // ------------------------------------------------------------------------------------------
-constexpr int LBW_ROWS = 64;
 constexpr int LBW_GRID = TSG_NUM_SMS * 2;
 
-__global__ void __launch_bounds__(LIN_THREADS)
+template <int NK, int U>
+__global__ void __launch_bounds__(256)
 k_linear_bwd_weight(const float* __restrict__ X, const float* __restrict__ dY, float* __restrict__ part,
-                    int N, int K, int M, int units, int row_groups) {
+                    int N, int K, int M, int m0) {
   extern __shared__ __align__(16) float smem[];
-  const int Mp = (M + 31) / 32 * 32;             // padded so every chunk is 32 wide
-  const int mch = Mp / 32;
-  const int pitch = K | 1;
-  float* Xs = smem;                              // [ROWS][pitch]
-  float* Ds = smem + LBW_ROWS * pitch;           // [ROWS][Mp]
-  const int K1 = K + 1;
-  const int slots = units * row_groups;          // active threads per pass
-  const int passes = (K1 * mch + units - 1) / units;    // units per thread when K1*mch > units
-  const int num_tiles = (N + LBW_ROWS - 1) / LBW_ROWS;
-  float* mypart = part + (size_t)blockIdx.x * K1 * M;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  float* acc = smem + (size_t)w * K * 32;                   // [K][32] private to this warp
+  for (int i = lane; i < K * 32; i += 32) acc[i] = 0.f;
+  __syncwarp();
+  const int rows_per_cta = (N + gridDim.x - 1) / gridDim.x;
+  const int r_begin = blockIdx.x * rows_per_cta;
+  const int r_end = min(N, r_begin + rows_per_cta);
+  const bool mok = m0 + lane < M;
+  // dense rows (many non-zeros) accumulate in REGISTERS (one accumulator per k for this lane's
+  // column) to avoid a serial shared-memory read-modify-write chain; only for K <= 64.
+  constexpr bool REG = NK <= 2;
+  float racc[REG ? NK * 32 : 1];
+#pragma unroll
+  for (int i = 0; i < (REG ? NK * 32 : 1); ++i) racc[i] = 0.f;
+  for (int rb = r_begin + w; rb < r_end; rb += nw * U) {
+    float xv[U][NK], dy[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int r = rb + u * nw;
+      const bool rok = r < r_end;
+      dy[u] = (rok && mok) ? __ldg(dY + (size_t)r * M + m0 + lane) : 0.f;
+#pragma unroll
+      for (int c = 0; c < NK; ++c) {
+        const int k = c * 32 + lane;
+        xv[u][c] = (rok && k < K) ? __ldg(X + (size_t)r * K + k) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+#pragma unroll
+      for (int c = 0; c < NK; ++c) {
+        unsigned mask = __ballot_sync(0xffffffffu, xv[u][c] != 0.f);
+        if (REG && __popc(mask) > 6) {
+#pragma unroll
+          for (int b = 0; b < 32; ++b) {
+            const float x = __shfl_sync(0xffffffffu, xv[u][c], b);
+            racc[(REG ? c : 0) * 32 + b] = fmaf(x, dy[u], racc[(REG ? c : 0) * 32 + b]);
+          }
+          mask = 0;
+        }
+        while (mask) {
+          const int b = __ffs(mask) - 1;
+          mask &= mask - 1;
+          const float x = __shfl_sync(0xffffffffu, xv[u][c], b);
+          float* a = acc + (c * 32 + b) * 32 + lane;
+          *a = fmaf(x, dy[u], *a);
+        }
+      }
+    }
+  }
+  if (REG) {
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < NK * 32; ++i)
+      if (i < K) acc[i * 32 + lane] += racc[i];
+  }
+  __syncthreads();
+  // combine the warps in index order, write this CTA's partial for columns [m0, m0+32)
+  float* mypart = part + (size_t)blockIdx.x * K * M;
+  for (int i = threadIdx.x; i < K * 32; i += blockDim.x) {
+    float s = smem[i];
+    for (int ww = 1; ww < nw; ++ww) s += smem[(size_t)ww * K * 32 + i];
+    const int k = i >> 5, m = m0 + (i & 31);
+    if (m < M) mypart[(size_t)k * M + m] = s;
+  }
+}
 
-  for (int pass = 0; pass < passes; ++pass) {
-    const int t = threadIdx.x;
-    const bool active = t < slots;
-    const int unit = pass * units + (active ? t % units : 0);
-    const int rg = active ? t / units : 0;
-    const bool uok = active && unit < K1 * mch;
-    const int k = uok ? unit / mch : 0;
-    const int mc = uok ? unit % mch : 0;
-    float acc[32];
+// ------------------------------------------------------------------------------------------
+// Narrow outputs (M <= 4: SAGPool's score layer is F -> 1): GEMV-shaped, pure streaming of X.
+//   fwd : LPR = K/4 lanes read one row as float4s, M dot products, width-LPR shuffle reduction.
+//   dW  : the same lanes keep acc[4][M] for their 4 feature rows over the CTA's row range; row groups
+//         are combined through shared memory in index order, CTAs by the fixed-grid second stage.
+// ------------------------------------------------------------------------------------------
+template <int LPR>
+__global__ void __launch_bounds__(256)
+k_linear_fwd_small(const float* __restrict__ X, const float* __restrict__ W, const float* __restrict__ bias,
+                   float* __restrict__ Y, int N, int K, int M, int w_transposed) {
+  __shared__ float Ws[4][512];                   // [m][k], K <= 512
+  for (int i = threadIdx.x; i < M * K; i += 256) {
+    int m = i / K, k = i - m * K;
+    Ws[m][k] = w_transposed ? W[(size_t)m * K + k] : W[(size_t)k * M + m];
+  }
+  __syncthreads();
+  const int l = threadIdx.x % LPR;
+  const int K4 = K >> 2;
+  const int groups = 256 / LPR;
+  const int iters = (N + gridDim.x * groups - 1) / (gridDim.x * groups);      // warp-uniform trip count
+  for (int it = 0; it < iters; ++it) {
+    const int r = (it * gridDim.x + blockIdx.x) * groups + threadIdx.x / LPR;
+    const bool rok = r < N;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (rok) {
+      const float4* xr = reinterpret_cast<const float4*>(X + (size_t)r * K);
+      for (int k4 = l; k4 < K4; k4 += LPR) {
+        const float4 x = __ldg(xr + k4);
 #pragma unroll
-    for (int c = 0; c < 32; ++c) acc[c] = 0.f;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int r0 = tile * LBW_ROWS;
-      const int rows = min(LBW_ROWS, N - r0);
-      __syncthreads();
-      for (int i = threadIdx.x; i < LBW_ROWS * K; i += LIN_THREADS) {
-        int r = i / K, kk = i - r * K;
-        Xs[r * pitch + kk] = r < rows ? X[(size_t)(r0 + r) * K + kk] : 0.f;
-      }
-      for (int i = threadIdx.x; i < LBW_ROWS * Mp; i += LIN_THREADS) {
-        int r = i / Mp, m = i - r * Mp;
-        Ds[i] = (r < rows && m < M) ? dY[(size_t)(r0 + r) * M + m] : 0.f;
-      }
-      __syncthreads();
-      if (uok) {
-        for (int r = rg; r < rows; r += row_groups) {
-          float x = k < K ? Xs[r * pitch + k] : 1.f;
-          if (x == 0.f) continue;
-          const float4* d = reinterpret_cast<const float4*>(Ds + r * Mp + mc * 32);
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            float4 v = d[q];
-            acc[4 * q + 0] = fmaf(x, v.x, acc[4 * q + 0]); acc[4 * q + 1] = fmaf(x, v.y, acc[4 * q + 1]);
-            acc[4 * q + 2] = fmaf(x, v.z, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(x, v.w, acc[4 * q + 3]);
+        for (int m = 0; m < 4; ++m) {
+          if (m < M) {
+            const float* w = &Ws[m][k4 * 4];
+            acc[m] = fmaf(x.x, w[0], acc[m]); acc[m] = fmaf(x.y, w[1], acc[m]);
+            acc[m] = fmaf(x.z, w[2], acc[m]); acc[m] = fmaf(x.w, w[3], acc[m]);
           }
         }
       }
     }
-    // combine the row groups in a fixed order through shared memory, one group at a time
-    __syncthreads();
-    float* red = smem;                           // reuse: [units][32]
-    for (int g = 0; g < row_groups; ++g) {
-      if (uok && rg == g) {
-        float* dst = red + (size_t)(t % units) * 32;
 #pragma unroll
-        for (int c = 0; c < 32; ++c) dst[c] = g == 0 ? acc[c] : dst[c] + acc[c];
-      }
-      __syncthreads();
-    }
-    if (uok && rg == 0) {
-      const float* src = red + (size_t)(t % units) * 32;
+    for (int m = 0; m < 4; ++m)
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        int m = mc * 32 + c;
-        if (m < M) mypart[(size_t)k * M + m] = src[c];
-      }
+      for (int d = LPR / 2; d > 0; d >>= 1) acc[m] += __shfl_xor_sync(0xffffffffu, acc[m], d, LPR);
+    if (rok && l == 0)
+      for (int m = 0; m < M; ++m) Y[(size_t)r * M + m] = acc[m] + (bias ? bias[m] : 0.f);
+  }
+}
+
+template <int LPR>
+__global__ void __launch_bounds__(256)
+k_linear_bwd_weight_small(const float* __restrict__ X, const float* __restrict__ dY, float* __restrict__ part,
+                          int N, int K, int M) {
+  extern __shared__ __align__(16) float smem[];            // [groups][K*M] for the in-CTA combine
+  const int l = threadIdx.x % LPR, grp = threadIdx.x / LPR;
+  const int groups = 256 / LPR;
+  const int K4 = K >> 2;
+  const int rows_per_cta = (N + gridDim.x - 1) / gridDim.x;
+  const int r_begin = blockIdx.x * rows_per_cta, r_end = min(N, r_begin + rows_per_cta);
+  // a lane owns k4 = l (and l + LPR, ... when K4 > LPR is not supported: K <= 4*LPR)
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int m = 0; m < 4; ++m) acc[a][m] = 0.f;
+  const bool lok = l < K4;
+  for (int rb = r_begin + grp; rb < r_end; rb += groups * 4) {
+    float4 xv[4]; float dv[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int r = rb + u * groups;
+      const bool rok = r < r_end;
+      xv[u] = (rok && lok) ? __ldg(reinterpret_cast<const float4*>(X + (size_t)r * K) + l) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int m = 0; m < 4; ++m) dv[u][m] = (rok && m < M) ? __ldg(dY + (size_t)r * M + m) : 0.f;
     }
-    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        acc[0][m] = fmaf(xv[u].x, dv[u][m], acc[0][m]); acc[1][m] = fmaf(xv[u].y, dv[u][m], acc[1][m]);
+        acc[2][m] = fmaf(xv[u].z, dv[u][m], acc[2][m]); acc[3][m] = fmaf(xv[u].w, dv[u][m], acc[3][m]);
+      }
+  }
+  if (lok)
+    for (int a = 0; a < 4; ++a)
+      for (int m = 0; m < M; ++m) smem[(size_t)grp * K * M + (size_t)(l * 4 + a) * M + m] = acc[a][m];
+  __syncthreads();
+  float* mypart = part + (size_t)blockIdx.x * K * M;
+  for (int i = threadIdx.x; i < K * M; i += 256) {
+    float sacc = smem[i];
+    for (int g = 1; g < groups; ++g) sacc += smem[(size_t)g * K * M + i];
+    mypart[i] = sacc;
   }
 }
 
@@ -363,7 +488,7 @@ static int pick_cg(int64_t M, int64_t K) {
 
 static size_t lin_smem_bytes(int cg, int64_t K) {
   int R = (LIN_THREADS / cg) * LIN_RPT;
-  return ((size_t)K * cg * 4 + (size_t)R * (K | 1)) * sizeof(float);
+  return ((size_t)K * cg * 4 + 2 * (size_t)R * (K | 1)) * sizeof(float);      // W + two X tiles
 }
 
 }  // namespace tsg
@@ -388,6 +513,17 @@ extern "C" int tsg_linear_fwd(const float* X, const float* W, const float* bias,
   if (N == 0) return TSG_OK;
   TSG_REQUIRE(X && W && Y, "linear_fwd: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
+  if (M <= 4 && flags == 0 && (K & 3) == 0 && K <= 128 && (((uintptr_t)X) & 15) == 0) {   // GEMV-shaped
+    int lpr = 1; while (lpr * 4 < K) lpr <<= 1;
+    int grid = grid_for(N, 256 / lpr, 16);
+#define TSG_GOS(L) k_linear_fwd_small<L><<<grid, 256, 0, st>>>(X, W, bias, Y, (int)N, (int)K, (int)M, w_transposed)
+    switch (lpr) {
+      case 1: TSG_GOS(1); break; case 2: TSG_GOS(2); break; case 4: TSG_GOS(4); break;
+      case 8: TSG_GOS(8); break; case 16: TSG_GOS(16); break; default: TSG_GOS(32); break;
+    }
+#undef TSG_GOS
+    return check_launch("linear_fwd(small)");
+  }
   // output columns are produced in chunks of <= 128 (one float4 per lane, 32 lanes per row)
   for (int64_t m0 = 0; m0 < M; m0 += 128) {
     int64_t mc = M - m0 < 128 ? M - m0 : 128;
@@ -436,8 +572,12 @@ extern "C" int tsg_dense_epilogue_bwd(const float* X, const float* W, const floa
   return check_launch("dense_epilogue_bwd");
 }
 
+extern "C" size_t tsg_colsum_workspace_bytes(int64_t N, int64_t F);
+extern "C" int tsg_relu_bwd_colsum(const float* dY, const float* Y, float* dYm, float* dbias, int64_t N,
+                                   int64_t F, void* workspace, size_t workspace_bytes, void* stream);
+
 extern "C" size_t tsg_linear_bwd_weight_workspace_bytes(int64_t K, int64_t M) {
-  return ws_bytes((size_t)LBW_GRID * (size_t)(K + 1) * (size_t)M, 4) + 256;
+  return ws_bytes((size_t)LBW_GRID * (size_t)K * (size_t)M, 4) + tsg_colsum_workspace_bytes(1 << 30, M) + 512;
 }
 
 extern "C" int tsg_linear_bwd_weight(const float* X, const float* dY, float* dW, float* db,
@@ -445,23 +585,53 @@ extern "C" int tsg_linear_bwd_weight(const float* X, const float* dY, float* dW,
                                      void* workspace, size_t workspace_bytes, void* stream) {
   TSG_REQUIRE(N >= 0 && K > 0 && M > 0, "linear_bwd_weight: bad shape");
   TSG_REQUIRE(X && dY && (dW || db), "linear_bwd_weight: null pointer");
+  TSG_REQUIRE(N < (int64_t)0x7fffffff, "linear_bwd_weight: too many rows");
   if (workspace_bytes < tsg_linear_bwd_weight_workspace_bytes(K, M)) { set_error("linear_bwd_weight: workspace too small"); return TSG_EWORKSPACE; }
   cudaStream_t st = (cudaStream_t)stream;
-  float* part = (float*)workspace;
-  int Mp = (int)((M + 31) / 32 * 32), mch = Mp / 32;
-  int total_units = (int)(K + 1) * mch;
-  int units = total_units < LIN_THREADS ? total_units : LIN_THREADS;
-  int row_groups = LIN_THREADS / units; if (row_groups < 1) row_groups = 1;
-  if (row_groups > LBW_ROWS) row_groups = LBW_ROWS;
-  size_t smem_tile = ((size_t)LBW_ROWS * ((int)K | 1) + (size_t)LBW_ROWS * Mp) * sizeof(float);
-  size_t smem_red = (size_t)units * 32 * sizeof(float);
-  size_t smem = smem_tile > smem_red ? smem_tile : smem_red;
-  int rc = set_smem(k_linear_bwd_weight, smem, "linear_bwd_weight"); if (rc) return rc;
-  int tiles = (int)((N + LBW_ROWS - 1) / LBW_ROWS);
+  Workspace ws(workspace, workspace_bytes);
+  float* part = ws.take<float>((size_t)LBW_GRID * K * M);
+  size_t cs_bytes = tsg_colsum_workspace_bytes(1 << 30, M);
+  char* cs_ws = ws.take<char>(cs_bytes);
+  if (db) {
+    int rc = tsg_relu_bwd_colsum(dY, nullptr, nullptr, db, N, M, cs_ws, cs_bytes, stream);
+    if (rc) return rc;
+  }
+  if (!dW) return TSG_OK;
+  if (M <= 4 && (K & 3) == 0 && K <= 128 && (((uintptr_t)X) & 15) == 0) {                 // GEMV-shaped
+    int lpr = 1; while (lpr * 4 < K) lpr <<= 1;
+    int groups = 256 / lpr;
+    size_t smem_s = (size_t)groups * K * M * sizeof(float);
+    if (smem_s <= 200 * 1024) {
+      int grid = LBW_GRID;
+#define TSG_GOS(L)                                                                                          \
+      { int rc = set_smem(k_linear_bwd_weight_small<L>, smem_s, "linear_bwd_weight(small)"); if (rc) return rc; \
+        k_linear_bwd_weight_small<L><<<grid, 256, smem_s, st>>>(X, dY, part, (int)N, (int)K, (int)M); }
+      switch (lpr) {
+        case 1: TSG_GOS(1) break; case 2: TSG_GOS(2) break; case 4: TSG_GOS(4) break;
+        case 8: TSG_GOS(8) break; case 16: TSG_GOS(16) break; default: TSG_GOS(32) break;
+      }
+#undef TSG_GOS
+      launch_partial_sum_final(part, dW, (int)(K * M), nullptr, grid, (int)(K * M), st);
+      return check_launch("linear_bwd_weight(small)");
+    }
+  }
+  TSG_REQUIRE(K <= 256, "linear_bwd_weight: in_feat %lld > 256 not supported", (long long)K);
+  int nk = (int)((K + 31) / 32);
+  int nwarps = 8;
+  while (nwarps > 1 && (size_t)nwarps * K * 32 * 4 > 200 * 1024) --nwarps;
+  size_t smem = (size_t)nwarps * K * 32 * sizeof(float);
   int grid = LBW_GRID;                       // fixed => the summation order never depends on the device
-  (void)tiles;
-  k_linear_bwd_weight<<<grid, LIN_THREADS, smem, st>>>(X, dY, part, (int)N, (int)K, (int)M, units, row_groups);
-  int total = (int)((K + 1) * M);
-  launch_partial_sum_final(part, dW, (int)(K * M), db, grid, total, st);
+  for (int m0 = 0; m0 < M; m0 += 32) {
+#define TSG_GO(NK_, U_)                                                                                    \
+    { int rc = set_smem(k_linear_bwd_weight<NK_, U_>, smem, "linear_bwd_weight"); if (rc) return rc;         \
+      k_linear_bwd_weight<NK_, U_><<<grid, nwarps * 32, smem, st>>>(X, dY, part, (int)N, (int)K, (int)M, m0); }
+    switch (nk) {
+      case 1: TSG_GO(1, 8); break; case 2: TSG_GO(2, 8); break; case 3: TSG_GO(3, 4); break;
+      case 4: TSG_GO(4, 4); break; case 5: TSG_GO(5, 2); break; case 6: TSG_GO(6, 2); break;
+      case 7: TSG_GO(7, 2); break; default: TSG_GO(8, 2); break;
+    }
+#undef TSG_GO
+  }
+  launch_partial_sum_final(part, dW, (int)(K * M), nullptr, grid, (int)(K * M), st);
   return check_launch("linear_bwd_weight");
 }

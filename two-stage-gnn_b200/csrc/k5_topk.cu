@@ -159,6 +159,38 @@ k_gate_gather_fwd(const float* __restrict__ x, const float* __restrict__ score,
   }
 }
 
+// float4 variant: LPR = F/4 lanes per node (8 lanes at F = 32 => 4 nodes per warp, 128-bit accesses)
+template <int LPR>
+__global__ void __launch_bounds__(256)
+k_gate_gather_bwd_v4(const float4* __restrict__ dxo, const float4* __restrict__ x,
+                     const float* __restrict__ score, const int* __restrict__ inv,
+                     float4* __restrict__ dx, float* __restrict__ dscore, int64_t N, int F4) {
+  const int l = threadIdx.x % LPR;
+  const int64_t groups = ((int64_t)gridDim.x * blockDim.x) / LPR;
+  const int64_t first = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
+  const int64_t iters = (N + groups - 1) / groups;                  // uniform trip count (shuffles below)
+  for (int64_t it = 0; it < iters; ++it) {
+    const int64_t j = first + it * groups;
+    const bool ok = j < N;
+    const int m = ok ? inv[j] : -1;
+    float t = 0.f, dot = 0.f;
+    if (m >= 0) t = tanhf(score[j]);
+    for (int f = l; f < F4; f += LPR) {
+      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m >= 0) {
+        const float4 go = __ldg(dxo + (int64_t)m * F4 + f);
+        const float4 xv = __ldg(x + j * F4 + f);
+        dot += go.x * xv.x + go.y * xv.y + go.z * xv.z + go.w * xv.w;
+        g = make_float4(go.x * t, go.y * t, go.z * t, go.w * t);
+      }
+      if (ok) dx[j * F4 + f] = g;
+    }
+#pragma unroll
+    for (int d = LPR / 2; d > 0; d >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, d, LPR);
+    if (ok && l == 0) dscore[j] = m >= 0 ? dot * (1.f - t * t) : 0.f;
+  }
+}
+
 // one group of LPR lanes per source node j; writes every row of dx (zeros for dropped nodes)
 template <int LPR>
 __global__ void __launch_bounds__(256)
@@ -275,6 +307,18 @@ extern "C" int tsg_gate_gather_bwd(const float* dxo, const float* x, const float
   if (N == 0) return TSG_OK;
   TSG_REQUIRE(dxo && x && score && inv && dx && dscore, "gate_gather_bwd: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
+  if (F % 4 == 0 && ((((uintptr_t)dxo) | ((uintptr_t)x) | ((uintptr_t)dx)) & 15) == 0) {
+    int F4 = (int)(F / 4);
+    int lp = 1; while (lp < F4 && lp < 32) lp <<= 1;
+    int gr = grid_for(N, 256 / lp, 16);
+#define TSG_GV(L) k_gate_gather_bwd_v4<L><<<gr, 256, 0, st>>>((const float4*)dxo, (const float4*)x, score, inv, (float4*)dx, dscore, N, F4)
+    switch (lp) {
+      case 1: TSG_GV(1); break; case 2: TSG_GV(2); break; case 4: TSG_GV(4); break;
+      case 8: TSG_GV(8); break; case 16: TSG_GV(16); break; default: TSG_GV(32); break;
+    }
+#undef TSG_GV
+    return check_launch("gate_gather_bwd");
+  }
   int lpr = 1; while (lpr < F && lpr < 32) lpr <<= 1;
   int grid = grid_for(N, 256 / lpr);
 #define TSG_GO(L) k_gate_gather_bwd<L><<<grid, 256, 0, st>>>(dxo, x, score, inv, dx, dscore, N, (int)F)

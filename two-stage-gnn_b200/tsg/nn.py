@@ -129,12 +129,16 @@ class PackedSAGNet(torch.nn.Module):
         edges = edge_index if isinstance(edge_index, EdgeList) else EdgeList.from_edge_index(edge_index)
         plan = host_level_ptrs(np.asarray(node_ptr_host), self.pooling_ratio)
         ptrs = torch.from_numpy(plan).pin_memory().to(dev, non_blocking=True)
+        # K2 shared-memory tiles: runs of whole graphs per pooling level (block-diagonal => self-contained)
+        tiles = ([torch.from_numpy(ops.make_tiles(plan[l])).pin_memory().to(dev, non_blocking=True)
+                  for l in range(3)] if ops.USE_TILED_SPMM else [None] * 3)
         aux = {"perm": [], "edges": [], "score": []}
         outs = []
         for lvl, (conv, pool) in enumerate(((self.conv1, self.pool1), (self.conv2, self.pool2),
                                             (self.conv3, self.pool3))):
             n_l, k_l = int(plan[lvl, -1]), int(plan[lvl + 1, -1])
             csr = ops.build_csr(edges, n_l)
+            csr.tile_ptr = tiles[lvl]
             h = conv(x, csr, relu=True)                                   # network.py:34
             score = pool.score_layer(h, csr).view(-1)                     # layers.py:18
             perm = ops.topk(score, ptrs[lvl], ptrs[lvl + 1], k_l)         # layers.py:20

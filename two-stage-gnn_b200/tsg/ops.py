@@ -16,6 +16,7 @@ from . import _lib
 from ._lib import call, ptr, stream_ptr, workspace, lib
 
 CSR_GCN, CSR_RAW = 0, 1
+USE_TILED_SPMM = False   # shared-memory-staged K2 (tsg_spmm_tiled); measured slower than the L1-blocked kernel
 SPMM_RELU = 1
 READOUT_MAX, READOUT_MEAN, READOUT_SUM = 1, 2, 4
 LIN_NORMALIZE, LIN_RELU, LIN_NODEBN = 1, 2, 4
@@ -57,6 +58,7 @@ class CSR:
     t_val: Optional[torch.Tensor]
     t_eid: Optional[torch.Tensor]
     num_nodes: int
+    tile_ptr: Optional[torch.Tensor] = None     # int64 [T+1]: self-contained row runs (whole graphs)
 
 
 def build_csr(edges: EdgeList, num_nodes: int, mode: int = CSR_GCN, transposed: bool = True,
@@ -86,13 +88,34 @@ def build_csr(edges: EdgeList, num_nodes: int, mode: int = CSR_GCN, transposed: 
     return CSR(rowptr, colidx, val, eid, t_rowptr, t_colidx, t_val, t_eid, N)
 
 
-def spmm_raw(rowptr, colidx, val, H: torch.Tensor, bias=None, relu: bool = False) -> torch.Tensor:
+def spmm_raw(rowptr, colidx, val, H: torch.Tensor, bias=None, relu: bool = False,
+             tile_ptr: Optional[torch.Tensor] = None) -> torch.Tensor:
     n = rowptr.numel() - 1
     H = H.contiguous()
     Y = torch.empty(n, H.size(1), dtype=torch.float32, device=H.device)
-    call("tsg_spmm", ptr(rowptr), ptr(colidx), ptr(val), ptr(H), ptr(bias), ptr(Y), n, H.size(1),
-         SPMM_RELU if relu else 0, stream_ptr())
+    if USE_TILED_SPMM and tile_ptr is not None and H.size(1) % 4 == 0:
+        call("tsg_spmm_tiled", ptr(rowptr), ptr(colidx), ptr(val), ptr(H), ptr(bias), ptr(Y), ptr(tile_ptr),
+             tile_ptr.numel() - 1, n, H.size(1), SPMM_RELU if relu else 0, stream_ptr())
+    else:
+        call("tsg_spmm", ptr(rowptr), ptr(colidx), ptr(val), ptr(H), ptr(bias), ptr(Y), n, H.size(1),
+             SPMM_RELU if relu else 0, stream_ptr())
     return Y
+
+
+def make_tiles(node_ptr_host, max_rows: int = 512):
+    """Greedy host-side tiling of a packed level: consecutive whole graphs per tile while the tile stays
+    <= max_rows rows (a larger graph is its own tile and takes the kernel's global-gather path).
+    Returns int64 numpy offsets [T+1]."""
+    import numpy as np
+    ptr_ = np.asarray(node_ptr_host, dtype=np.int64)
+    out = [0]
+    start = 0
+    for g in range(1, ptr_.shape[0]):
+        if ptr_[g] - start > max_rows and ptr_[g - 1] > start:
+            out.append(int(ptr_[g - 1])); start = int(ptr_[g - 1])
+    if ptr_[-1] > out[-1] or len(out) == 1:
+        out.append(int(ptr_[-1]))
+    return np.asarray(out, dtype=np.int64)
 
 
 def relu_bwd_colsum(dY: torch.Tensor, Y: Optional[torch.Tensor], want_masked: bool):
@@ -112,7 +135,7 @@ class _SpMM(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, H, bias, csr: CSR, relu: bool):
-        Y = spmm_raw(csr.rowptr, csr.colidx, csr.val, H, bias, relu)
+        Y = spmm_raw(csr.rowptr, csr.colidx, csr.val, H, bias, relu, csr.tile_ptr)
         ctx.csr, ctx.relu, ctx.has_bias = csr, relu, bias is not None
         ctx.save_for_backward(Y if relu else None)
         return Y
@@ -131,7 +154,8 @@ class _SpMM(torch.autograd.Function):
                 dY = dYm
             if not ctx.has_bias:
                 db = None
-        dH = spmm_raw(csr.t_rowptr, csr.t_colidx, csr.t_val, dY) if ctx.needs_input_grad[0] else None
+        dH = (spmm_raw(csr.t_rowptr, csr.t_colidx, csr.t_val, dY, tile_ptr=csr.tile_ptr)
+              if ctx.needs_input_grad[0] else None)
         return dH, db, None, None
 
 
