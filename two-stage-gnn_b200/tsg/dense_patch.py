@@ -1,0 +1,124 @@
+"""B2 drop-in surface: replacements for the methods of the classes DEFINED INSIDE the
+reference's dense script directories, installed by patching the imported modules (files untouched):
+
+    encoders.GraphConv.forward(self, x[B,N,F], adj[B,N,N])          -> K2 + K3
+    encoders.GcnEncoderGraph.apply_bn(self, x[B,N,F])               -> node-wise BN kernel
+    encoders_GAT.DGATHead.forward(self, input[B,N,F], adj[B,N,N])   -> K4
+    eigengcn encoders.Pool.forward(self, x[B,N,D])                   -> K8 (K2 on P^T)
+
+These keep the reference's dense, zero-padded WIRE FORMAT (every one of the B*N rows is a row of the
+operator; padded rows simply have empty adjacency rows, which reproduces the "virtual padded node"
+and the GAT uniform-1/N columns without special cases) but never multiply an N x N dense matrix: the
+adjacency is converted once to CSR (cached per tensor, graphs are static) and aggregated sparsely.
+The packed modules in tsg.dense / tsg.gat / tsg.diffpool are the throughput path; this file is the
+"scripts run unchanged" path.
+"""
+from __future__ import annotations
+
+from typing import Dict, Tuple
+
+import torch
+import torch.nn.functional as F
+
+from . import dense, ops
+from .gat import _GatAggregate
+from .ops import CSR, LIN_NORMALIZE
+
+
+class _DenseCsrCache:
+    """adjacency tensor -> CSR over all B*N rows.  Keyed on the tensor object + version + options;
+    the tensor is held alive so its storage cannot be recycled under the key."""
+
+    def __init__(self, slots: int = 16):
+        self.slots, self.items = slots, []
+
+    def get(self, mat: torch.Tensor, transpose: bool = False, want_eid: bool = False) -> CSR:
+        for m, ver, tr, we, csr in self.items:
+            if m is mat and ver == mat._version and tr == transpose and (we or not want_eid):
+                return csr
+        B, R, C = mat.shape
+        csr, _, _ = dense.dense_to_csr(mat, [R] * B, [C] * B, transpose=transpose, packed=False, want_eid=want_eid)
+        self.items.append((mat, mat._version, transpose, want_eid, csr))
+        if len(self.items) > self.slots:
+            self.items.pop(0)
+        return csr
+
+
+CACHE = _DenseCsrCache()
+
+
+def _as_cuda_f32(t: torch.Tensor) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError("tsg dense drop-ins need CUDA tensors (there is no CPU path)")
+    return t if t.dtype == torch.float32 else t.float()
+
+
+def graphconv_forward(self, x: torch.Tensor, adj: torch.Tensor) -> torch.Tensor:
+    """Code/sage+gat+diffpool/encoders.py:30-42 (== Code/eigengcn/encoders.py:28-41)."""
+    x, adj = _as_cuda_f32(x), _as_cuda_f32(adj)
+    if getattr(self, "dropout", 0.0) > 0.001:
+        x = self.dropout_layer(x)
+    B, N, Fi = x.shape
+    csr = CACHE.get(adj)
+    xf = x.reshape(B * N, Fi)
+    y = ops.spmm(csr, xf)
+    if self.add_self:
+        y = y + xf
+    out = ops.linear(y, self.weight, self.bias, LIN_NORMALIZE if self.normalize_embedding else 0)
+    return out.view(B, N, -1)
+
+
+def apply_bn(self, x: torch.Tensor) -> torch.Tensor:
+    """encoders.py:134-138."""
+    return dense.node_bn(_as_cuda_f32(x))
+
+
+def dgathead_forward(self, input: torch.Tensor, adj: torch.Tensor) -> torch.Tensor:
+    """Code/sage+gat+diffpool/encoders_GAT.py:29-49.  Only input[0] is used upstream (:32); adj
+    [1,N,N] broadcasts, so the softmax runs over rows i for every column j (:41-43)."""
+    x, adj = _as_cuda_f32(input)[0], _as_cuda_f32(adj)[:1]
+    N = x.size(0)
+    Fo = self.output_dim
+    csr = CACHE.get(adj, want_eid=True)
+    h = ops.linear(x, self.w)
+    s1 = h @ self.a[:Fo, 0]
+    s2 = h @ self.a[Fo:, 0]
+    raw = _GatAggregate.apply(h, s1.view(-1, 1), s2.view(-1, 1), csr, 1, Fo, float(self.leakyRELU_neg_input_slope))
+    # columns without any edge are uniform 1/N over all N rows upstream and add h_j / N to every row
+    iso = ((csr.t_rowptr[1:] - csr.t_rowptr[:-1]) == 0).to(h.dtype)
+    corr = (h * iso.view(-1, 1)).sum(0, keepdim=True) / float(N)
+    hp = (raw + corr).unsqueeze(0)
+    if getattr(self, "dropout", 0.0) and self.training and self.dropout > 0:
+        raise NotImplementedError("attention dropout > 0 is not supported by the fused kernel")
+    return F.elu(hp) if self.concat else hp
+
+
+def pool_forward(self, x: torch.Tensor) -> torch.Tensor:
+    """Code/eigengcn/encoders.py:396-417: X_j = P_j^T X, concatenated on the feature axis."""
+    x = _as_cuda_f32(x)
+    B, N, D = x.shape
+    xf = x.reshape(B * N, D)
+    res = []
+    for i in range(self.num_pool):
+        pm = _as_cuda_f32(self.pool_matrices[i])
+        res.append(ops.spmm(CACHE.get(pm, transpose=True), xf).view(B, N, D))
+    return torch.cat(res, 2) if len(res) > 1 else res[0]
+
+
+def install(encoders=None, encoders_gat=None, eigen_encoders=None) -> Dict[str, Tuple[object, str]]:
+    """Patch the imported reference modules in place; returns what was patched."""
+    done = {}
+    if encoders is not None:
+        encoders.GraphConv.forward = graphconv_forward
+        encoders.GcnEncoderGraph.apply_bn = apply_bn
+        done["GraphConv.forward"] = (encoders, "K2+K3")
+        done["GcnEncoderGraph.apply_bn"] = (encoders, "nodebn")
+    if encoders_gat is not None:
+        encoders_gat.DGATHead.forward = dgathead_forward
+        done["DGATHead.forward"] = (encoders_gat, "K4")
+    if eigen_encoders is not None:
+        eigen_encoders.GraphConv.forward = graphconv_forward
+        eigen_encoders.GcnEncoderGraph.apply_bn = apply_bn
+        eigen_encoders.Pool.forward = pool_forward
+        done["Pool.forward"] = (eigen_encoders, "K8")
+    return done

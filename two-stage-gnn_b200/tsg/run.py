@@ -47,12 +47,30 @@ def install(script_dir: str | None = None) -> None:
         pass
 
 
+def patch_dense_modules(script_dir: str):
+    """B2: pre-import the script directory's `encoders` / `encoders_GAT` modules (they then sit in
+    sys.modules for the script's own imports) and swap the hot methods for the tsg drop-ins."""
+    import importlib
+    from . import dense_patch
+    done = {}
+    if os.path.exists(os.path.join(script_dir, "encoders.py")):
+        enc = importlib.import_module("encoders")
+        if hasattr(enc, "Pool"):
+            done.update(dense_patch.install(eigen_encoders=enc))
+        else:
+            done.update(dense_patch.install(encoders=enc))
+    if os.path.exists(os.path.join(script_dir, "encoders_GAT.py")):
+        done.update(dense_patch.install(encoders_gat=importlib.import_module("encoders_GAT")))
+    return done
+
+
 def main(argv=None) -> None:
     argv = list(sys.argv[1:] if argv is None else argv)
     if not argv:
         raise SystemExit("usage: python -m tsg.run <reference script.py> [script args...]")
     script = os.path.abspath(argv[0])
     install(os.path.dirname(script))
+    patch_dense_modules(os.path.dirname(script))
     sys.argv = [script] + argv[1:]
     os.chdir(os.path.dirname(script)) if os.access(os.path.dirname(script), os.W_OK) else None
     runpy.run_path(script, run_name="__main__")
