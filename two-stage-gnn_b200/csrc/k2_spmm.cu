@@ -15,6 +15,7 @@
 //   * neighbours of a row live in the same small graph block, so the gathers hit L1/L2 and DRAM
 //     sees ~compulsory traffic (H once, Y once, CSR once);
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace tsg {
 
@@ -70,6 +71,69 @@ k_spmm_vec4(const int* __restrict__ rowptr, const int* __restrict__ colidx,
         acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f);
       }
       Y[(int64_t)r * F4 + f] = acc;
+    }
+  }
+}
+
+// Cooperative variant for F4 <= LPR (one float4 per lane): the LPR lanes of a row fetch up to NB
+// (colidx, val) pairs with one coalesced request, broadcast them with width-LPR shuffles, and issue ALL
+// H gathers of the batch back to back (volatile asm keeps ptxas from re-serialising them) before the
+// sequential accumulation.  Dependent chain per row: rowptr -> colidx -> H.  Same arithmetic order.
+__device__ __forceinline__ float4 ldg_nc_v4(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+
+template <int LPR, bool HAS_VAL>
+__global__ void __launch_bounds__(SPMM_THREADS)
+k_spmm_coop(const int* __restrict__ rowptr, const int* __restrict__ colidx,
+            const float* __restrict__ val, const float4* __restrict__ H,
+            const float4* __restrict__ bias, float4* __restrict__ Y,
+            int num_rows, int F4, int relu) {
+  constexpr int NB = LPR < 8 ? LPR : 8;
+  const int l = threadIdx.x % LPR;
+  const int rpc = (num_rows + gridDim.x - 1) / gridDim.x;
+  const int r_begin = blockIdx.x * rpc;
+  const int r_end = min(num_rows, r_begin + rpc);
+  const int iters = (r_end - r_begin + SPMM_THREADS / LPR - 1) / (SPMM_THREADS / LPR);
+  const bool fok = l < F4;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int it = 0; it < iters; ++it) {
+    const int r = r_begin + it * (SPMM_THREADS / LPR) + threadIdx.x / LPR;
+    const bool rok = r < r_end;
+    const int s = rok ? __ldg(rowptr + r) : 0, t = rok ? __ldg(rowptr + r + 1) : 0;
+    float4 acc = zero4;
+    for (int p0 = s; __any_sync(0xffffffffu, p0 < t); p0 += NB) {
+      int myc = 0; float myv = 1.f;
+      if (l < NB && p0 + l < t) {
+        myc = __ldg(colidx + p0 + l);
+        if (HAS_VAL) myv = __ldg(val + p0 + l);
+      }
+      float4 h[NB];
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        const int c = __shfl_sync(0xffffffffu, myc, j, LPR);
+        // out-of-range slots gather row c = 0 (always valid memory) and are masked below
+        h[j] = fok ? ldg_nc_v4(H + (int64_t)c * F4 + l) : zero4;
+      }
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        const float v = __shfl_sync(0xffffffffu, myv, j, LPR);
+        if (p0 + j < t) {
+          acc.x = __fadd_rn(acc.x, __fmul_rn(v, h[j].x)); acc.y = __fadd_rn(acc.y, __fmul_rn(v, h[j].y));
+          acc.z = __fadd_rn(acc.z, __fmul_rn(v, h[j].z)); acc.w = __fadd_rn(acc.w, __fmul_rn(v, h[j].w));
+        }
+      }
+    }
+    if (rok && fok) {
+      if (bias != nullptr) {
+        float4 b = __ldg(bias + l);
+        acc.x = __fadd_rn(acc.x, b.x); acc.y = __fadd_rn(acc.y, b.y);
+        acc.z = __fadd_rn(acc.z, b.z); acc.w = __fadd_rn(acc.w, b.w);
+      }
+      if (relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
+      Y[(int64_t)r * F4 + l] = acc;
     }
   }
 }
@@ -246,10 +310,16 @@ static int launch_spmm(const int* rowptr, const int* colidx, const float* val, c
     int rows_per_block = SPMM_THREADS / lpr;
     int grid = grid_for(N, rows_per_block, 32);
 #define TSG_GO(L) k_spmm_vec4<L, HAS_VAL><<<grid, SPMM_THREADS, 0, st>>>(rowptr, colidx, val, (const float4*)H, (const float4*)bias, (float4*)Y, (int)N, F4, relu)
+#define TSG_GC(L) k_spmm_coop<L, HAS_VAL><<<grid, SPMM_THREADS, 0, st>>>(rowptr, colidx, val, (const float4*)H, (const float4*)bias, (float4*)Y, (int)N, F4, relu)
+    static const bool coop = getenv("TSG_SPMM_COOP") != nullptr;
+    if (coop && F4 <= lpr && lpr >= 8) {
+      switch (lpr) { case 8: TSG_GC(8); break; case 16: TSG_GC(16); break; default: TSG_GC(32); break; }
+    } else
     switch (lpr) {
       case 1: TSG_GO(1); break; case 2: TSG_GO(2); break; case 4: TSG_GO(4); break;
       case 8: TSG_GO(8); break; case 16: TSG_GO(16); break; default: TSG_GO(32); break;
     }
+#undef TSG_GC
 #undef TSG_GO
   } else {
     int lpr = 1; while (lpr < F && lpr < 32) lpr <<= 1;

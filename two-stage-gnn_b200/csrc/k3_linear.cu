@@ -33,18 +33,44 @@ __device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N_> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N_) : "memory"); }
 
-// asynchronously stage rows [r0, r0+R) of X[N,K] into Xs[R][pitch] (rows past N are zero filled);
-// warp w copies rows w, w+8, ..., lanes run along K so every global request is a contiguous run.
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(s), "l"(gsrc) : "memory");
+}
+
+// shared-memory row pitch: odd K needs no padding (odd stride = conflict free) and lets a tile be copied
+// as ONE contiguous 16-byte stream; K % 4 == 0 pads by 4 floats so every row stays 16-byte aligned.
+__host__ __device__ __forceinline__ int lin_pitch(int K) { return (K & 1) ? K : ((K & 3) == 0 ? K + 4 : K + 1); }
+
+// asynchronously stage rows [r0, r0+R) of X[N,K] into Xs[R][pitch] (rows past N are zero filled)
 __device__ __forceinline__ void stage_rows_async(float* Xs, const float* __restrict__ X, int r0, int R,
                                                  int N, int K, int pitch) {
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int r = w; r < R; r += LIN_THREADS / 32) {
-    float* dst = Xs + r * pitch;
-    if (r0 + r < N) {
-      const float* src = X + (size_t)(r0 + r) * K;
-      for (int k = lane; k < K; k += 32) cp_async4(dst + k, src + k);
-    } else {
-      for (int k = lane; k < K; k += 32) dst[k] = 0.f;
+  const int rows = min(R, N - r0);
+  const bool base16 = ((((size_t)(X + (size_t)r0 * K)) & 15) == 0);
+  if (pitch == K && base16) {                    // contiguous tile: 16-byte stream + scalar tail
+    const float* src = X + (size_t)r0 * K;
+    const int total = rows * K, total4 = total & ~3;
+    for (int i = threadIdx.x * 4; i < total4; i += LIN_THREADS * 4) cp_async16(Xs + i, src + i);
+    for (int i = total4 + threadIdx.x; i < total; i += LIN_THREADS) cp_async4(Xs + i, src + i);
+    for (int i = total + threadIdx.x; i < R * K; i += LIN_THREADS) Xs[i] = 0.f;
+  } else if ((K & 3) == 0 && base16) {           // 16-byte aligned rows, padded pitch
+    const int K4 = K >> 2;
+    for (int i = threadIdx.x; i < R * K4; i += LIN_THREADS) {
+      const int r = i / K4, k = (i - r * K4) * 4;
+      float* dst = Xs + r * pitch + k;
+      if (r < rows) cp_async16(dst, X + (size_t)(r0 + r) * K + k);
+      else { dst[0] = 0.f; dst[1] = 0.f; dst[2] = 0.f; dst[3] = 0.f; }
+    }
+  } else {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int r = w; r < R; r += LIN_THREADS / 32) {
+      float* dst = Xs + r * pitch;
+      if (r < rows) {
+        const float* src = X + (size_t)(r0 + r) * K;
+        for (int k = lane; k < K; k += 32) cp_async4(dst + k, src + k);
+      } else {
+        for (int k = lane; k < K; k += 32) dst[k] = 0.f;
+      }
     }
   }
   cp_async_commit();
@@ -99,7 +125,7 @@ k_linear_fwd(const float* __restrict__ X, const float* __restrict__ W, const flo
   constexpr int RS = LIN_THREADS / CG;
   constexpr int R = RS * LIN_RPT;
   const int Mp = CG * 4;
-  const int pitch = K | 1;                       // odd pitch: rows of a warp hit distinct banks
+  const int pitch = lin_pitch(K);
   float* Ws = smem;                              // [K][Mp]
   float* Xs = smem + (size_t)K * Mp;             // [R][pitch]
   const int cg = threadIdx.x % CG, rs = threadIdx.x / CG;
@@ -181,7 +207,7 @@ k_dense_epilogue_bwd(const float* __restrict__ X, const float* __restrict__ W, c
   constexpr int RS = LIN_THREADS / CG;
   constexpr int R = RS * LIN_RPT;
   const int Mp = CG * 4;
-  const int pitch = K | 1;
+  const int pitch = lin_pitch(K);
   float* Ws = smem;
   float* Xs = smem + (size_t)K * Mp;
   const int cg = threadIdx.x % CG, rs = threadIdx.x / CG;
@@ -482,13 +508,13 @@ k_linear_bwd_weight_small(const float* __restrict__ X, const float* __restrict__
 static int pick_cg(int64_t M, int64_t K) {
   int c = 1;
   while (c * 4 < M && c < 32) c <<= 1;
-  while (c < 32 && (size_t)(LIN_THREADS / c) * LIN_RPT * (size_t)(K | 1) * 4 > 64 * 1024) c <<= 1;
+  while (c < 32 && (size_t)(LIN_THREADS / c) * LIN_RPT * (size_t)lin_pitch((int)K) * 4 > 64 * 1024) c <<= 1;
   return c;
 }
 
 static size_t lin_smem_bytes(int cg, int64_t K) {
   int R = (LIN_THREADS / cg) * LIN_RPT;
-  return ((size_t)K * cg * 4 + 2 * (size_t)R * (K | 1)) * sizeof(float);      // W + two X tiles
+  return ((size_t)K * cg * 4 + 2 * (size_t)R * lin_pitch((int)K)) * sizeof(float);      // W + two X tiles
 }
 
 }  // namespace tsg
