@@ -46,6 +46,21 @@ const char* tsg_last_error(void);
 int tsg_check_device(void);
 
 /* ------------------------------------------------------------------------------------------
+ * K0  device-side batch assembly from an HBM-resident corpus
+ *   replaces PyG Batch.from_data_list (Code/sag/train.py:181) + the per-graph `.to(device)` /
+ *   `torch.Tensor([ndarray]).cuda()` marshaling of the triplet loops (Code/sag/train_triplet.py:207;
+ *   Code/sage+gat+diffpool/tripletnet.py:18-33).  Graph b of the batch is corpus graph ids[b]; its nodes
+ *   land at rows out_node_ptr[b].. of x_out (one-hot of c_label when given, else rows of c_x) and its
+ *   edges at out_edge_ptr[b].. of row_out/col_out with global (batch) node ids.  Offsets are computed by
+ *   the host from the graph sizes it already knows (no device round trip).
+ * ------------------------------------------------------------------------------------------ */
+int tsg_pack_batch(const int64_t* ids, const int64_t* out_node_ptr, const int64_t* out_edge_ptr,
+                   int64_t batch_graphs, const int64_t* corpus_node_ptr, const int64_t* corpus_edge_ptr,
+                   const int32_t* corpus_row, const int32_t* corpus_col,
+                   const int32_t* corpus_label /*nullable*/, const float* corpus_x /*nullable*/,
+                   int64_t feat, float* x_out, int64_t* row_out, int64_t* col_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * K1  CSR construction + GCN normalisation
  *   replaces: PyG GCNConv.norm / gcn_norm (add_remaining_self_loops, scatter_add degree,
  *   deg^-1/2 A deg^-1/2) as called from Code/sag/network.py:34,38,42 and Code/sag/layers.py:18.

@@ -396,3 +396,22 @@ def test_spmm_tiled_bit_exact(cuda, F):
     yt = ops.spmm_raw(csr.t_rowptr, csr.t_colidx, csr.t_val, h.to(cuda), tile_ptr=torch.from_numpy(tiles).to(cuda))
     assert torch.equal(yt.cpu(), ops.spmm_raw(csr.t_rowptr, csr.t_colidx, csr.t_val, h.to(cuda)).cpu())
     ops.USE_TILED_SPMM = False
+
+
+# ------------------------------------------------------------------ K0 device-side batch assembly
+def test_pack_batch_bit_exact(cuda):
+    """GPU batch assembly == host packer (PyG Batch layout), for repeated / out-of-order graph ids."""
+    from tsg.feeder import DeviceCorpus
+    c = synth.make_corpus("DD", 20, seed=9)
+    ids = np.array([3, 3, 0, 19, 7, 7, 7, 1], dtype=np.int64)
+    ref = synth.pack(c, ids)
+    dc = DeviceCorpus(c, cuda)
+    x, ei, nptr = dc.pack(ids)
+    assert np.array_equal(nptr, ref["node_ptr"])
+    assert torch.equal(x.cpu(), torch.from_numpy(ref["x"]))
+    assert torch.equal(ei.cpu(), torch.from_numpy(ref["edge_index"]))
+    dense = np.random.default_rng(0).standard_normal((int(c.node_ptr[-1]), 5)).astype(np.float32)
+    dc2 = DeviceCorpus(c, cuda, dense_x=dense)
+    x2, _, _ = dc2.pack(ids)
+    want = np.concatenate([dense[c.node_ptr[g]:c.node_ptr[g + 1]] for g in ids])
+    assert torch.equal(x2.cpu(), torch.from_numpy(want))

@@ -96,3 +96,10 @@ class TripletTrainer:
         ei = edge_index_host.to(device, non_blocking=True)
         tr = triplets_host.to(device, non_blocking=True)
         return float(self.step(x, ei, node_ptr_host, tr).item())
+
+    def step_from_ids(self, corpus, graph_ids_host: np.ndarray, triplets_host: torch.Tensor) -> float:
+        """End-to-end call against an HBM-resident corpus (tsg.feeder.DeviceCorpus): the host sends the
+        step's graph ids + triplet index list, the batch is assembled on the GPU, the loss is read back."""
+        x, ei, nptr = corpus.pack(graph_ids_host)
+        tr = triplets_host.to(corpus.device, non_blocking=True)
+        return float(self.step(x, ei, nptr, tr).item())
