@@ -85,17 +85,39 @@ int tsg_csr_build(const int64_t* row, const int64_t* col, const float* edge_weig
                   int32_t* t_eid /*nullable*/,
                   void* workspace, size_t workspace_bytes, void* stream);
 
+/* K1b: the same CSR (TSG_CSR_GCN, unit weights, both orientations) for a block-diagonal packed batch
+ * whose edge list keeps every graph's edges contiguous (PyG Batch.from_data_list; the
+ * order-preserving filter_adj keeps it true at every pooling level).  One CTA per graph, counting /
+ * slot claim / rank-in-row placement in shared memory: bit-identical to tsg_csr_build.
+ *   tsg_edge_ptr: edge_ptr[g] = first edge whose source row >= node_ptr[g] (int64 [G+1], device).
+ *   max_graph_nodes: host-side upper bound over the graphs of the batch (sizes the shared-memory
+ *   arrays; TSG_EINVAL if a graph cannot fit, caller then uses tsg_csr_build).  The bound is the
+ *   caller's contract (the packer knows every graph's size; pooling only shrinks graphs); a graph that
+ *   violates it at run time traps the kernel (loud failure, no corruption). */
+int tsg_edge_ptr(const int64_t* row, int64_t num_edges, const int64_t* num_edges_dev /*nullable*/,
+                 const int64_t* node_ptr, int64_t num_graphs, int64_t* edge_ptr, void* stream);
+size_t tsg_csr_build_graphs_workspace_bytes(int64_t num_graphs, int64_t num_edges_cap);
+int tsg_csr_build_graphs(const int64_t* row, const int64_t* col, const int64_t* edge_ptr,
+                         const int64_t* node_ptr, int64_t num_graphs, int64_t num_nodes,
+                         int64_t num_edges_cap, int64_t max_graph_nodes,
+                         int32_t* rowptr, int32_t* colidx, float* val, int32_t* eid /*nullable*/,
+                         int32_t* t_rowptr /*nullable*/, int32_t* t_colidx, float* t_val,
+                         int32_t* t_eid /*nullable*/,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * K2  CSR segment-sum SpMM:  Y[r,:] = sum_p val[p] * H[colidx[p],:]  (+ bias) (ReLU optional)
  *   replaces: the gather / mul / scatter_add of PyG GCNConv.propagate (Code/sag/network.py:34)
  *   and `torch.matmul(adj, x)` of the dense GraphConv (Code/sage+gat+diffpool/encoders.py:33,
- *   Code/eigengcn/encoders.py:31).  Per-row accumulation is sequential in CSR order with the
- *   product rounded before the add, so it is bit-identical to index_add_ in COO order.
+ *   Code/eigengcn/encoders.py:31).  Per-row accumulation is sequential in CSR order (deterministic,
+ *   launch-geometry independent); with TSG_SPMM_EXACT the product is rounded before the add, which
+ *   is bit-identical to index_add_ in COO order; without it the product is fused (FFMA).
  *   The backward (dH = A^T dY) is the same call on the src-major CSR.
  *   flags: TSG_SPMM_RELU applies max(.,0) after the bias; relu_mask (nullable, uint8 [N,F]) is
  *   not needed because ReLU's backward is recomputed from Y > 0.
  * ------------------------------------------------------------------------------------------ */
 #define TSG_SPMM_RELU 1
+#define TSG_SPMM_EXACT 2 /* round every product before the add: bit-identical to index_add_ in COO order (default fuses: <= 1 ulp/term) */
 int tsg_spmm(const int32_t* rowptr, const int32_t* colidx, const float* val /*nullable => 1*/,
              const float* H, const float* bias /*nullable*/, float* Y,
              int64_t num_rows, int64_t feat, int flags, void* stream);

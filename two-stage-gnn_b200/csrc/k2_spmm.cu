@@ -4,16 +4,18 @@
 // 38,42; Code/sag/layers.py:18) and torch.matmul(adj, x) of the dense GraphConv
 // (Code/sage+gat+diffpool/encoders.py:33; Code/eigengcn/encoders.py:31) on a block-diagonal CSR.
 //
-// HBM-bound gather kernel, no tensor cores (AI ~ 0.5 flop/B).  Design:
+// Gather kernel, no tensor cores (AI ~ 0.5 flop/B).  Common design of every variant below:
 //   * a group of LPR lanes owns one destination row; each lane carries 4 consecutive features in
 //     a float4 (128-bit loads/stores); LPR = F/4 rounded up to a power of two (8 lanes at F=32, 32
 //     lanes at F=128) so one warp covers 32/LPR rows and every gathered row is one or more
 //     fully-used 128-byte lines;
-//   * the per-row loop is sequential in CSR order with the product rounded before the add
-//     (__fmul_rn / __fadd_rn, no FMA contraction): bit-identical to index_add_ in COO order and
-//     independent of the launch geometry; loads are issued 4 neighbours ahead for MLP;
+//   * the per-row loop is sequential in CSR order: deterministic, independent of the launch geometry;
+//     with TSG_SPMM_EXACT the product is rounded before the add (__fmul_rn / __fadd_rn), which is
+//     bit-identical to index_add_ in COO order;
 //   * neighbours of a row live in the same small graph block, so the gathers hit L1/L2 and DRAM
-//     sees ~compulsory traffic (H once, Y once, CSR once);
+//     sees ~compulsory traffic (H once, Y once, CSR once).
+// k_spmm_g is the production kernel; k_spmm_vec4 (round-1 first cut) stays as the legacy baseline the
+// profiles compare against (TSG_SPMM_LEGACY=1); k_spmm_scalar serves widths that are not multiples of 4.
 #include "common.cuh"
 #include <stdlib.h>
 
@@ -71,69 +73,6 @@ k_spmm_vec4(const int* __restrict__ rowptr, const int* __restrict__ colidx,
         acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f);
       }
       Y[(int64_t)r * F4 + f] = acc;
-    }
-  }
-}
-
-// Cooperative variant for F4 <= LPR (one float4 per lane): the LPR lanes of a row fetch up to NB
-// (colidx, val) pairs with one coalesced request, broadcast them with width-LPR shuffles, and issue ALL
-// H gathers of the batch back to back (volatile asm keeps ptxas from re-serialising them) before the
-// sequential accumulation.  Dependent chain per row: rowptr -> colidx -> H.  Same arithmetic order.
-__device__ __forceinline__ float4 ldg_nc_v4(const float4* p) {
-  float4 r;
-  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
-  return r;
-}
-
-template <int LPR, bool HAS_VAL>
-__global__ void __launch_bounds__(SPMM_THREADS)
-k_spmm_coop(const int* __restrict__ rowptr, const int* __restrict__ colidx,
-            const float* __restrict__ val, const float4* __restrict__ H,
-            const float4* __restrict__ bias, float4* __restrict__ Y,
-            int num_rows, int F4, int relu) {
-  constexpr int NB = LPR < 8 ? LPR : 8;
-  const int l = threadIdx.x % LPR;
-  const int rpc = (num_rows + gridDim.x - 1) / gridDim.x;
-  const int r_begin = blockIdx.x * rpc;
-  const int r_end = min(num_rows, r_begin + rpc);
-  const int iters = (r_end - r_begin + SPMM_THREADS / LPR - 1) / (SPMM_THREADS / LPR);
-  const bool fok = l < F4;
-  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int it = 0; it < iters; ++it) {
-    const int r = r_begin + it * (SPMM_THREADS / LPR) + threadIdx.x / LPR;
-    const bool rok = r < r_end;
-    const int s = rok ? __ldg(rowptr + r) : 0, t = rok ? __ldg(rowptr + r + 1) : 0;
-    float4 acc = zero4;
-    for (int p0 = s; __any_sync(0xffffffffu, p0 < t); p0 += NB) {
-      int myc = 0; float myv = 1.f;
-      if (l < NB && p0 + l < t) {
-        myc = __ldg(colidx + p0 + l);
-        if (HAS_VAL) myv = __ldg(val + p0 + l);
-      }
-      float4 h[NB];
-#pragma unroll
-      for (int j = 0; j < NB; ++j) {
-        const int c = __shfl_sync(0xffffffffu, myc, j, LPR);
-        // out-of-range slots gather row c = 0 (always valid memory) and are masked below
-        h[j] = fok ? ldg_nc_v4(H + (int64_t)c * F4 + l) : zero4;
-      }
-#pragma unroll
-      for (int j = 0; j < NB; ++j) {
-        const float v = __shfl_sync(0xffffffffu, myv, j, LPR);
-        if (p0 + j < t) {
-          acc.x = __fadd_rn(acc.x, __fmul_rn(v, h[j].x)); acc.y = __fadd_rn(acc.y, __fmul_rn(v, h[j].y));
-          acc.z = __fadd_rn(acc.z, __fmul_rn(v, h[j].z)); acc.w = __fadd_rn(acc.w, __fmul_rn(v, h[j].w));
-        }
-      }
-    }
-    if (rok && fok) {
-      if (bias != nullptr) {
-        float4 b = __ldg(bias + l);
-        acc.x = __fadd_rn(acc.x, b.x); acc.y = __fadd_rn(acc.y, b.y);
-        acc.z = __fadd_rn(acc.z, b.z); acc.w = __fadd_rn(acc.w, b.w);
-      }
-      if (relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
-      Y[(int64_t)r * F4 + l] = acc;
     }
   }
 }
@@ -299,28 +238,170 @@ k_spmm_tiled(const int* __restrict__ rowptr, const int* __restrict__ colidx, con
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// k_spmm_g (default for 16-byte aligned widths): what the ncu captures of round 1 taught
+// (profiles/r01b_spmm_variants.md):
+//   * k_spmm_vec4 is NOT DRAM bound: an L2-resident problem runs no faster per row.  It is bound by
+//     the L2 -> L1 fill traffic of gathers that miss L1 (487 MB for 175 MB of compulsory reads, L1 hit
+//     rate 51 %).  Every H row is gathered ~6 times, always from rows of the same graph, so it should
+//     miss once and hit five times; it does not because 8 small CTAs per SM walk 8 different graphs.
+//     => 1024-thread CTAs: all 32 warps of a CTA sweep the SAME graph at the same time, an SM holds two
+//     graph windows instead of eight (L1 hit rate 74 %, L2 -> L1 traffic halved);
+//   * after that the L1 misses are the compulsory DRAM stream.  One thread per CTA asks the TMA engine
+//     (`cp.async.bulk.prefetch.L2`) for the contiguous ranges the CTA is about to read: the H rows
+//     `hdist` rows ahead and the colidx / val slices ~2 iterations ahead (position extrapolated from
+//     the CTA's average row length: no dependent load).  Per-lane `prefetch.global.L2` did cut the
+//     long-scoreboard stalls too but cost more issue slots / LSU queue than it won;
+//   * lean loop: one IMAD.WIDE.U32 per gathered address (lane base + col * row_bytes), batches of 4
+//     neighbours + ONE predicated batch for the 1..3 left over (no serial remainder chain).
+// Accumulation is sequential in CSR order in every mode: run-to-run deterministic and independent of
+// the launch geometry.  FMA = false rounds the product before the add (bit-identical to index_add_
+// in COO order: flag TSG_SPMM_EXACT); FMA = true (default) fuses it: <= 1 ulp per term.
+// Negative results kept out of the tree: warp-private cp.async staging of the CSR slice (153-200 us),
+// a producer warp issuing per-line L2 prefetches (126 us), L1 evict_first / evict_last hints (+10 %).
+// ------------------------------------------------------------------------------------------
+// TMA bulk prefetch into L2 of [p, p + bytes): address aligned down / size rounded up to 16 bytes
+__device__ __forceinline__ void bulk_prefetch_l2(const void* p, size_t bytes) {
+  if (bytes == 0) return;
+  const uintptr_t a = reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)15;
+  const uintptr_t e = (reinterpret_cast<uintptr_t>(p) + bytes + 15) & ~(uintptr_t)15;
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(a), "r"((unsigned)(e - a)) : "memory");
+}
+
+template <int LPR, bool HAS_VAL, bool FMA, int THREADS>
+__global__ void __launch_bounds__(THREADS, 2048 / THREADS)
+k_spmm_g(const int* __restrict__ rowptr, const int* __restrict__ colidx,
+         const float* __restrict__ val, const float4* __restrict__ H,
+         const float4* __restrict__ bias, float4* __restrict__ Y,
+         int num_rows, int F4, int relu, int hdist) {
+  constexpr int RPI = THREADS / LPR;              // rows per CTA iteration
+  const int l = threadIdx.x % LPR;
+  const int rpc = (num_rows + gridDim.x - 1) / gridDim.x;
+  const int r_begin = blockIdx.x * rpc;
+  const int r_end = min(num_rows, r_begin + rpc);
+  const unsigned row_bytes = (unsigned)F4 * 16u;
+  __shared__ int s_pf[2];                         // [0] CSR entries per CTA iteration (estimate), [1] nnz
+  if (hdist > 0 && threadIdx.x == 0 && r_begin < r_end) {
+    const int p_b = __ldg(rowptr + r_begin), p_e = __ldg(rowptr + r_end);
+    const int nnz_end = __ldg(rowptr + num_rows);
+    const int epi = (int)(((long long)(p_e - p_b) * RPI) / (r_end - r_begin)) + 1;
+    s_pf[0] = epi; s_pf[1] = nnz_end;
+    // head of this CTA's H window and CSR slice
+    bulk_prefetch_l2(reinterpret_cast<const char*>(H) + (size_t)r_begin * row_bytes,
+                     (size_t)min(hdist, num_rows - r_begin) * row_bytes);
+    const size_t n0 = (size_t)min(2 * epi, nnz_end - p_b) * 4;
+    bulk_prefetch_l2(colidx + p_b, n0);
+    if (HAS_VAL) bulk_prefetch_l2(val + p_b, n0);
+  }
+  for (int r = r_begin + threadIdx.x / LPR; r < r_end; r += RPI) {
+    const int s = __ldg(rowptr + r), t = __ldg(rowptr + r + 1);
+    if (hdist > 0 && threadIdx.x == 0) {
+      const int hr = r + hdist;                                       // H rows [hr, hr + RPI)
+      if (hr < num_rows)
+        bulk_prefetch_l2(reinterpret_cast<const char*>(H) + (size_t)hr * row_bytes,
+                         (size_t)min(RPI, num_rows - hr) * row_bytes);
+      const int epi = s_pf[0], nnz_end = s_pf[1];
+      const long long q = (long long)s + 2LL * epi - (epi >> 2);      // CSR entries ~2 iterations ahead
+      if (q < (long long)nnz_end) {
+        const size_t n = (size_t)min((long long)epi + (epi >> 1), (long long)nnz_end - q) * 4;
+        bulk_prefetch_l2(colidx + q, n);
+        if (HAS_VAL) bulk_prefetch_l2(val + q, n);
+      }
+    }
+    for (int f = l; f < F4; f += LPR) {
+      const char* Hl = reinterpret_cast<const char*>(H + f);
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#define TSG_LD(c) __ldg(reinterpret_cast<const float4*>(Hl + (size_t)(unsigned)(c) * row_bytes))
+#define TSG_ACC(h, v)                                                                                   \
+      if (FMA) { acc.x = fmaf(v, h.x, acc.x); acc.y = fmaf(v, h.y, acc.y);                              \
+                 acc.z = fmaf(v, h.z, acc.z); acc.w = fmaf(v, h.w, acc.w); }                            \
+      else { acc.x = __fadd_rn(acc.x, __fmul_rn(v, h.x)); acc.y = __fadd_rn(acc.y, __fmul_rn(v, h.y));  \
+             acc.z = __fadd_rn(acc.z, __fmul_rn(v, h.z)); acc.w = __fadd_rn(acc.w, __fmul_rn(v, h.w)); }
+      int p = s;
+      for (; p + 4 <= t; p += 4) {
+        const int c0 = __ldg(colidx + p), c1 = __ldg(colidx + p + 1);
+        const int c2 = __ldg(colidx + p + 2), c3 = __ldg(colidx + p + 3);
+        float v0 = 1.f, v1 = 1.f, v2 = 1.f, v3 = 1.f;
+        if (HAS_VAL) { v0 = __ldg(val + p); v1 = __ldg(val + p + 1); v2 = __ldg(val + p + 2); v3 = __ldg(val + p + 3); }
+        const float4 h0 = TSG_LD(c0), h1 = TSG_LD(c1), h2 = TSG_LD(c2), h3 = TSG_LD(c3);
+        TSG_ACC(h0, v0) TSG_ACC(h1, v1) TSG_ACC(h2, v2) TSG_ACC(h3, v3)
+      }
+      const int rem = t - p;
+      if (rem > 0) {                     // 1..3 left: one predicated batch
+        int c0 = __ldg(colidx + p), c1 = 0, c2 = 0;
+        float v0 = 1.f, v1 = 1.f, v2 = 1.f;
+        if (HAS_VAL) v0 = __ldg(val + p);
+        if (rem > 1) { c1 = __ldg(colidx + p + 1); if (HAS_VAL) v1 = __ldg(val + p + 1); }
+        if (rem > 2) { c2 = __ldg(colidx + p + 2); if (HAS_VAL) v2 = __ldg(val + p + 2); }
+        const float4 h0 = TSG_LD(c0);
+        float4 h1 = h0, h2 = h0;
+        if (rem > 1) h1 = TSG_LD(c1);
+        if (rem > 2) h2 = TSG_LD(c2);
+        TSG_ACC(h0, v0)
+        if (rem > 1) { TSG_ACC(h1, v1) }
+        if (rem > 2) { TSG_ACC(h2, v2) }
+      }
+#undef TSG_ACC
+#undef TSG_LD
+      if (bias != nullptr) {
+        const float4 b = __ldg(bias + f);
+        acc.x = __fadd_rn(acc.x, b.x); acc.y = __fadd_rn(acc.y, b.y);
+        acc.z = __fadd_rn(acc.z, b.z); acc.w = __fadd_rn(acc.w, b.w);
+      }
+      if (relu) {
+        acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f);
+        acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f);
+      }
+      Y[(size_t)r * F4 + f] = acc;
+    }
+  }
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* s = getenv(name);
+  return s ? atoi(s) : dflt;
+}
+
 template <bool HAS_VAL>
 static int launch_spmm(const int* rowptr, const int* colidx, const float* val, const float* H,
-                       const float* bias, float* Y, int64_t N, int64_t F, int relu, cudaStream_t st) {
+                       const float* bias, float* Y, int64_t N, int64_t F, int relu, bool exact, cudaStream_t st) {
   bool vec = (F % 4 == 0) && (((uintptr_t)H & 15) == 0) && (((uintptr_t)Y & 15) == 0) &&
              (bias == nullptr || ((uintptr_t)bias & 15) == 0);
   if (vec) {
     int F4 = (int)(F / 4);
     int lpr = 1; while (lpr < F4 && lpr < 32) lpr <<= 1;
-    int rows_per_block = SPMM_THREADS / lpr;
-    int grid = grid_for(N, rows_per_block, 32);
+    // tuning knobs (defaults = measured best on B200, DD-shape level 1): TSG_SPMM_LEGACY=1 selects k_spmm_vec4
+    static const bool legacy = env_int("TSG_SPMM_LEGACY", 0) != 0;
+    static const int hdist = env_int("TSG_SPMM_HDIST", 128);
+    static const int ctas_per_sm_1024 = env_int("TSG_SPMM_CTAS", 2);
+    if (legacy) {
+      int grid = grid_for(N, SPMM_THREADS / lpr, 32);
 #define TSG_GO(L) k_spmm_vec4<L, HAS_VAL><<<grid, SPMM_THREADS, 0, st>>>(rowptr, colidx, val, (const float4*)H, (const float4*)bias, (float4*)Y, (int)N, F4, relu)
-#define TSG_GC(L) k_spmm_coop<L, HAS_VAL><<<grid, SPMM_THREADS, 0, st>>>(rowptr, colidx, val, (const float4*)H, (const float4*)bias, (float4*)Y, (int)N, F4, relu)
-    static const bool coop = getenv("TSG_SPMM_COOP") != nullptr;
-    if (coop && F4 <= lpr && lpr >= 8) {
-      switch (lpr) { case 8: TSG_GC(8); break; case 16: TSG_GC(16); break; default: TSG_GC(32); break; }
-    } else
-    switch (lpr) {
-      case 1: TSG_GO(1); break; case 2: TSG_GO(2); break; case 4: TSG_GO(4); break;
-      case 8: TSG_GO(8); break; case 16: TSG_GO(16); break; default: TSG_GO(32); break;
-    }
-#undef TSG_GC
+      switch (lpr) {
+        case 1: TSG_GO(1); break; case 2: TSG_GO(2); break; case 4: TSG_GO(4); break;
+        case 8: TSG_GO(8); break; case 16: TSG_GO(16); break; default: TSG_GO(32); break;
+      }
 #undef TSG_GO
+    } else {
+      // 1024-thread CTAs once every SM gets two of them; smaller problems use 256-thread CTAs so the
+      // grid still covers the machine
+      const bool big = N >= (int64_t)TSG_NUM_SMS * 2 * (1024 / lpr) * 2;
+      const int threads = big ? 1024 : 256;
+      const int rpi = threads / lpr;
+      int g = (int)((N + rpi - 1) / rpi);
+      const int cap = big ? TSG_NUM_SMS * ctas_per_sm_1024 : TSG_NUM_SMS * 32;
+      if (g > cap) g = cap;
+#define TSG_G(L, FM, T) k_spmm_g<L, HAS_VAL, FM, T><<<g, T, 0, st>>>(rowptr, colidx, val, (const float4*)H, (const float4*)bias, (float4*)Y, (int)N, F4, relu, big ? hdist : 0)
+#define TSG_GT(L, FM) if (big) TSG_G(L, FM, 1024); else TSG_G(L, FM, 256);
+#define TSG_GV(L) if (exact) { TSG_GT(L, false) } else { TSG_GT(L, true) }
+      switch (lpr) {
+        case 1: TSG_GV(1) break; case 2: TSG_GV(2) break; case 4: TSG_GV(4) break;
+        case 8: TSG_GV(8) break; case 16: TSG_GV(16) break; default: TSG_GV(32) break;
+      }
+#undef TSG_GV
+#undef TSG_GT
+#undef TSG_G
+    }
   } else {
     int lpr = 1; while (lpr < F && lpr < 32) lpr <<= 1;
     int rows_per_block = SPMM_THREADS / lpr;
@@ -387,9 +468,10 @@ extern "C" int tsg_spmm(const int32_t* rowptr, const int32_t* colidx, const floa
   if (num_rows == 0) return TSG_OK;
   TSG_REQUIRE(rowptr && colidx && H && Y, "spmm: null pointer");
   int relu = (flags & TSG_SPMM_RELU) ? 1 : 0;
+  const bool exact = (flags & TSG_SPMM_EXACT) != 0;
   cudaStream_t st = (cudaStream_t)stream;
-  return val ? launch_spmm<true>(rowptr, colidx, val, H, bias, Y, num_rows, feat, relu, st)
-             : launch_spmm<false>(rowptr, colidx, val, H, bias, Y, num_rows, feat, relu, st);
+  return val ? launch_spmm<true>(rowptr, colidx, val, H, bias, Y, num_rows, feat, relu, exact, st)
+             : launch_spmm<false>(rowptr, colidx, val, H, bias, Y, num_rows, feat, relu, exact, st);
 }
 
 

@@ -24,6 +24,9 @@ _PROTOTYPES = {
     "tsg_pack_batch": (I, [P, P, P, I64, P, P, P, P, P, P, I64, P, P, P, P]),
     "tsg_csr_build_workspace_bytes": (SZ, [I64, I64]),
     "tsg_csr_build": (I, [P, P, P, I64, P, I64, I, P, P, P, P, P, P, P, P, P, SZ, P]),
+    "tsg_edge_ptr": (I, [P, I64, P, P, I64, P, P]),
+    "tsg_csr_build_graphs_workspace_bytes": (SZ, [I64, I64]),
+    "tsg_csr_build_graphs": (I, [P, P, P, P, I64, I64, I64, I64, P, P, P, P, P, P, P, P, P, SZ, P]),
     "tsg_spmm": (I, [P, P, P, P, P, P, I64, I64, I, P]),
     "tsg_spmm_tiled": (I, [P, P, P, P, P, P, P, I64, I64, I64, I, P]),
     "tsg_colsum_workspace_bytes": (SZ, [I64, I64]),
@@ -75,7 +78,7 @@ if lib.tsg_abi_version() != 1:
 
 # kernels each entry point enqueues (memsets not counted); bench.py reports the sum as gpu_launches
 KERNELS_PER_CALL = {
-    "tsg_pack_batch": 1, "tsg_csr_build": 12, "tsg_spmm": 1, "tsg_spmm_tiled": 1, "tsg_relu_bwd_colsum": 2, "tsg_topk_sizes": 3, "tsg_topk": 1,
+    "tsg_pack_batch": 1, "tsg_csr_build": 12, "tsg_edge_ptr": 1, "tsg_csr_build_graphs": 5, "tsg_spmm": 1, "tsg_spmm_tiled": 1, "tsg_relu_bwd_colsum": 2, "tsg_topk_sizes": 3, "tsg_topk": 1,
     "tsg_batch_to_ptr": 1, "tsg_filter_adj": 7, "tsg_gate_gather_fwd": 1, "tsg_gate_gather_bwd": 1,
     "tsg_readout_fwd": 1, "tsg_readout_bwd": 1, "tsg_triplet_fwd": 2, "tsg_triplet_bwd": 9,
     "tsg_pairdist_matrix": 1, "tsg_linear_fwd": 1, "tsg_dense_epilogue_bwd": 1, "tsg_linear_bwd_weight": 2,

@@ -137,7 +137,10 @@ class PackedSAGNet(torch.nn.Module):
         for lvl, (conv, pool) in enumerate(((self.conv1, self.pool1), (self.conv2, self.pool2),
                                             (self.conv3, self.pool3))):
             n_l, k_l = int(plan[lvl, -1]), int(plan[lvl + 1, -1])
-            csr = ops.build_csr(edges, n_l)
+            if ops.USE_GRAPH_CSR and n_l > 0:
+                csr = ops.build_csr_graphs(edges, ptrs[lvl], n_l, int(np.diff(plan[lvl]).max()))
+            else:
+                csr = ops.build_csr(edges, n_l)
             csr.tile_ptr = tiles[lvl]
             h = conv(x, csr, relu=True)                                   # network.py:34
             score = pool.score_layer(h, csr).view(-1)                     # layers.py:18

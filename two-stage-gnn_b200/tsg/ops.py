@@ -7,6 +7,7 @@ There is no CPU path: CPU tensors raise.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Optional, Tuple
 
@@ -18,6 +19,8 @@ from ._lib import call, ptr, stream_ptr, workspace, lib
 CSR_GCN, CSR_RAW = 0, 1
 USE_TILED_SPMM = False   # shared-memory-staged K2 (tsg_spmm_tiled); measured slower than the L1-blocked kernel
 SPMM_RELU = 1
+SPMM_EXACT = 2
+SPMM_EXACT_DEFAULT = False   # True: separately rounded products everywhere (6 % slower K2)
 READOUT_MAX, READOUT_MEAN, READOUT_SUM = 1, 2, 4
 LIN_NORMALIZE, LIN_RELU, LIN_NODEBN = 1, 2, 4
 
@@ -88,17 +91,56 @@ def build_csr(edges: EdgeList, num_nodes: int, mode: int = CSR_GCN, transposed: 
     return CSR(rowptr, colidx, val, eid, t_rowptr, t_colidx, t_val, t_eid, N)
 
 
+USE_GRAPH_CSR = os.environ.get("TSG_GRAPH_CSR", "1") != "0"     # K1b (one CTA per graph, shared memory) for packed batches; False = generic K1
+GRAPH_CSR_MAX_NODES = 6000   # shared-memory budget of K1b (7 ints per node)
+
+
+def build_csr_graphs(edges: EdgeList, node_ptr: torch.Tensor, num_nodes: int, max_graph_nodes: int,
+                     transposed: bool = True, want_eid: bool = False) -> CSR:
+    """K1b: same result as build_csr(mode=CSR_GCN) for a packed batch whose edges are grouped by graph
+    (PyG Batch layout; preserved by filter_adj).  node_ptr int64 [G+1] on the device; max_graph_nodes is
+    the host-side bound over the batch.  Falls back to K1 when a graph exceeds the smem budget."""
+    if max_graph_nodes > GRAPH_CSR_MAX_NODES:
+        return build_csr(edges, num_nodes, CSR_GCN, transposed, None, want_eid)
+    dev = edges.row.device
+    E, N, G = edges.cap, int(num_nodes), node_ptr.numel() - 1
+    cap = E + N
+    i32 = dict(dtype=torch.int32, device=dev)
+    rowptr = torch.empty(N + 1, **i32)
+    colidx = torch.empty(cap, **i32)
+    val = torch.empty(cap, dtype=torch.float32, device=dev)
+    eid = torch.empty(cap, **i32) if want_eid else None
+    if transposed:
+        t_rowptr = torch.empty(N + 1, **i32)
+        t_colidx = torch.empty(cap, **i32)
+        t_val = torch.empty(cap, dtype=torch.float32, device=dev)
+        t_eid = torch.empty(cap, **i32) if want_eid else None
+    else:
+        t_rowptr = t_colidx = t_val = t_eid = None
+    eptr = torch.empty(G + 1, dtype=torch.int64, device=dev)
+    call("tsg_edge_ptr", ptr(edges.row), E, ptr(edges.count), ptr(node_ptr), G, ptr(eptr), stream_ptr())
+    wsb = lib.tsg_csr_build_graphs_workspace_bytes(G, E)
+    ws = workspace(wsb, dev)
+    call("tsg_csr_build_graphs", ptr(edges.row), ptr(edges.col), ptr(eptr), ptr(node_ptr), G, N, E,
+         int(max_graph_nodes), ptr(rowptr), ptr(colidx), ptr(val), ptr(eid), ptr(t_rowptr), ptr(t_colidx),
+         ptr(t_val), ptr(t_eid), ptr(ws), wsb, stream_ptr())
+    return CSR(rowptr, colidx, val, eid, t_rowptr, t_colidx, t_val, t_eid, N)
+
+
 def spmm_raw(rowptr, colidx, val, H: torch.Tensor, bias=None, relu: bool = False,
-             tile_ptr: Optional[torch.Tensor] = None) -> torch.Tensor:
+             tile_ptr: Optional[torch.Tensor] = None, exact: Optional[bool] = None) -> torch.Tensor:
+    """exact=True rounds every product before the add (bit-identical to index_add_ in COO order);
+    the default (SPMM_EXACT_DEFAULT = False) fuses it (FFMA): same order, <= 1 ulp per term."""
     n = rowptr.numel() - 1
     H = H.contiguous()
     Y = torch.empty(n, H.size(1), dtype=torch.float32, device=H.device)
+    flags = (SPMM_RELU if relu else 0) | (SPMM_EXACT if (SPMM_EXACT_DEFAULT if exact is None else exact) else 0)
     if USE_TILED_SPMM and tile_ptr is not None and H.size(1) % 4 == 0:
         call("tsg_spmm_tiled", ptr(rowptr), ptr(colidx), ptr(val), ptr(H), ptr(bias), ptr(Y), ptr(tile_ptr),
-             tile_ptr.numel() - 1, n, H.size(1), SPMM_RELU if relu else 0, stream_ptr())
+             tile_ptr.numel() - 1, n, H.size(1), flags, stream_ptr())
     else:
         call("tsg_spmm", ptr(rowptr), ptr(colidx), ptr(val), ptr(H), ptr(bias), ptr(Y), n, H.size(1),
-             SPMM_RELU if relu else 0, stream_ptr())
+             flags, stream_ptr())
     return Y
 
 
