@@ -268,11 +268,19 @@ def main():
     clocks = sampler.finish()
     value = world * graphs_per_step * a.steps / (ms / 1000.0)
 
-    # ---- end to end with host buffers
+    # ---- end to end with host buffers: per-step blocking call, and the pipelined loop (H2D of batch i+1
+    #      overlaps the step on batch i; every step still uploads its own inputs and reads its loss back)
     for i in range(2):
         step_e2e(i)
-    ms_e2e = timed(step_e2e, a.steps)
+    ms_e2e_blocking = timed(step_e2e, a.steps)
+
+    def run_e2e(steps):
+        return trainer.run_from_host((batches[i % len(batches)] for i in range(steps)), dev)
+
+    run_e2e(2)
+    ms_e2e = timed(lambda i: run_e2e(a.steps) if i == 0 else None, 1)
     e2e_val = world * graphs_per_step * a.steps / (ms_e2e / 1000.0)
+    e2e_blocking_val = world * graphs_per_step * a.steps / (ms_e2e_blocking / 1000.0)
     # ---- end to end against the HBM-resident corpus (tsg.feeder): host sends graph ids + triplets only
     from tsg import synth
     from tsg.feeder import DeviceCorpus
@@ -322,13 +330,30 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = alg_bytes / (spmm_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": f"k_spmm_vec4 (level-1 GCN aggregation, N={N}, nnz={nnz}, F={Fh})",
+    traffic = None
+    try:      # dram__bytes_read.sum + dram__bytes_write.sum of the same launch from the committed ncu --set full capture
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01b_spmm_g_traffic.json")))
+        if tj.get("N") == N and tj.get("F") == Fh:
+            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": f"k_spmm_g (level-1 GCN aggregation, N={N}, nnz={nnz}, F={Fh})",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
-                "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": spmm_ms, "traffic": None}
+                "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": spmm_ms, "traffic": traffic,
+                "frac_of_nominal_8TBs": achieved / 8000.0}
 
     # ---- optional per-entry-point breakdown (device time shares; not part of any reported number)
     if a.breakdown and rank == 0:
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(10):
+            step_resident(i)
+        t1 = time.perf_counter()
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        print(f"[breakdown] host enqueue {1e2 * (t1 - t0):.3f} ms/step, drained after {1e3 * (t2 - t1):.3f} ms "
+              f"(enqueue ~ step time => launch bound)", file=sys.stderr)
         step_resident(0)
         _lib.profile = {}
         torch.cuda.synchronize()
@@ -360,7 +385,12 @@ def main():
                            "l2_policy": "inputs larger than L2 (x alone is %.0f MB), 2 alternating batches" % (N * corpus.num_node_labels * 4 / 1e6),
                            "parallelism": f"dp{world}: shard by graph, all-gather embeddings, all-reduce grads"},
                 "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": ms_e2e / a.steps,
-                        "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4},
+                        "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
+                        "api": "TripletTrainer.run_from_host: pinned host x[f32 N,89] / edge_index[i64 2,E] / triplets, "
+                               "copy stream double buffering, loss read back every step"},
+                "e2e_blocking": {"value": e2e_blocking_val, "unit": UNIT, "ms_per_step": ms_e2e_blocking / a.steps,
+                                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
+                                 "api": "TripletTrainer.step_from_host: one blocking call per step (H2D, step, loss.item())"},
                 "e2e_resident_corpus": {"value": ids_val, "unit": UNIT, "ms_per_step": ms_ids / a.steps,
                                         "h2d_bytes_per_step": int(ids_h2d), "d2h_bytes_per_step": 4,
                                         "note": "corpus uploaded once (tsg.feeder.DeviceCorpus); a step sends graph ids + "

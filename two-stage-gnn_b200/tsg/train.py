@@ -97,6 +97,48 @@ class TripletTrainer:
         tr = triplets_host.to(device, non_blocking=True)
         return float(self.step(x, ei, node_ptr_host, tr).item())
 
+    def run_from_host(self, host_batches, device) -> list:
+        """Pipelined end-to-end loop over an iterable of HOST batches (dicts with pinned `x`, `edge_index`,
+        `triplets` and numpy `node_ptr`): the H2D copies of batch i+1 run on a copy stream while the step
+        on batch i computes, and every step's loss is read back into pinned host memory without stalling
+        the enqueue thread.  Same arithmetic as step_from_host; returns the per-step losses."""
+        cur = torch.cuda.current_stream(device)
+        copy = getattr(self, "_copy_stream", None)
+        if copy is None:
+            copy = self._copy_stream = torch.cuda.Stream(device)
+
+        def upload(b):
+            copy.wait_stream(cur)      # staging memory freed by earlier steps must be done being read
+            with torch.cuda.stream(copy):
+                x = b["x"].to(device, non_blocking=True)
+                ei = b["edge_index"].to(device, non_blocking=True)
+                tr = b["triplets"].to(device, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy)
+            return x, ei, b["node_ptr"], tr, ev
+
+        it = iter(host_batches)
+        try:
+            nxt = upload(next(it))
+        except StopIteration:
+            return []
+        host_losses = []
+        while nxt is not None:
+            x, ei, nptr, tr, ev = nxt
+            try:
+                nxt = upload(next(it))
+            except StopIteration:
+                nxt = None
+            cur.wait_event(ev)
+            for t in (x, ei, tr):
+                t.record_stream(cur)
+            loss = self.step(x, ei, nptr, tr)
+            h = torch.empty((), dtype=torch.float32, pin_memory=True)
+            h.copy_(loss, non_blocking=True)
+            host_losses.append(h)
+        cur.synchronize()
+        return [float(h) for h in host_losses]
+
     def step_from_ids(self, corpus, graph_ids_host: np.ndarray, triplets_host: torch.Tensor) -> float:
         """End-to-end call against an HBM-resident corpus (tsg.feeder.DeviceCorpus): the host sends the
         step's graph ids + triplet index list, the batch is assembled on the GPU, the loss is read back."""
