@@ -307,6 +307,31 @@ int tsg_triplet_bwd(const float* emb, const int64_t* triplets, int64_t num_tripl
 int tsg_pairdist_matrix(const float* emb, int64_t num_rows, int64_t dim, float eps,
                         float* dist, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * K10  native step executor for the SAGPool encoder
+ *   replaces the Python-level sequencing of Code/sag/network.py:33-46 (`Net.forward` up to the sum
+ *   of the three readouts) and Code/sag/layers.py:14-26 (`SAGPool.forward`) over a packed batch: ONE
+ *   call enqueues K1b, K3, K2, K5a, K5b, gate and K6 of all three levels (same kernels, same order as
+ *   the per-kernel entry points above), ONE call the whole backward.  All intermediates live in the
+ *   caller's arena (tsg_sag_arena_bytes); the forward leaves its saved tensors there for the backward.
+ *   n[l] = packed node count of level l (n[0] = input rows, n[l+1] = sum_g ceil(ratio * n_g) computed
+ *   on the host exactly as PyG's topk does); level_ptr = device int64 [4, G+1] node offsets per level;
+ *   params / grads = 12 device pointers: for l = 0..2 { conv_l.weight [in,H], conv_l.bias [H],
+ *   pool_l.score_layer.weight [H,1], pool_l.score_layer.bias [1] }.  z, dz: [G, 2H].
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int64_t num_graphs, in_feat, hidden, num_edges;
+  int64_t n[4];
+  int64_t max_graph_nodes[3];
+} tsg_sag_shape;
+size_t tsg_sag_arena_bytes(const tsg_sag_shape* shape);
+int tsg_sag_encoder_fwd(const tsg_sag_shape* shape, const float* x, const int64_t* row, const int64_t* col,
+                        const int64_t* level_ptr, const float* const* params, float* z,
+                        void* arena, size_t arena_bytes, void* stream);
+int tsg_sag_encoder_bwd(const tsg_sag_shape* shape, const float* x, const int64_t* level_ptr,
+                        const float* const* params, const float* dz, float* const* grads,
+                        void* arena, size_t arena_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

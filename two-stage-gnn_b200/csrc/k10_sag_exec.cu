@@ -1,0 +1,209 @@
+// K10 -- native step executor for the SAGPool encoder (Code/sag/network.py:33-46 + layers.py:14-26).
+//
+// The per-kernel entry points of this library are driven from Python one ctypes call at a time; with
+// ~110 launches per training step that costs 3.3 ms of host time for 2.9 ms of kernels (measured,
+// profiles/r01b_bench_breakdown.txt): the step was launch bound.  This file sequences the SAME entry
+// points (same kernels, same order, same arithmetic as tsg/nn.py PackedSAGNet drives them) from C++:
+// one call enqueues the whole encoder forward, one call the whole backward.  Every intermediate lives
+// in a caller-provided arena whose layout is a pure function of the shape, so the forward leaves its
+// saved tensors where the backward finds them; nothing is allocated, nothing synchronises.
+//
+//   per level l = 0..2 (n = n[l] rows in, k = n[l+1] rows out):
+//     CSR   = K1b(edges_l, level_ptr[l])                      conv_l and score_l share it
+//     h     = ReLU(A_hat (x_l W_l) + b_l)                     network.py:34,38,42
+//     score = A_hat (h ws_l) + bs_l                           layers.py:18
+//     perm  = topk(score)                                     layers.py:20
+//     edges_{l+1}, inv = filter_adj(edges_l, perm)            layers.py:23
+//     x_{l+1} = h[perm] * tanh(score[perm])                   layers.py:21
+//     out_l = [gmp(x_{l+1}) || gap(x_{l+1})]                  network.py:36,40,44
+//   z = out_0 + out_1 + out_2                                 network.py:46
+#include "common.cuh"
+
+namespace tsg {
+
+struct LevelBuf {
+  int64_t* eptr;
+  int32_t *rowptr, *colidx, *t_rowptr, *t_colidx;
+  float *val, *t_val;
+  float *xw, *h, *sw, *score, *xg, *out;
+  int64_t* perm;
+  int32_t* inv;
+  int64_t *erow, *ecol, *ecount;     // edges surviving this level's pooling (input of the next level)
+  int32_t* argmax;
+};
+
+struct SagArena {
+  LevelBuf lv[3];
+  // backward temporaries, sized for level 0 and reused by every level
+  float *dxg, *dh, *dh_score, *dhm, *dxw, *dx_next, *dscore, *dsw, *db_tmp;
+  void* scratch; size_t scratch_bytes;
+  size_t total;
+};
+
+static size_t scratch_need(const tsg_sag_shape* sh) {
+  size_t m = 0;
+  auto up = [&](size_t v) { if (v > m) m = v; };
+  for (int l = 0; l < 3; ++l) {
+    up(tsg_csr_build_graphs_workspace_bytes(sh->num_graphs, sh->num_edges));
+    up(tsg_topk_workspace_bytes(sh->n[l], sh->num_graphs));
+    up(tsg_filter_adj_workspace_bytes(sh->num_edges));
+    up(tsg_colsum_workspace_bytes(sh->n[l], sh->hidden));
+    up(tsg_linear_bwd_weight_workspace_bytes(l == 0 ? sh->in_feat : sh->hidden, sh->hidden));
+    up(tsg_linear_bwd_weight_workspace_bytes(sh->hidden, 1));
+  }
+  return align_up(m, 256) + 256;
+}
+
+// layout(arena == nullptr) only measures
+static void layout(const tsg_sag_shape* sh, void* arena, SagArena* a) {
+  char* base = (char*)arena;
+  size_t off = 0;
+  auto take = [&](size_t bytes) -> void* {
+    void* p = base ? (void*)(base + off) : nullptr;
+    off += align_up(bytes, 256);
+    return p;
+  };
+  const int64_t G = sh->num_graphs, H = sh->hidden, E = sh->num_edges;
+  for (int l = 0; l < 3; ++l) {
+    LevelBuf& b = a->lv[l];
+    const int64_t n = sh->n[l], k = sh->n[l + 1], cap = E + n;
+    b.eptr = (int64_t*)take((G + 1) * 8);
+    b.rowptr = (int32_t*)take((n + 1) * 4); b.t_rowptr = (int32_t*)take((n + 1) * 4);
+    b.colidx = (int32_t*)take(cap * 4); b.t_colidx = (int32_t*)take(cap * 4);
+    b.val = (float*)take(cap * 4); b.t_val = (float*)take(cap * 4);
+    b.xw = (float*)take(n * H * 4); b.h = (float*)take(n * H * 4);
+    b.sw = (float*)take(n * 4); b.score = (float*)take(n * 4);
+    b.perm = (int64_t*)take((k > 0 ? k : 1) * 8);
+    b.inv = (int32_t*)take((n > 0 ? n : 1) * 4);
+    b.erow = (int64_t*)take((E > 0 ? E : 1) * 8); b.ecol = (int64_t*)take((E > 0 ? E : 1) * 8);
+    b.ecount = (int64_t*)take(8);
+    b.xg = (float*)take((k > 0 ? k : 1) * H * 4);
+    b.out = (float*)take(G * 2 * H * 4);
+    b.argmax = (int32_t*)take(G * H * 4);
+  }
+  const int64_t n0 = sh->n[0] > 0 ? sh->n[0] : 1;
+  a->dxg = (float*)take(n0 * H * 4); a->dh = (float*)take(n0 * H * 4); a->dh_score = (float*)take(n0 * H * 4);
+  a->dhm = (float*)take(n0 * H * 4); a->dxw = (float*)take(n0 * H * 4); a->dx_next = (float*)take(n0 * H * 4);
+  a->dscore = (float*)take(n0 * 4); a->dsw = (float*)take(n0 * 4); a->db_tmp = (float*)take(256);
+  a->scratch_bytes = scratch_need(sh);
+  a->scratch = take(a->scratch_bytes);
+  a->total = off;
+}
+
+__global__ void __launch_bounds__(256)
+k_add3(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c, float* __restrict__ o, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    o[i] = (a[i] + b[i]) + c[i];
+}
+
+// a[i] += b[i], 128-bit where possible (n4 float4 + tail)
+__global__ void __launch_bounds__(256)
+k_add_inplace(float* __restrict__ a, const float* __restrict__ b, int64_t n) {
+  const int64_t n4 = n >> 2;
+  float4* a4 = reinterpret_cast<float4*>(a);
+  const float4* b4 = reinterpret_cast<const float4*>(b);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 x = a4[i]; const float4 y = b4[i];
+    x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w;
+    a4[i] = x;
+  }
+  for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    a[i] += b[i];
+}
+
+static bool shape_ok(const tsg_sag_shape* sh) {
+  if (!sh || sh->num_graphs <= 0 || sh->in_feat <= 0 || sh->hidden <= 0 || sh->num_edges < 0) return false;
+  for (int l = 0; l < 4; ++l) if (sh->n[l] <= 0) return false;
+  for (int l = 0; l < 3; ++l) if (sh->max_graph_nodes[l] <= 0) return false;
+  return true;
+}
+
+}  // namespace tsg
+
+using namespace tsg;
+
+#define TSG_TRY(call)                 \
+  do {                                \
+    int _rc = (call);                 \
+    if (_rc != TSG_OK) return _rc;    \
+  } while (0)
+
+extern "C" size_t tsg_sag_arena_bytes(const tsg_sag_shape* shape) {
+  if (!shape_ok(shape)) return 0;
+  SagArena a;
+  layout(shape, nullptr, &a);
+  return a.total;
+}
+
+extern "C" int tsg_sag_encoder_fwd(const tsg_sag_shape* sh, const float* x, const int64_t* row, const int64_t* col,
+                                   const int64_t* level_ptr, const float* const* params, float* z,
+                                   void* arena, size_t arena_bytes, void* stream) {
+  TSG_REQUIRE(shape_ok(sh), "sag_encoder_fwd: bad shape");
+  TSG_REQUIRE(x && level_ptr && params && z && arena && (sh->num_edges == 0 || (row && col)), "sag_encoder_fwd: null pointer");
+  SagArena a;
+  layout(sh, arena, &a);
+  if (arena_bytes < a.total) { set_error("sag_encoder_fwd: arena too small (%zu < %zu)", arena_bytes, a.total); return TSG_EWORKSPACE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t G = sh->num_graphs, H = sh->hidden, E = sh->num_edges;
+  const float* xin = x;
+  const int64_t *erow = row, *ecol = col, *ecount = nullptr;
+  for (int l = 0; l < 3; ++l) {
+    LevelBuf& b = a.lv[l];
+    const int64_t n = sh->n[l], k = sh->n[l + 1], fin = l == 0 ? sh->in_feat : H;
+    const float *W = params[4 * l], *bias = params[4 * l + 1], *ws = params[4 * l + 2], *bs = params[4 * l + 3];
+    const int64_t* ptr_l = level_ptr + (size_t)l * (G + 1);
+    const int64_t* ptr_n = level_ptr + (size_t)(l + 1) * (G + 1);
+    TSG_TRY(tsg_edge_ptr(erow, E, ecount, ptr_l, G, b.eptr, stream));
+    TSG_TRY(tsg_csr_build_graphs(erow, ecol, b.eptr, ptr_l, G, n, E, sh->max_graph_nodes[l], b.rowptr, b.colidx, b.val,
+                                 nullptr, b.t_rowptr, b.t_colidx, b.t_val, nullptr, a.scratch, a.scratch_bytes, stream));
+    TSG_TRY(tsg_linear_fwd(xin, W, nullptr, b.xw, n, fin, H, 0, 0, stream));
+    TSG_TRY(tsg_spmm(b.rowptr, b.colidx, b.val, b.xw, bias, b.h, n, H, TSG_SPMM_RELU, stream));
+    TSG_TRY(tsg_linear_fwd(b.h, ws, nullptr, b.sw, n, H, 1, 0, 0, stream));
+    TSG_TRY(tsg_spmm(b.rowptr, b.colidx, b.val, b.sw, bs, b.score, n, 1, 0, stream));
+    TSG_TRY(tsg_topk(b.score, ptr_l, ptr_n, G, n, b.perm, a.scratch, a.scratch_bytes, stream));
+    TSG_TRY(tsg_filter_adj(erow, ecol, E, ecount, b.perm, k, n, b.inv, b.erow, b.ecol, b.ecount,
+                           a.scratch, a.scratch_bytes, stream));
+    TSG_TRY(tsg_gate_gather_fwd(b.h, b.score, b.perm, nullptr, b.xg, nullptr, k, H, stream));
+    TSG_TRY(tsg_readout_fwd(b.xg, ptr_n, G, H, TSG_READOUT_MAX | TSG_READOUT_MEAN, b.out, 2 * H, b.argmax, stream));
+    xin = b.xg; erow = b.erow; ecol = b.ecol; ecount = b.ecount;
+  }
+  const int64_t tot = G * 2 * H;
+  k_add3<<<grid_for(tot, 256, 8), 256, 0, st>>>(a.lv[0].out, a.lv[1].out, a.lv[2].out, z, tot);
+  return check_launch("sag_encoder_fwd");
+}
+
+extern "C" int tsg_sag_encoder_bwd(const tsg_sag_shape* sh, const float* x, const int64_t* level_ptr,
+                                   const float* const* params, const float* dz, float* const* grads,
+                                   void* arena, size_t arena_bytes, void* stream) {
+  TSG_REQUIRE(shape_ok(sh), "sag_encoder_bwd: bad shape");
+  TSG_REQUIRE(x && level_ptr && params && dz && grads && arena, "sag_encoder_bwd: null pointer");
+  SagArena a;
+  layout(sh, arena, &a);
+  if (arena_bytes < a.total) { set_error("sag_encoder_bwd: arena too small (%zu < %zu)", arena_bytes, a.total); return TSG_EWORKSPACE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t G = sh->num_graphs, H = sh->hidden;
+  for (int l = 2; l >= 0; --l) {
+    LevelBuf& b = a.lv[l];
+    const int64_t n = sh->n[l], k = sh->n[l + 1], fin = l == 0 ? sh->in_feat : H;
+    const float *W = params[4 * l], *ws = params[4 * l + 2];
+    float *dW = grads[4 * l], *dbias = grads[4 * l + 1], *dws = grads[4 * l + 2], *dbs = grads[4 * l + 3];
+    const float* xin = l == 0 ? x : a.lv[l - 1].xg;
+    const int64_t* ptr_n = level_ptr + (size_t)(l + 1) * (G + 1);
+    // d(x_{l+1}) = readout backward (+ the next level's input gradient)
+    TSG_TRY(tsg_readout_bwd(dz, 2 * H, b.argmax, ptr_n, G, k, H, TSG_READOUT_MAX | TSG_READOUT_MEAN, a.dxg, stream));
+    if (l < 2) k_add_inplace<<<grid_for(k * H / 4 + 1, 256, 16), 256, 0, st>>>(a.dxg, a.dx_next, k * H);
+    TSG_TRY(tsg_gate_gather_bwd(a.dxg, b.h, b.score, b.inv, a.dh, a.dscore, n, H, stream));
+    // score layer: score = A_hat (h ws) + bs
+    TSG_TRY(tsg_relu_bwd_colsum(a.dscore, nullptr, nullptr, dbs, n, 1, a.scratch, a.scratch_bytes, stream));
+    TSG_TRY(tsg_spmm(b.t_rowptr, b.t_colidx, b.t_val, a.dscore, nullptr, a.dsw, n, 1, 0, stream));
+    TSG_TRY(tsg_linear_fwd(a.dsw, ws, nullptr, a.dh_score, n, 1, H, 1, 0, stream));
+    TSG_TRY(tsg_linear_bwd_weight(b.h, a.dsw, dws, nullptr, n, H, 1, a.scratch, a.scratch_bytes, stream));
+    k_add_inplace<<<grid_for(n * H / 4 + 1, 256, 16), 256, 0, st>>>(a.dh, a.dh_score, n * H);
+    // conv layer: h = ReLU(A_hat (x W) + b)
+    TSG_TRY(tsg_relu_bwd_colsum(a.dh, b.h, a.dhm, dbias, n, H, a.scratch, a.scratch_bytes, stream));
+    TSG_TRY(tsg_spmm(b.t_rowptr, b.t_colidx, b.t_val, a.dhm, nullptr, a.dxw, n, H, 0, stream));
+    if (l > 0) TSG_TRY(tsg_linear_fwd(a.dxw, W, nullptr, a.dx_next, n, H, fin, 1, 0, stream));
+    TSG_TRY(tsg_linear_bwd_weight(xin, a.dxw, dW, nullptr, n, fin, H, a.scratch, a.scratch_bytes, stream));
+  }
+  return check_launch("sag_encoder_bwd");
+}

@@ -183,7 +183,7 @@ extern "C" int tsg_csr_build_graphs(const int64_t* row, const int64_t* col, cons
                                     void* workspace, size_t workspace_bytes, void* stream) {
   TSG_REQUIRE(num_graphs > 0 && num_nodes > 0, "csr_build_graphs: empty batch");
   TSG_REQUIRE(num_nodes + num_edges_cap < (int64_t)0x7fffffff, "csr_build_graphs: sum n + sum E must stay below 2^31");
-  TSG_REQUIRE(row && col && edge_ptr && node_ptr && rowptr && colidx && val, "csr_build_graphs: null pointer");
+  TSG_REQUIRE((num_edges_cap == 0 || (row && col)) && edge_ptr && node_ptr && rowptr && colidx && val, "csr_build_graphs: null pointer");
   TSG_REQUIRE(!t_rowptr || (t_colidx && t_val), "csr_build_graphs: null transposed output");
   size_t smem = graph_smem_bytes(max_graph_nodes);
   TSG_REQUIRE(smem <= 200 * 1024, "csr_build_graphs: a graph with %lld nodes needs %zu B of shared memory",

@@ -9,7 +9,9 @@
 """
 from __future__ import annotations
 
+import ctypes
 import math
+import os
 from typing import Optional
 
 import numpy as np
@@ -18,6 +20,9 @@ import torch.nn.functional as F
 
 from . import ops
 from .ops import CSR, EdgeList
+
+
+USE_EXECUTOR = os.environ.get("TSG_SAG_EXECUTOR", "1") != "0"   # K10 native step executor for PackedSAGNet
 
 
 def _glorot_(t: torch.Tensor) -> None:
@@ -103,6 +108,42 @@ def host_level_ptrs(node_ptr: np.ndarray, ratio: float, levels: int = 3) -> np.n
     return out
 
 
+class _SagEncoderFn(torch.autograd.Function):
+    """The three conv/pool/readout levels through the native executor (K10): two C-ABI calls per step
+    instead of ~110.  Same kernels in the same order as the op-by-op path below."""
+
+    @staticmethod
+    def forward(ctx, x, row, col, ptrs, shape, *params):
+        from . import _lib
+        dev = x.device
+        x = x.contiguous()
+        params = [p.contiguous() for p in params]
+        arena_bytes = _lib.lib.tsg_sag_arena_bytes(ctypes.byref(shape))
+        if arena_bytes == 0:
+            raise RuntimeError("tsg: bad SAG encoder shape")
+        arena = torch.empty(arena_bytes, dtype=torch.uint8, device=dev)
+        z = torch.empty(shape.num_graphs, 2 * shape.hidden, dtype=torch.float32, device=dev)
+        parr = (ctypes.c_void_p * 12)(*[p.data_ptr() for p in params])
+        _lib.call("tsg_sag_encoder_fwd", ctypes.byref(shape), _lib.ptr(x), _lib.ptr(row), _lib.ptr(col), _lib.ptr(ptrs),
+                  parr, _lib.ptr(z), _lib.ptr(arena), arena_bytes, _lib.stream_ptr())
+        ctx.shape, ctx.arena, ctx.arena_bytes = shape, arena, arena_bytes
+        ctx.save_for_backward(x, ptrs, *params)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        from . import _lib
+        x, ptrs, *params = ctx.saved_tensors
+        dz = dz.contiguous()
+        grads = [torch.empty_like(p) for p in params]
+        parr = (ctypes.c_void_p * 12)(*[p.data_ptr() for p in params])
+        garr = (ctypes.c_void_p * 12)(*[g.data_ptr() for g in grads])
+        _lib.call("tsg_sag_encoder_bwd", ctypes.byref(ctx.shape), _lib.ptr(x), _lib.ptr(ptrs), parr, _lib.ptr(dz), garr,
+                  _lib.ptr(ctx.arena), ctx.arena_bytes, _lib.stream_ptr())
+        ctx.arena = None
+        return (None, None, None, None, None, *grads)
+
+
 class PackedSAGNet(torch.nn.Module):
     """Code/sag/network.py `Net` over a packed batch.  Three levels of
     GCNConv -> ReLU -> SAGPool(score GCNConv, top-k, gate, filter_adj) -> [gmp || gap],
@@ -132,6 +173,19 @@ class PackedSAGNet(torch.nn.Module):
         # K2 shared-memory tiles: runs of whole graphs per pooling level (block-diagonal => self-contained)
         tiles = ([torch.from_numpy(ops.make_tiles(plan[l])).pin_memory().to(dev, non_blocking=True)
                   for l in range(3)] if ops.USE_TILED_SPMM else [None] * 3)
+        if USE_EXECUTOR and not return_aux and edges.count is None and x.dim() == 2:
+            from . import _lib
+            shape = _lib.SagShape(plan.shape[1] - 1, x.size(1), self.nhid, edges.cap)
+            for l in range(4):
+                shape.n[l] = int(plan[l, -1])
+            for l in range(3):
+                shape.max_graph_nodes[l] = max(int(np.diff(plan[l]).max()), 1)
+            if min(shape.n) > 0 and max(shape.max_graph_nodes) <= ops.GRAPH_CSR_MAX_NODES:
+                params = []
+                for conv, pool in ((self.conv1, self.pool1), (self.conv2, self.pool2), (self.conv3, self.pool3)):
+                    params += [conv.weight, conv.bias, pool.score_layer.weight, pool.score_layer.bias]
+                z = _SagEncoderFn.apply(x, edges.row, edges.col, ptrs, shape, *params)
+                return self.head(z)
         aux = {"perm": [], "edges": [], "score": []}
         outs = []
         for lvl, (conv, pool) in enumerate(((self.conv1, self.pool1), (self.conv2, self.pool2),
@@ -150,12 +204,15 @@ class PackedSAGNet(torch.nn.Module):
             outs.append(ops.readout(x, ptrs[lvl + 1]))                    # network.py:36
             if return_aux:
                 aux["perm"].append(perm); aux["edges"].append(edges); aux["score"].append(score)
-        z = outs[0] + outs[1] + outs[2]                                   # network.py:46
+        z = self.head(outs[0] + outs[1] + outs[2])                        # network.py:46
+        return (z, aux) if return_aux else z
+
+    def head(self, z: torch.Tensor) -> torch.Tensor:
+        """network.py:48-52: lin1 / ReLU / dropout / lin2 / ReLU / lin3 / log_softmax."""
         z = F.relu(self.lin1(z))
         z = F.dropout(z, p=self.dropout_ratio, training=self.training)
         z = F.relu(self.lin2(z))
-        z = F.log_softmax(self.lin3(z), dim=-1)
-        return (z, aux) if return_aux else z
+        return F.log_softmax(self.lin3(z), dim=-1)
 
 
 class PackedTripletNet(torch.nn.Module):
