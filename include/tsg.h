@@ -138,6 +138,13 @@ size_t tsg_colsum_workspace_bytes(int64_t num_rows, int64_t feat);
 int tsg_relu_bwd_colsum(const float* dY, const float* Y /*nullable*/, float* dY_masked /*nullable*/,
                         float* dbias, int64_t num_rows, int64_t feat,
                         void* workspace, size_t workspace_bytes, void* stream);
+/* Same with the gradient of a rank-1 branch added on the fly: g[r,f] = dY[r,f] + row_scale[r] * col_vec[f]
+ * before the mask (the score layer's  d h += d(h ws) ws^T  of Code/sag/layers.py:18 without materialising
+ * the [N,F] outer product or a separate add pass).  Product rounded before the add (== the unfused path). */
+int tsg_relu_bwd_colsum_rank1(const float* dY, const float* Y /*nullable*/, const float* row_scale,
+                              const float* col_vec, float* dY_masked /*nullable*/, float* dbias,
+                              int64_t num_rows, int64_t feat,
+                              void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * K3  tall-skinny row-local dense products (N ~ 10^6 rows, K and M <= 128 columns), fp32 FFMA,
@@ -279,6 +286,7 @@ int tsg_gate_gather_bwd(const float* dxo, const float* x, const float* score,
 #define TSG_READOUT_MAX 1
 #define TSG_READOUT_MEAN 2
 #define TSG_READOUT_SUM 4
+#define TSG_READOUT_ACCUM 8 /* tsg_readout_bwd only: dx += (instead of dx =), fusing the add of a second gradient */
 int tsg_readout_fwd(const float* x, const int64_t* graph_ptr, int64_t num_graphs, int64_t feat,
                     int mode, float* out, int64_t out_stride, int32_t* argmax, void* stream);
 /* dx[i,f] = (argmax[g,f]==i) * dout[g,f] + dout[g,F+f]/n_g ; g found from graph_ptr. */

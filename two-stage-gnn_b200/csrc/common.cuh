@@ -181,22 +181,32 @@ int exclusive_scan(F f, int64_t n, OutT* out, int* tile_ws, cudaStream_t st) {
 
 // ------------------------------------------------------------------------------------------
 // Second stage of every deterministic two-stage reduction: out[i] = sum_b part[b][i], b ascending
-// inside 8 fixed slices that are then combined in slice order.  Block (32 entries x 8 slices).
+// inside 32 fixed slices (4 independent accumulators each, so the loads overlap) that are then combined
+// in slice order.  Block = 32 entries x 32 slices; the order never depends on the grid or the device.
 // ------------------------------------------------------------------------------------------
-static __global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(1024)
 k_partial_sum_final(const float* __restrict__ part, float* __restrict__ out0, int n0,
                     float* __restrict__ out1, int nb, int total) {
-  __shared__ float sm[8][33];
+  __shared__ float sm[32][33];
   const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + x;
-  float s = 0.f;
-  if (i < total) for (int b = y; b < nb; b += 8) s += part[(size_t)b * total + i];
-  sm[y][x] = s;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (i < total) {
+    int b = y;
+    for (; b + 96 < nb; b += 128) {
+      s0 += part[(size_t)b * total + i];
+      s1 += part[(size_t)(b + 32) * total + i];
+      s2 += part[(size_t)(b + 64) * total + i];
+      s3 += part[(size_t)(b + 96) * total + i];
+    }
+    for (; b < nb; b += 32) s0 += part[(size_t)b * total + i];
+  }
+  sm[y][x] = (s0 + s1) + (s2 + s3);
   __syncthreads();
   if (y == 0 && i < total) {
     float t = sm[0][x];
 #pragma unroll
-    for (int k = 1; k < 8; ++k) t += sm[k][x];
+    for (int k = 1; k < 32; ++k) t += sm[k][x];
     if (i < n0) { if (out0) out0[i] = t; }
     else if (out1) out1[i - n0] = t;
   }
@@ -204,7 +214,7 @@ k_partial_sum_final(const float* __restrict__ part, float* __restrict__ out0, in
 
 static inline void launch_partial_sum_final(const float* part, float* out0, int n0, float* out1, int nb,
                                             int total, cudaStream_t st) {
-  k_partial_sum_final<<<(total + 31) / 32, 256, 0, st>>>(part, out0, n0, out1, nb, total);
+  k_partial_sum_final<<<(total + 31) / 32, 1024, 0, st>>>(part, out0, n0, out1, nb, total);
 }
 
 }  // namespace tsg

@@ -35,7 +35,7 @@ struct LevelBuf {
 struct SagArena {
   LevelBuf lv[3];
   // backward temporaries, sized for level 0 and reused by every level
-  float *dxg, *dh, *dh_score, *dhm, *dxw, *dx_next, *dscore, *dsw, *db_tmp;
+  float *dxg, *dh, *dhm, *dxw, *dscore, *dsw;
   void* scratch; size_t scratch_bytes;
   size_t total;
 };
@@ -82,9 +82,9 @@ static void layout(const tsg_sag_shape* sh, void* arena, SagArena* a) {
     b.argmax = (int32_t*)take(G * H * 4);
   }
   const int64_t n0 = sh->n[0] > 0 ? sh->n[0] : 1;
-  a->dxg = (float*)take(n0 * H * 4); a->dh = (float*)take(n0 * H * 4); a->dh_score = (float*)take(n0 * H * 4);
-  a->dhm = (float*)take(n0 * H * 4); a->dxw = (float*)take(n0 * H * 4); a->dx_next = (float*)take(n0 * H * 4);
-  a->dscore = (float*)take(n0 * 4); a->dsw = (float*)take(n0 * 4); a->db_tmp = (float*)take(256);
+  a->dxg = (float*)take(n0 * H * 4); a->dh = (float*)take(n0 * H * 4);
+  a->dhm = (float*)take(n0 * H * 4); a->dxw = (float*)take(n0 * H * 4);
+  a->dscore = (float*)take(n0 * 4); a->dsw = (float*)take(n0 * 4);
   a->scratch_bytes = scratch_need(sh);
   a->scratch = take(a->scratch_bytes);
   a->total = off;
@@ -94,21 +94,6 @@ __global__ void __launch_bounds__(256)
 k_add3(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c, float* __restrict__ o, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     o[i] = (a[i] + b[i]) + c[i];
-}
-
-// a[i] += b[i], 128-bit where possible (n4 float4 + tail)
-__global__ void __launch_bounds__(256)
-k_add_inplace(float* __restrict__ a, const float* __restrict__ b, int64_t n) {
-  const int64_t n4 = n >> 2;
-  float4* a4 = reinterpret_cast<float4*>(a);
-  const float4* b4 = reinterpret_cast<const float4*>(b);
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-    float4 x = a4[i]; const float4 y = b4[i];
-    x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w;
-    a4[i] = x;
-  }
-  for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    a[i] += b[i];
 }
 
 static bool shape_ok(const tsg_sag_shape* sh) {
@@ -190,19 +175,18 @@ extern "C" int tsg_sag_encoder_bwd(const tsg_sag_shape* sh, const float* x, cons
     const float* xin = l == 0 ? x : a.lv[l - 1].xg;
     const int64_t* ptr_n = level_ptr + (size_t)(l + 1) * (G + 1);
     // d(x_{l+1}) = readout backward (+ the next level's input gradient)
-    TSG_TRY(tsg_readout_bwd(dz, 2 * H, b.argmax, ptr_n, G, k, H, TSG_READOUT_MAX | TSG_READOUT_MEAN, a.dxg, stream));
-    if (l < 2) k_add_inplace<<<grid_for(k * H / 4 + 1, 256, 16), 256, 0, st>>>(a.dxg, a.dx_next, k * H);
+    //   (the next level's linear backward already wrote its dX into a.dxg: accumulate in place)
+    TSG_TRY(tsg_readout_bwd(dz, 2 * H, b.argmax, ptr_n, G, k, H,
+                            TSG_READOUT_MAX | TSG_READOUT_MEAN | (l < 2 ? TSG_READOUT_ACCUM : 0), a.dxg, stream));
     TSG_TRY(tsg_gate_gather_bwd(a.dxg, b.h, b.score, b.inv, a.dh, a.dscore, n, H, stream));
     // score layer: score = A_hat (h ws) + bs
     TSG_TRY(tsg_relu_bwd_colsum(a.dscore, nullptr, nullptr, dbs, n, 1, a.scratch, a.scratch_bytes, stream));
     TSG_TRY(tsg_spmm(b.t_rowptr, b.t_colidx, b.t_val, a.dscore, nullptr, a.dsw, n, 1, 0, stream));
-    TSG_TRY(tsg_linear_fwd(a.dsw, ws, nullptr, a.dh_score, n, 1, H, 1, 0, stream));
     TSG_TRY(tsg_linear_bwd_weight(b.h, a.dsw, dws, nullptr, n, H, 1, a.scratch, a.scratch_bytes, stream));
-    k_add_inplace<<<grid_for(n * H / 4 + 1, 256, 16), 256, 0, st>>>(a.dh, a.dh_score, n * H);
-    // conv layer: h = ReLU(A_hat (x W) + b)
-    TSG_TRY(tsg_relu_bwd_colsum(a.dh, b.h, a.dhm, dbias, n, H, a.scratch, a.scratch_bytes, stream));
+    // conv layer: h = ReLU(A_hat (x W) + b); its incoming gradient is dh + dsw ws^T, added on the fly
+    TSG_TRY(tsg_relu_bwd_colsum_rank1(a.dh, b.h, a.dsw, ws, a.dhm, dbias, n, H, a.scratch, a.scratch_bytes, stream));
     TSG_TRY(tsg_spmm(b.t_rowptr, b.t_colidx, b.t_val, a.dhm, nullptr, a.dxw, n, H, 0, stream));
-    if (l > 0) TSG_TRY(tsg_linear_fwd(a.dxw, W, nullptr, a.dx_next, n, H, fin, 1, 0, stream));
+    if (l > 0) TSG_TRY(tsg_linear_fwd(a.dxw, W, nullptr, a.dxg, n, H, fin, 1, 0, stream));   // d(x_l), k_{l-1} = n rows
     TSG_TRY(tsg_linear_bwd_weight(xin, a.dxw, dW, nullptr, n, fin, H, a.scratch, a.scratch_bytes, stream));
   }
   return check_launch("sag_encoder_bwd");

@@ -426,7 +426,8 @@ constexpr int CS_MAX_BLOCKS = TSG_NUM_SMS * 8;
 
 __global__ void __launch_bounds__(CS_THREADS)
 k_relu_bwd_colsum(const float* __restrict__ dY, const float* __restrict__ Y, float* __restrict__ dYm,
-                  float* __restrict__ part, int64_t N, int F, int64_t rows_per_block) {
+                  float* __restrict__ part, int64_t N, int F, int64_t rows_per_block,
+                  const float* __restrict__ row_scale, const float* __restrict__ col_vec) {
   // thread layout: column f = threadIdx.x % Fp, row lane = threadIdx.x / Fp  (Fp = cols per pass)
   extern __shared__ float sm[];
   int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
@@ -438,8 +439,10 @@ k_relu_bwd_colsum(const float* __restrict__ dY, const float* __restrict__ Y, flo
     int lane_r = threadIdx.x / cols;
     float acc = 0.f;
     if (lane_r < rl && f < F) {
+      const float cv = col_vec ? col_vec[f] : 0.f;
       for (int64_t r = r0 + lane_r; r < r1; r += rl) {
         float g = dY[r * F + f];
+        if (row_scale) g = __fadd_rn(g, __fmul_rn(row_scale[r], cv));
         if (Y != nullptr && !(Y[r * F + f] > 0.f)) g = 0.f;
         if (dYm != nullptr) dYm[r * F + f] = g;
         acc += g;
@@ -515,16 +518,27 @@ extern "C" size_t tsg_colsum_workspace_bytes(int64_t N, int64_t F) {
   return ws_bytes((size_t)colsum_blocks(N) * (size_t)F, 4) + 256;
 }
 
+extern "C" int tsg_relu_bwd_colsum_rank1(const float* dY, const float* Y, const float* row_scale, const float* col_vec,
+                                         float* dYm, float* dbias, int64_t N, int64_t F,
+                                         void* workspace, size_t workspace_bytes, void* stream);
+
 extern "C" int tsg_relu_bwd_colsum(const float* dY, const float* Y, float* dYm, float* dbias,
                                    int64_t N, int64_t F, void* workspace, size_t workspace_bytes,
                                    void* stream) {
+  return tsg_relu_bwd_colsum_rank1(dY, Y, nullptr, nullptr, dYm, dbias, N, F, workspace, workspace_bytes, stream);
+}
+
+extern "C" int tsg_relu_bwd_colsum_rank1(const float* dY, const float* Y, const float* row_scale, const float* col_vec,
+                                         float* dYm, float* dbias, int64_t N, int64_t F,
+                                         void* workspace, size_t workspace_bytes, void* stream) {
   TSG_REQUIRE(N >= 0 && F > 0 && dY && dbias, "relu_bwd_colsum: bad arguments");
+  TSG_REQUIRE((row_scale == nullptr) == (col_vec == nullptr), "relu_bwd_colsum: row_scale and col_vec go together");
   cudaStream_t st = (cudaStream_t)stream;
   if (workspace_bytes < tsg_colsum_workspace_bytes(N, F)) { set_error("relu_bwd_colsum: workspace too small"); return TSG_EWORKSPACE; }
   float* part = (float*)workspace;
   int nb = colsum_blocks(N);
   int64_t rpb = (N + nb - 1) / nb; if (rpb < 1) rpb = 1;
-  k_relu_bwd_colsum<<<nb, CS_THREADS, CS_THREADS * sizeof(float), st>>>(dY, Y, dYm, part, N, (int)F, rpb);
+  k_relu_bwd_colsum<<<nb, CS_THREADS, CS_THREADS * sizeof(float), st>>>(dY, Y, dYm, part, N, (int)F, rpb, row_scale, col_vec);
   launch_partial_sum_final(part, dbias, (int)F, nullptr, nb, (int)F, st);
   return check_launch("relu_bwd_colsum");
 }

@@ -127,9 +127,13 @@ k_readout_bwd(const float* __restrict__ dout, int64_t dstride, const int* __rest
 #pragma unroll
         for (int v = 0; v < VEC; ++v) r[v] = gs[v] + ((am[v] == (int)(lo + i)) ? gm[v] : 0.f);
         if (VEC == 4) {
-          reinterpret_cast<float4*>(dx)[(lo + i) * FV + f] = make_float4(r[0], r[1 % VEC], r[2 % VEC], r[3 % VEC]);
+          float4* p = reinterpret_cast<float4*>(dx) + (lo + i) * FV + f;
+          float4 o = make_float4(r[0], r[1 % VEC], r[2 % VEC], r[3 % VEC]);
+          if (mode & TSG_READOUT_ACCUM) { const float4 e = *p; o.x += e.x; o.y += e.y; o.z += e.z; o.w += e.w; }
+          *p = o;
         } else {
-          dx[(lo + i) * FV + f] = r[0];
+          float* p = dx + (lo + i) * FV + f;
+          *p = (mode & TSG_READOUT_ACCUM) ? *p + r[0] : r[0];
         }
       }
     }

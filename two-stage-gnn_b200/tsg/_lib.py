@@ -31,6 +31,7 @@ _PROTOTYPES = {
     "tsg_spmm_tiled": (I, [P, P, P, P, P, P, P, I64, I64, I64, I, P]),
     "tsg_colsum_workspace_bytes": (SZ, [I64, I64]),
     "tsg_relu_bwd_colsum": (I, [P, P, P, P, I64, I64, P, SZ, P]),
+    "tsg_relu_bwd_colsum_rank1": (I, [P, P, P, P, P, P, I64, I64, P, SZ, P]),
     "tsg_linear_fwd": (I, [P, P, P, P, I64, I64, I64, I, I, P]),
     "tsg_dense_epilogue_bwd": (I, [P, P, P, P, P, I64, I64, I64, I, P]),
     "tsg_linear_bwd_weight_workspace_bytes": (SZ, [I64, I64]),
@@ -91,7 +92,7 @@ KERNELS_PER_CALL = {
     "tsg_batch_to_ptr": 1, "tsg_filter_adj": 7, "tsg_gate_gather_fwd": 1, "tsg_gate_gather_bwd": 1,
     "tsg_readout_fwd": 1, "tsg_readout_bwd": 1, "tsg_triplet_fwd": 2, "tsg_triplet_bwd": 9,
     "tsg_pairdist_matrix": 1, "tsg_linear_fwd": 1, "tsg_dense_epilogue_bwd": 1, "tsg_linear_bwd_weight": 2,
-    "tsg_sag_encoder_fwd": 43, "tsg_sag_encoder_bwd": 51, "tsg_seg_contract": 1, "tsg_seg_linear": 1, "tsg_gat_fwd": 2, "tsg_gat_bwd": 2, "tsg_dense_to_coo": 6, "tsg_nodebn_fwd": 1, "tsg_nodebn_bwd": 1,
+    "tsg_sag_encoder_fwd": 43, "tsg_sag_encoder_bwd": 42, "tsg_relu_bwd_colsum_rank1": 2, "tsg_seg_contract": 1, "tsg_seg_linear": 1, "tsg_gat_fwd": 2, "tsg_gat_bwd": 2, "tsg_dense_to_coo": 6, "tsg_nodebn_fwd": 1, "tsg_nodebn_bwd": 1,
 }
 launch_calls = 0        # libtsg entry points called since import
 kernel_launches = 0     # kernels enqueued by them
