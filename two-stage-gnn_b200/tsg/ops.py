@@ -18,6 +18,7 @@ from ._lib import call, ptr, stream_ptr, workspace, lib
 
 CSR_GCN, CSR_RAW = 0, 1
 USE_TILED_SPMM = False   # shared-memory-staged K2 (tsg_spmm_tiled); measured slower than the L1-blocked kernel
+USE_TCGEN05 = True      # tcgen05 (3xTF32, TMEM) kernel for the K7 contraction / GEMM-shaped dW; False = fp32 SIMT kernels
 SPMM_RELU = 1
 SPMM_EXACT = 2
 SPMM_EXACT_DEFAULT = False   # True: separately rounded products everywhere (6 % slower K2)
@@ -219,9 +220,36 @@ def linear_raw(x: torch.Tensor, w: torch.Tensor, bias=None, transposed: bool = F
     return y
 
 
+DW_TC_MIN_WORK = 64 * 64        # K*M at which dW = X^T dY moves from the tall-skinny SIMT kernel to tcgen05
+DW_TC_SEG_ROWS = 512            # tcgen05 accumulates fp32 with truncation: the error grows linearly with the rows per
+                                # accumulator (measured 1.7e-6 @256, 7e-6 @1024, 2.8e-5 @4096), so segments stay short
+
+
+def _linear_bwd_weight_tc(x: torch.Tensor, dy: torch.Tensor) -> torch.Tensor:
+    """dW = X^T dY for GEMM-shaped K x M (DiffPool's Linear(164 -> 100) on ~10^6 rows) on the K7 tcgen05
+    contraction: rows are cut into fixed pseudo-segments of DW_TC_SEG_ROWS, every segment's partial K x M product is
+    one CTA's TMEM accumulator (3xTF32), partials are summed by one fixed-shape reduction (deterministic)."""
+    n, k = x.shape; m = dy.size(1)
+    segs = (n + DW_TC_SEG_ROWS - 1) // DW_TC_SEG_ROWS
+    ptr_ = torch.arange(segs + 1, device=x.device, dtype=torch.int64) * DW_TC_SEG_ROWS
+    ptr_[-1] = n
+    out = torch.empty(k, m, dtype=torch.float32, device=x.device)
+    for m0 in range(0, m, 256):
+        dyc = dy if (m0 == 0 and m <= 256) else dy[:, m0:m0 + 256].contiguous()
+        for k0 in range(0, k, 128):
+            xc = x if (k0 == 0 and k <= 128) else x[:, k0:k0 + 128].contiguous()
+            part = seg_contract_raw(xc, dyc, ptr_, tensor_cores=True)            # [segs, kx, my]
+            out[k0:k0 + xc.size(1), m0:m0 + dyc.size(1)] = part.sum(dim=0)
+    return out
+
+
 def linear_bwd_weight(x: torch.Tensor, dy: torch.Tensor, want_bias: bool):
     x = x.contiguous(); dy = dy.contiguous()
     n, k = x.shape; m = dy.size(1)
+    if USE_TCGEN05 and k * m >= DW_TC_MIN_WORK and n >= 16384 and k % 4 == 0 and m % 4 == 0:
+        dw = _linear_bwd_weight_tc(x, dy)
+        db = relu_bwd_colsum(dy, None, want_masked=False)[1] if want_bias else None
+        return dw, db
     dw = torch.empty(k, m, dtype=torch.float32, device=x.device)
     db = torch.empty(m, dtype=torch.float32, device=x.device) if want_bias else None
     wsb = lib.tsg_linear_bwd_weight_workspace_bytes(k, m)
@@ -427,7 +455,6 @@ def pairdist_matrix(emb: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
 # --------------------------------------------------------------------------------------------
 # K7 per-graph dense contractions (DiffPool)
 # --------------------------------------------------------------------------------------------
-USE_TCGEN05 = True      # tcgen05 (3xTF32, TMEM) kernel for the contraction; False = fp32 SIMT kernel
 
 
 def seg_contract_raw(x: torch.Tensor, y: torch.Tensor, graph_ptr: torch.Tensor,
