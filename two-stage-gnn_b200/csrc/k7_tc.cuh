@@ -12,6 +12,7 @@
 // SASS evidence: UTCHMMA / UTCCP-free path with LDTM in the epilogue (see profiles/).
 #pragma once
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace tsg {
 
@@ -185,12 +186,231 @@ k_seg_contract_tc(const float* __restrict__ X, const float* __restrict__ Y, cons
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// v2: TMA-fed, pipelined.  v1 above serialises  stage (scalar global loads) -> MMA -> wait  per 32-row
+// chunk (ncu: tensor pipe 12.7 %, issue 19.5 %: latency bound).  Here
+//   * the raw fp32 rows of a chunk (KC2 contraction rows of X and of Y; contiguous in global memory
+//     because both operands are row-major with the contraction index as the row) are fetched by the TMA
+//     engine: one thread arms an mbarrier with the byte count and issues two `cp.async.bulk` copies;
+//     three raw stages are in flight, so HBM latency never sits on the critical path;
+//   * the 128 threads transpose + hi/lo-split a landed raw stage into the K-major MMA tiles (the 3xTF32
+//     split has to pass through registers, so this is the only SIMT work left) -- the MMA tiles are
+//     double buffered and guarded by their own mbarriers (tcgen05.commit), so the tensor pipe works on
+//     chunk i while the threads transform chunk i+1 and the TMA loads chunks i+2..i+4.
+// Needs Kx % 4 == 0 and Ky % 4 == 0 (16-byte TMA granularity); other widths use v1.
+// ------------------------------------------------------------------------------------------
+constexpr int KC2 = 16;                   // contraction rows per chunk (2 MMA k-steps of 8)
+constexpr int RAW_STAGES = 4;
+constexpr int TC2_SPIN_LIMIT = 1 << 18;   // hang guard (a wait normally returns within microseconds)
+
+__device__ __forceinline__ bool mbar_wait2(uint32_t bar, uint32_t parity) {
+  for (int spin = 0; spin < TC2_SPIN_LIMIT; ++spin) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) return true;
+  }
+  return false;
+}
+
+__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// raw [k][width] fp32 (as landed by the TMA) -> K-major no-swizzle hi / lo tiles; k >= rows zero-filled.
+// 512 threads = 4 groups of contraction rows (kq = tid / 128) x 128 feature columns (n = tid % 128, + 128
+// for the wide operand): no index division, consecutive shared-memory words per warp, and a branch-free
+// fast path for full chunks.  Columns beyond the operand width never reach a stored output.
+constexpr int TC2_THREADS = 512;
+static_assert(KC2 == 16, "transform_operand maps tid / 128 to the 4 row groups of a 16-row chunk");
+
+template <bool FULL>
+__device__ __forceinline__ void transform_item(const float* __restrict__ raw, int rows, int width, int n, int kq,
+                                               char* hi, char* lo) {
+  constexpr uint32_t SBO = (KC2 / 4) * 128;
+  const float* src = raw + (kq * 4) * width + n;
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float v = (FULL || kq * 4 + i < rows) ? src[i * width] : 0.f;
+    h[i] = to_tf32(v);
+    l[i] = to_tf32(v - __uint_as_float(h[i]));
+  }
+  const uint32_t off = (uint32_t)(n >> 3) * SBO + (uint32_t)kq * 128 + (uint32_t)(n & 7) * 16;
+  *reinterpret_cast<uint4*>(hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+__device__ __forceinline__ void transform_operand(const float* __restrict__ raw, int rows, int width,
+                                                  char* hi, char* lo) {
+  const int kq = threadIdx.x >> 7, n0 = threadIdx.x & 127;
+  if (rows == KC2) {
+    for (int n = n0; n < width; n += 128) transform_item<true>(raw, rows, width, n, kq, hi, lo);
+  } else {
+    for (int n = n0; n < width; n += 128) transform_item<false>(raw, rows, width, n, kq, hi, lo);
+  }
+}
+
+template <int NPAD>
+__global__ void __launch_bounds__(TC2_THREADS + 32)
+k_seg_contract_tc2(const float* __restrict__ X, const float* __restrict__ Y, const int64_t* __restrict__ gptr,
+                   int Kx, int Ky, int Nmma, float* __restrict__ C, int* __restrict__ err) {
+  extern __shared__ __align__(128) char tc_smem[];
+  constexpr int A_BYTES = TC_M * KC2 * 4, B_BYTES = NPAD * KC2 * 4;
+  constexpr int MMA_SET = 2 * A_BYTES + 2 * B_BYTES;                 // a_hi a_lo b_hi b_lo
+  constexpr int TWARPS = TC2_THREADS / 32;                           // transform warps
+  char* mma_buf = tc_smem;                                           // 2 sets
+  char* raw_buf = tc_smem + 2 * MMA_SET;                             // RAW_STAGES x raw_stride
+  const int raw_stride = (KC2 * (Kx + Ky) * 4 + 127) & ~127;
+  __shared__ __align__(8) uint64_t bar_raw[RAW_STAGES];              // TMA landed (tx bytes)
+  __shared__ __align__(8) uint64_t bar_full[2];                      // MMA tile set written (TWARPS arrivals)
+  __shared__ __align__(8) uint64_t bar_mma[2];                       // MMAs that read the set are done (commit)
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = blockIdx.x;
+  const int64_t lo_r = gptr[g], hi_r = gptr[g + 1];
+  const int nch = (int)((hi_r - lo_r + KC2 - 1) / KC2);
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "r"((uint32_t)NPAD) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < RAW_STAGES; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&bar_raw[i])), "r"(1u) : "memory");
+    for (int i = 0; i < 2; ++i) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&bar_full[i])), "r"((uint32_t)TWARPS) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&bar_mma[i])), "r"(1u) : "memory");
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_base_s;
+  bool ok = true;
+
+  if (warp == TWARPS) {
+    // ---------------- issuer warp: one lane feeds the TMA engine and the tensor pipe
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(TC_M, Nmma);
+      constexpr uint32_t SBO = (KC2 / 4) * 128, LBO = 128;
+      auto issue_tma = [&](int i) {
+        const int64_t r0 = lo_r + (int64_t)i * KC2;
+        const int rows = (int)min((int64_t)KC2, hi_r - r0);
+        const int s = i % RAW_STAGES;
+        const uint32_t bar = smem_u32(&bar_raw[s]);
+        const uint32_t bx = (uint32_t)rows * Kx * 4, by = (uint32_t)rows * Ky * 4;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bx + by) : "memory");
+        const uint32_t dst = smem_u32(raw_buf + (size_t)s * raw_stride);
+        tma_load_1d(dst, X + r0 * Kx, bx, bar);
+        tma_load_1d(dst + (uint32_t)KC2 * Kx * 4, Y + r0 * Ky, by, bar);
+      };
+      for (int i = 0; i < RAW_STAGES && i < nch; ++i) issue_tma(i);
+      for (int i = 0; i < nch && ok; ++i) {
+        const int t = i & 1;
+        ok = mbar_wait2(smem_u32(&bar_full[t]), (uint32_t)((i >> 1) & 1));       // set t written, raw stage consumed
+        if (i + RAW_STAGES < nch) issue_tma(i + RAW_STAGES);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_hi = smem_u32(mma_buf + (size_t)t * MMA_SET), a_lo = a_hi + A_BYTES;
+        const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < KC2 / 8; ++ks) {
+          const uint32_t koff = ks * 2 * 128;
+          const uint64_t ah = make_desc(a_hi + koff, LBO, SBO), al = make_desc(a_lo + koff, LBO, SBO);
+          const uint64_t bh = make_desc(b_hi + koff, LBO, SBO), bl = make_desc(b_lo + koff, LBO, SBO);
+          mma_tf32(tmem, al, bh, idesc, (i > 0 || ks > 0) ? 1u : 0u);  // small terms first
+          mma_tf32(tmem, ah, bl, idesc, 1u);
+          mma_tf32(tmem, ah, bh, idesc, 1u);
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&bar_mma[t])) : "memory");
+      }
+    }
+  } else {
+    // ---------------- transform warps
+    for (int i = 0; i < nch && ok; ++i) {
+      const int s = i % RAW_STAGES, t = i & 1;
+      const int rows = (int)min((int64_t)KC2, hi_r - (lo_r + (int64_t)i * KC2));
+      ok = mbar_wait2(smem_u32(&bar_raw[s]), (uint32_t)((i / RAW_STAGES) & 1));              // raw chunk landed
+      if (i >= 2) ok = mbar_wait2(smem_u32(&bar_mma[t]), (uint32_t)(((i >> 1) - 1) & 1)) && ok;  // MMA(i-2) left set t
+      char* set = mma_buf + (size_t)t * MMA_SET;
+      const float* raw = reinterpret_cast<const float*>(raw_buf + (size_t)s * raw_stride);
+      transform_operand(raw, rows, Kx, set, set + A_BYTES);
+      transform_operand(raw + KC2 * Kx, rows, Ky, set + 2 * A_BYTES, set + 2 * A_BYTES + B_BYTES);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes -> async proxy
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(&bar_full[t])) : "memory");
+    }
+  }
+  if (nch > 0 && ok) {                                                 // the last commit covers every earlier MMA
+    const int last = nch - 1;
+    ok = mbar_wait2(smem_u32(&bar_mma[last & 1]), (uint32_t)((last >> 1) & 1));
+  }
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (!ok) atomicExch(err, 1);                          // any role's hang guard tripped
+
+  // epilogue: 16 warps; warp w reads TMEM lanes 32*(w%4).. (its hardware lane quarter) and the column slabs
+  // c0 = 32*(w/4), +128, ...; thread = accumulator row m
+  const int m = (warp & 3) * 32 + lane;
+  const bool epi = warp < TC2_THREADS / 32;              // the issuer warp has no TMEM lane quarter of its own here
+  float* Cg = C + (int64_t)g * Kx * Ky;
+  for (int c0 = (warp >> 2) * 32; c0 < Nmma; c0 += 32 * (TC2_THREADS / 128)) {
+    uint32_t v[32];
+    if (!epi) break;
+    if (nch > 0) {
+      const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+            "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+            "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+            "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+          : "r"(taddr) : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = 0u;
+    }
+    if (m < Kx) {
+      if (c0 + 32 <= Ky) {                                   // full 32-column slab: 128-bit stores (Ky % 4 == 0)
+        float4* dst = reinterpret_cast<float4*>(Cg + (int64_t)m * Ky + c0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                               __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c0 + i < Ky) Cg[(int64_t)m * Ky + c0 + i] = __uint_as_float(v[i]);
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"((uint32_t)NPAD) : "memory");
+  }
+}
+
 static int launch_seg_contract_tc(const float* X, const float* Y, const int64_t* gptr, int G, int Kx, int Ky,
                                   float* C, int* err, cudaStream_t st) {
   if (Kx > 128 || Ky > 256) { set_error("seg_contract(tcgen05): needs Kx <= 128 and Ky <= 256 (got %d, %d)", Kx, Ky); return TSG_EINVAL; }
   int Nmma = (Ky + 15) / 16 * 16;
   if (Nmma < 16) Nmma = 16;
   int npad = Nmma <= 64 ? 64 : (Nmma <= 128 ? 128 : 256);
+  static const bool force_v1 = getenv("TSG_K7_V1") != nullptr;
+  if (!force_v1 && Kx % 4 == 0 && Ky % 4 == 0 && (((uintptr_t)X | (uintptr_t)Y | (uintptr_t)C) & 15) == 0) {
+    const size_t raw_stride = ((size_t)KC2 * (Kx + Ky) * 4 + 127) & ~(size_t)127;
+    const size_t smem2 = 2 * (2 * (size_t)TC_M * KC2 * 4 + 2 * (size_t)npad * KC2 * 4) + RAW_STAGES * raw_stride + 128;
+#define TSG_GO2(NP)                                                                                        \
+    cudaFuncSetAttribute(k_seg_contract_tc2<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);   \
+    k_seg_contract_tc2<NP><<<G, TC2_THREADS + 32, smem2, st>>>(X, Y, gptr, Kx, Ky, Nmma, C, err)
+    if (npad == 64) { TSG_GO2(64); } else if (npad == 128) { TSG_GO2(128); } else { TSG_GO2(256); }
+#undef TSG_GO2
+    return check_launch("seg_contract(tcgen05 v2)");
+  }
   size_t smem = 2 * TC_A_BYTES + 2 * (size_t)npad * TC_KC * 4 + 128;
 #define TSG_GO(NP)                                                                                        \
   cudaFuncSetAttribute(k_seg_contract_tc<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
