@@ -124,6 +124,107 @@ k_gat_bwd_col(const int* __restrict__ t_rowptr, const int* __restrict__ t_colidx
   }
 }
 
+// v2 of the column kernel for F % 4 == 0: warp per (column j, head); the 32 lanes are 4 entry slots x 8 lanes,
+// each 8-lane group owns one column entry per step and reads its dhp row as float4 (128-bit gathers, 4
+// independent entries in flight instead of one entry at a time with a 5-step shuffle reduction per entry).
+// Two sweeps like v1 (the second re-reads the just-gathered rows from L1/L2); d_alpha is recomputed instead of
+// round-tripping through a global scratch array.  Fixed reduction order: deterministic.
+template <int GB_MAXF4>                             // float4 per lane: F <= 32 * GB_MAXF4
+__global__ void __launch_bounds__(256)
+k_gat_bwd_col_v4(const int* __restrict__ t_rowptr, const int* __restrict__ t_colidx, const int* __restrict__ t_eid,
+                 const float* __restrict__ h, const float* __restrict__ s1, const float* __restrict__ s2,
+                 const float* __restrict__ mx, const float* __restrict__ zs, const float* __restrict__ dhp,
+                 int n, int heads, int F, float slope, float* __restrict__ dz_coo,
+                 float* __restrict__ dh, float* __restrict__ ds2) {
+  const int lane = threadIdx.x & 31, grp = lane >> 3, l = lane & 7;
+  const int W4 = heads * F / 4, F4 = F / 4;
+  const int64_t items = (int64_t)n * heads;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const float4* h4 = reinterpret_cast<const float4*>(h);
+  const float4* d4p = reinterpret_cast<const float4*>(dhp);
+  for (int64_t it = warp; it < items; it += nwarps) {
+    const int j = (int)(it / heads), hd = (int)(it - (int64_t)j * heads);
+    const int p0 = t_rowptr[j], p1 = t_rowptr[j + 1];
+    const float sj = s2[it], m = mx[it], z = zs[it];
+    float4 hj[GB_MAXF4];
+#pragma unroll
+    for (int q = 0; q < GB_MAXF4; ++q)
+      hj[q] = (l + 8 * q < F4) ? h4[(int64_t)j * W4 + hd * F4 + l + 8 * q] : make_float4(0.f, 0.f, 0.f, 0.f);
+    // sweep 1: t = sum_i alpha_ij (dhp_i . h_j)
+    float t = 0.f;
+    for (int pb = p0; pb < p1; pb += 4) {
+      const int p = pb + grp;
+      const bool valid = p < p1;
+      const int i = valid ? t_colidx[p] : j;
+      float part = 0.f;
+#pragma unroll
+      for (int q = 0; q < GB_MAXF4; ++q) {
+        if (l + 8 * q < F4) {
+          const float4 d = d4p[(int64_t)i * W4 + hd * F4 + l + 8 * q];
+          part += d.x * hj[q].x + d.y * hj[q].y + d.z * hj[q].z + d.w * hj[q].w;
+        }
+      }
+      part += __shfl_xor_sync(0xffffffffu, part, 1);
+      part += __shfl_xor_sync(0xffffffffu, part, 2);
+      part += __shfl_xor_sync(0xffffffffu, part, 4);
+      const float a = expf(lrelu(s1[(int64_t)i * heads + hd] + sj, slope) - m) / z;
+      if (valid) t += a * part;
+    }
+    t += __shfl_xor_sync(0xffffffffu, t, 8);
+    t += __shfl_xor_sync(0xffffffffu, t, 16);
+    // sweep 2: dz_ij, ds2_j and dh_j = sum_i alpha_ij dhp_i
+    float dsum = 0.f;
+    float4 acc[GB_MAXF4];
+#pragma unroll
+    for (int q = 0; q < GB_MAXF4; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int pb = p0; pb < p1; pb += 4) {
+      const int p = pb + grp;
+      const bool valid = p < p1;
+      const int i = valid ? t_colidx[p] : j;
+      float4 d[GB_MAXF4];
+      float part = 0.f;
+#pragma unroll
+      for (int q = 0; q < GB_MAXF4; ++q) {
+        if (l + 8 * q < F4) {
+          d[q] = d4p[(int64_t)i * W4 + hd * F4 + l + 8 * q];
+          part += d[q].x * hj[q].x + d[q].y * hj[q].y + d[q].z * hj[q].z + d[q].w * hj[q].w;
+        } else {
+          d[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      part += __shfl_xor_sync(0xffffffffu, part, 1);
+      part += __shfl_xor_sync(0xffffffffu, part, 2);
+      part += __shfl_xor_sync(0xffffffffu, part, 4);
+      const float pre = s1[(int64_t)i * heads + hd] + sj;
+      const float a = expf(lrelu(pre, slope) - m) / z;
+      if (valid) {
+        const float dzv = a * (part - t) * (pre > 0.f ? 1.f : slope);
+        dsum += dzv;
+        if (l == 0) dz_coo[(int64_t)t_eid[p] * heads + hd] = dzv;
+#pragma unroll
+        for (int q = 0; q < GB_MAXF4; ++q) {
+          acc[q].x = fmaf(a, d[q].x, acc[q].x); acc[q].y = fmaf(a, d[q].y, acc[q].y);
+          acc[q].z = fmaf(a, d[q].z, acc[q].z); acc[q].w = fmaf(a, d[q].w, acc[q].w);
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < GB_MAXF4; ++q) {
+#pragma unroll
+      for (int o = 8; o <= 16; o <<= 1) {
+        acc[q].x += __shfl_xor_sync(0xffffffffu, acc[q].x, o); acc[q].y += __shfl_xor_sync(0xffffffffu, acc[q].y, o);
+        acc[q].z += __shfl_xor_sync(0xffffffffu, acc[q].z, o); acc[q].w += __shfl_xor_sync(0xffffffffu, acc[q].w, o);
+      }
+      if (grp == 0 && l + 8 * q < F4)
+        reinterpret_cast<float4*>(dh)[(int64_t)j * W4 + hd * F4 + l + 8 * q] = acc[q];
+    }
+    dsum += __shfl_xor_sync(0xffffffffu, dsum, 8);
+    dsum += __shfl_xor_sync(0xffffffffu, dsum, 16);
+    if (lane == 0) ds2[it] = dsum;
+  }
+}
+
 __global__ void __launch_bounds__(256)
 k_gat_bwd_row(const int* __restrict__ rowptr, const int* __restrict__ eid, const float* __restrict__ dz_coo,
               int n, int heads, float* __restrict__ ds1) {
@@ -183,8 +284,15 @@ extern "C" int tsg_gat_bwd(const int32_t* rowptr, const int32_t* eid, const int3
   Workspace ws(workspace, workspace_bytes);
   float* dal = ws.take<float>((nnz + 1) * heads);
   float* dz = ws.take<float>((nnz + 1) * heads);
-  k_gat_bwd_col<<<grid_for(n, 8), 256, 0, st>>>(t_rowptr, t_colidx, t_eid, h, s1, s2, mx, zs, dhp, (int)n, (int)heads,
-                                                (int)F, slope, dal, dz, dh, ds2);
+  if (F % 4 == 0 && ((((uintptr_t)h) | ((uintptr_t)dhp) | ((uintptr_t)dh)) & 15) == 0)
+  {
+#define TSG_GB(Q) k_gat_bwd_col_v4<Q><<<grid_for(n * heads, 8), 256, 0, st>>>(t_rowptr, t_colidx, t_eid, h, s1, s2, mx, zs, dhp, (int)n, (int)heads, (int)F, slope, dz, dh, ds2)
+    if (F <= 32) TSG_GB(1); else if (F <= 64) TSG_GB(2); else TSG_GB(4);
+#undef TSG_GB
+  }
+  else
+    k_gat_bwd_col<<<grid_for(n, 8), 256, 0, st>>>(t_rowptr, t_colidx, t_eid, h, s1, s2, mx, zs, dhp, (int)n, (int)heads,
+                                                  (int)F, slope, dal, dz, dh, ds2);
   k_gat_bwd_row<<<grid_for(n * heads, 256), 256, 0, st>>>(rowptr, eid, dz, (int)n, (int)heads, ds1);
   return check_launch("gat_bwd");
 }
