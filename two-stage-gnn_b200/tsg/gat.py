@@ -89,7 +89,7 @@ class DGATLayer(nn.Module):
         h_pad = x_pad @ wcat                                                    # [G, Hd*Fo]
         iso_sum = ops.readout(h * iso.view(-1, 1), graph_ptr, READOUT_SUM)      # sum of isolated real h_j
         corr = (iso_sum + num_pad.view(-1, 1) * h_pad) / float(max_nodes)
-        hp, hp_pad = raw + corr[batch], corr
+        hp, hp_pad = raw + ops.broadcast_rows(corr, graph_ptr, raw.size(0)), corr
         if self.concat:                                                         # :46-49, :75-76
             return F.elu(hp), F.elu(hp_pad)
         avg = hp.view(-1, Hd, Fo).mean(1); avg_pad = hp_pad.view(-1, Hd, Fo).mean(1)   # :78-83

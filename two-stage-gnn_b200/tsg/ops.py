@@ -404,6 +404,34 @@ def readout(x: torch.Tensor, graph_ptr: torch.Tensor, mode: int = READOUT_MAX | 
     return _Readout.apply(x, graph_ptr, mode)
 
 
+class _BroadcastRows(torch.autograd.Function):
+    """out[i,:] = v[g(i),:] for the rows i of graph g (the adjoint of the per-graph SUM readout): forward is
+    K6's backward kernel in SUM mode, backward is K6's forward -- no index tensor, no sort-based
+    index_put in the gradient."""
+
+    @staticmethod
+    def forward(ctx, v, graph_ptr, n):
+        v = v.contiguous()
+        G, F = v.shape
+        out = torch.empty(n, F, dtype=torch.float32, device=v.device)
+        call("tsg_readout_bwd", ptr(v), F, None, ptr(graph_ptr), G, n, F, READOUT_SUM, ptr(out), stream_ptr())
+        ctx.save_for_backward(graph_ptr)
+        ctx.g, ctx.f = G, F
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (gptr,) = ctx.saved_tensors
+        dout = dout.contiguous()
+        dv = torch.empty(ctx.g, ctx.f, dtype=torch.float32, device=dout.device)
+        call("tsg_readout_fwd", ptr(dout), ptr(gptr), ctx.g, ctx.f, READOUT_SUM, ptr(dv), ctx.f, None, stream_ptr())
+        return dv, None, None
+
+
+def broadcast_rows(v: torch.Tensor, graph_ptr: torch.Tensor, n: int) -> torch.Tensor:
+    return _BroadcastRows.apply(v, graph_ptr, n)
+
+
 # --------------------------------------------------------------------------------------------
 # triplet loss
 # --------------------------------------------------------------------------------------------
