@@ -316,6 +316,35 @@ int tsg_pairdist_matrix(const float* emb, int64_t num_rows, int64_t dim, float e
                         float* dist, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * K11  EigenPooling preprocessing
+ *   replaces the post-clustering half of `_coarserning_pooling_`
+ *   (Code/eigengcn/coarsen_pooling_with_last_eigen_padding.py:121-182): per cluster the unnormalised
+ *   Laplacian L = D - W of the induced subgraph (graph.py:116-126), its eigendecomposition in ascending
+ *   order (graph.py:147-163), sign rule "first entry >= 0" (:165-168), last vector repeated for j >= size
+ *   (:169-173); and A_coarse = Omega^T A_ext Omega (:135-149).  Cluster labels are an input (the reference
+ *   gets them from sklearn SpectralClustering, :125-126).
+ *   tsg_eigpool_build: adjacency as RAW CSR (any orientation: symmetric); cluster_of[N] = global cluster id
+ *     of every node; (member_ptr[C+1], member[N]) = nodes of every cluster in ascending node order (K1 RAW
+ *     on the (node -> cluster) list).  pool_val[j, p] = P_j[member[p], cluster] (CSR value order of P_j^T),
+ *     pool_val_nodes[j, v] = the same value in node order (the transposed operator).  eigvals (nullable):
+ *     [C, TSG_EIG_MAX] ascending, zero padded.  Clusters larger than TSG_EIG_MAX set *status_dev = 1 and are
+ *     left untouched (host fallback).  Warp per cluster, double-precision cyclic Jacobi in shared memory.
+ *   tsg_coarsen_edges: the inter-cluster edges relabelled to cluster ids, original order kept; duplicates
+ *     are NOT merged (K2 sums them), count on the device.
+ * ------------------------------------------------------------------------------------------ */
+#define TSG_EIG_MAX 32
+int tsg_eigpool_build(const int32_t* adj_rowptr, const int32_t* adj_colidx, const float* adj_val /*nullable => 1*/,
+                      const int32_t* cluster_of, const int32_t* member_ptr, const int32_t* member,
+                      int64_t num_nodes, int64_t num_clusters, int num_vectors,
+                      float* pool_val, float* pool_val_nodes, float* eigvals /*nullable*/,
+                      int32_t* status_dev, void* stream);
+size_t tsg_coarsen_edges_workspace_bytes(int64_t num_edges);
+int tsg_coarsen_edges(const int64_t* row, const int64_t* col, const float* weight /*nullable => 1*/,
+                      int64_t num_edges, const int32_t* cluster_of, int64_t* out_row, int64_t* out_col,
+                      float* out_weight, int64_t* out_count_dev,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * K10  native step executor for the SAGPool encoder
  *   replaces the Python-level sequencing of Code/sag/network.py:33-46 (`Net.forward` up to the sum
  *   of the three readouts) and Code/sag/layers.py:14-26 (`SAGPool.forward`) over a packed batch: ONE
