@@ -345,6 +345,25 @@ int tsg_coarsen_edges(const int64_t* row, const int64_t* col, const float* weigh
                       void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * H1  TU-format dataset loader -> packed corpus arrays.  HOST pointers throughout.
+ *   replaces `read_graphfile` (Code/sage+gat+diffpool/load_data.py:12-126, Code/eigengcn/load_data.py) in
+ *   TSG_TU_NETWORKX mode (node set / order / labels exactly as the networkx graphs the reference builds) and
+ *   PyG's TUDataset reader (Code/sag/train*.py:161-163) in TSG_TU_PYG mode.  `prefix` = <datadir>/<NAME>/<NAME>
+ *   (files <prefix>_A.txt, _graph_indicator.txt, _graph_labels.txt, optional _node_labels.txt /
+ *   _node_attributes.txt).  sizes[6] = {graphs, nodes, directed edges, node-label classes, attribute width,
+ *   graph classes}; tsg_tu_fill copies node_ptr[G+1], edge_ptr[G+1], local row/col[E] (sorted by (row, col)
+ *   inside a graph), node_label[N], y[G], attr[N, width] (nullable) into caller-allocated host arrays.
+ * ------------------------------------------------------------------------------------------ */
+#define TSG_TU_NETWORKX 0
+#define TSG_TU_PYG 1
+typedef struct tsg_tu_handle tsg_tu_handle;
+int tsg_tu_load(const char* prefix, int mode, int64_t max_nodes /*0 = no limit*/, tsg_tu_handle** out);
+int tsg_tu_sizes(const tsg_tu_handle* h, int64_t* sizes);
+int tsg_tu_fill(const tsg_tu_handle* h, int64_t* node_ptr, int64_t* edge_ptr, int64_t* row, int64_t* col,
+                int32_t* node_label, int64_t* y, float* attr /*nullable*/);
+void tsg_tu_free(tsg_tu_handle* h);
+
+/* ------------------------------------------------------------------------------------------
  * K10  native step executor for the SAGPool encoder
  *   replaces the Python-level sequencing of Code/sag/network.py:33-46 (`Net.forward` up to the sum
  *   of the three readouts) and Code/sag/layers.py:14-26 (`SAGPool.forward`) over a packed batch: ONE

@@ -62,6 +62,10 @@ _PROTOTYPES = {
     "tsg_eigpool_build": (I, [P, P, P, P, P, P, I64, I64, I, P, P, P, P, P]),
     "tsg_coarsen_edges_workspace_bytes": (SZ, [I64]),
     "tsg_coarsen_edges": (I, [P, P, P, I64, P, P, P, P, P, P, SZ, P]),
+    "tsg_tu_load": (I, [c_char_p, I, I64, P]),
+    "tsg_tu_sizes": (I, [P, P]),
+    "tsg_tu_fill": (I, [P, P, P, P, P, P, P, P]),
+    "tsg_tu_free": (None, [P]),
     "tsg_sag_arena_bytes": (SZ, [P]),
     "tsg_sag_encoder_fwd": (I, [P, P, P, P, P, P, P, P, SZ, P]),
     "tsg_sag_encoder_bwd": (I, [P, P, P, P, P, P, P, SZ, P]),
