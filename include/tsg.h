@@ -345,6 +345,27 @@ int tsg_coarsen_edges(const int64_t* row, const int64_t* col, const float* weigh
                       void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * K12  stage-2 evaluation heads on graph embeddings
+ *   tsg_knn_predict replaces KNeighborsClassifier(n_neighbors=3).fit(train).predict(query) of `evaluate`
+ *     (Code/sage+gat+diffpool/train_triplet.py:80-85): Euclidean, uniform weights; distance ties -> lower
+ *     train index, vote ties -> lower class id.  k <= 8, num_classes <= 16.
+ *   tsg_mlp1_train replaces the stage-2 classifier loop of `evaluate_mlp` (train_triplet.py:148-165):
+ *     MLP dim -> hidden1 -> hidden2 -> classes with LeakyReLU(slope), Adam, ONE sample per step in the given
+ *     order; all num_samples steps run inside one CTA with weights and moments in shared memory.
+ *     params / adam_m / adam_v: flat fp32 [W1 (hidden1 x dim), b1, W2 (hidden2 x hidden1), b2, W3 (classes x
+ *     hidden2), b3] (torch nn.Linear layout), updated in place; step0 = Adam steps already taken;
+ *     losses (nullable) [num_samples] = the per-step cross-entropy.
+ * ------------------------------------------------------------------------------------------ */
+int tsg_knn_predict(const float* train, const int64_t* train_labels, const float* query,
+                    int64_t num_train, int64_t num_query, int64_t dim, int k, int num_classes,
+                    int64_t* pred, void* stream);
+int tsg_mlp1_train(const float* emb, const int64_t* labels, int64_t num_samples, int64_t dim,
+                   int64_t hidden1, int64_t hidden2, int64_t num_classes,
+                   float* params, float* adam_m, float* adam_v, int64_t step0,
+                   float lr, float beta1, float beta2, float eps, float slope,
+                   float* losses /*nullable*/, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * H1  TU-format dataset loader -> packed corpus arrays.  HOST pointers throughout.
  *   replaces `read_graphfile` (Code/sage+gat+diffpool/load_data.py:12-126, Code/eigengcn/load_data.py) in
  *   TSG_TU_NETWORKX mode (node set / order / labels exactly as the networkx graphs the reference builds) and

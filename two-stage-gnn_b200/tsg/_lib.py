@@ -62,6 +62,8 @@ _PROTOTYPES = {
     "tsg_eigpool_build": (I, [P, P, P, P, P, P, I64, I64, I, P, P, P, P, P]),
     "tsg_coarsen_edges_workspace_bytes": (SZ, [I64]),
     "tsg_coarsen_edges": (I, [P, P, P, I64, P, P, P, P, P, P, SZ, P]),
+    "tsg_knn_predict": (I, [P, P, P, I64, I64, I64, I, I, P, P]),
+    "tsg_mlp1_train": (I, [P, P, I64, I64, I64, I64, I64, P, P, P, I64, F32, F32, F32, F32, F32, P, P]),
     "tsg_tu_load": (I, [c_char_p, I, I64, P]),
     "tsg_tu_sizes": (I, [P, P]),
     "tsg_tu_fill": (I, [P, P, P, P, P, P, P, P]),
