@@ -12,8 +12,10 @@ embeddings are all-gathered for the loss and gradients all-reduced (NCCL).
   python bench.py --impl reference ...                         reference CPU arm (oracle port, B=1)
 
 One JSON line on stdout (rank 0).  `value` = graphs/s with inputs resident in HBM; `e2e` = same step
-through TripletTrainer.step_from_host with pinned HOST buffers (H2D of x / edge_index / triplets and
-the loss read back inside the timed region); `roofline` = the level-1 GCN aggregation (K2 SpMM)
+through TripletTrainer.run_from_host_compact with pinned HOST buffers holding what the dataset stores per
+graph (node labels, local edge lists), expanded on the GPU by K0, H2D + loss read-back inside the timed
+region; `e2e_fp32_wire` = the same with the fp32 one-hot x / int64 edge_index tensors PyG's Batch.to(device)
+moves (PCIe bound); `e2e_blocking` = one blocking call per step; `roofline` = the level-1 GCN aggregation (K2 SpMM)
 timed alone with CUDA events, algorithmic bytes / measured HBM peak; `cpu_baseline` = the oracle
 port of the reference path timed on this box's host cores on a bounded sample.
 """
@@ -66,7 +68,7 @@ def workload_name(a):
 def make_step_batches(a, rank: int, num_batches: int):
     from tsg import synth
     corpus = synth.make_corpus("DD", a.corpus, seed=777 + 1_000_003 * rank)
-    out = []
+    out, compact = [], []
     for b in range(num_batches):
         trip = synth.sample_triplets(corpus.y, a.triplets, seed=1000 * rank + b)
         ids = np.concatenate([trip[:, 0], trip[:, 1], trip[:, 2]])
@@ -76,7 +78,13 @@ def make_step_batches(a, rank: int, num_batches: int):
         out.append(dict(x=torch.from_numpy(pk["x"]).pin_memory(),
                         edge_index=torch.from_numpy(pk["edge_index"]).pin_memory(),
                         node_ptr=pk["node_ptr"], triplets=torch.from_numpy(tidx).pin_memory()))
-    return corpus, out
+        sel = synth.select(corpus, ids)
+        compact.append(dict(label=torch.from_numpy(sel.node_label.astype(np.int32)).pin_memory(),
+                            row=torch.from_numpy(sel.row.astype(np.int32)).pin_memory(),
+                            col=torch.from_numpy(sel.col.astype(np.int32)).pin_memory(),
+                            node_ptr=sel.node_ptr.copy(), edge_ptr=sel.edge_ptr.copy(),
+                            triplets=torch.from_numpy(tidx).pin_memory()))
+    return corpus, out, compact
 
 
 # ------------------------------------------------------------------------------------------ clocks
@@ -219,7 +227,7 @@ def main():
     from tsg.train import TripletTrainer
     assert _lib.lib.tsg_check_device() == 0, _lib.last_error()
 
-    corpus, batches = make_step_batches(a, rank, num_batches=2)
+    corpus, batches, compact = make_step_batches(a, rank, num_batches=2)
     dev_batches = [dict(x=b["x"].to(dev), edge_index=b["edge_index"].to(dev), node_ptr=b["node_ptr"],
                         triplets=b["triplets"].to(dev)) for b in batches]
     torch.manual_seed(777)
@@ -278,9 +286,22 @@ def main():
         return trainer.run_from_host((batches[i % len(batches)] for i in range(steps)), dev)
 
     run_e2e(2)
-    ms_e2e = timed(lambda i: run_e2e(a.steps) if i == 0 else None, 1)
-    e2e_val = world * graphs_per_step * a.steps / (ms_e2e / 1000.0)
+    ms_e2e_wire = timed(lambda i: run_e2e(a.steps) if i == 0 else None, 1)
+    e2e_wire_val = world * graphs_per_step * a.steps / (ms_e2e_wire / 1000.0)
     e2e_blocking_val = world * graphs_per_step * a.steps / (ms_e2e_blocking / 1000.0)
+
+    # ---- end to end from COMPACT host batches (node labels + local int32 edge lists: what the TU files store);
+    #      K0 expands them on the GPU into the same x / edge_index tensors
+    def run_compact(steps):
+        return trainer.run_from_host_compact((compact[i % len(compact)] for i in range(steps)), dev,
+                                             corpus.num_node_labels)
+
+    run_compact(2)
+    ms_e2e = timed(lambda i: run_compact(a.steps) if i == 0 else None, 1)
+    e2e_val = world * graphs_per_step * a.steps / (ms_e2e / 1000.0)
+    c0 = compact[0]
+    h2d_compact = (c0["label"].numel() * 4 + c0["row"].numel() * 8 + c0["triplets"].numel() * 8
+                   + 8 * (3 * (graphs_per_step + 1)))
     # ---- end to end against the HBM-resident corpus (tsg.feeder): host sends graph ids + triplets only
     from tsg import synth
     from tsg.feeder import DeviceCorpus
@@ -385,9 +406,14 @@ def main():
                            "l2_policy": "inputs larger than L2 (x alone is %.0f MB), 2 alternating batches" % (N * corpus.num_node_labels * 4 / 1e6),
                            "parallelism": f"dp{world}: shard by graph, all-gather embeddings, all-reduce grads"},
                 "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": ms_e2e / a.steps,
-                        "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
-                        "api": "TripletTrainer.run_from_host: pinned host x[f32 N,89] / edge_index[i64 2,E] / triplets, "
-                               "copy stream double buffering, loss read back every step"},
+                        "h2d_bytes_per_step": int(h2d_compact), "d2h_bytes_per_step": 4,
+                        "api": "TripletTrainer.run_from_host_compact: pinned host node labels[i32 N] + local edge lists"
+                               "[i32 2,E] + offsets + triplets per step (what the TU files store); K0 expands to x[f32 N,89] "
+                               "/ edge_index[i64 2,E] on the GPU; copy-stream double buffering, loss read back every step"},
+                "e2e_fp32_wire": {"value": e2e_wire_val, "unit": UNIT, "ms_per_step": ms_e2e_wire / a.steps,
+                                  "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
+                                  "api": "TripletTrainer.run_from_host: pinned host x[f32 N,89] / edge_index[i64 2,E] / triplets "
+                                         "(the tensors PyG's Batch.to(device) moves), same pipeline: PCIe bound"},
                 "e2e_blocking": {"value": e2e_blocking_val, "unit": UNIT, "ms_per_step": ms_e2e_blocking / a.steps,
                                  "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
                                  "api": "TripletTrainer.step_from_host: one blocking call per step (H2D, step, loss.item())"},

@@ -47,3 +47,37 @@ def test_executor_single_node_graphs(cuda):
         outs.append(model(x, ei, node_ptr).detach().clone())
     tnn.USE_EXECUTOR = True
     assert torch.equal(outs[0], outs[1])
+
+
+def test_host_feeders_agree(cuda):
+    """fp32-wire feeder (x / edge_index from the host), compact feeder (labels + local int32 edges, expanded by K0)
+    and the blocking per-step call produce identical losses: the inputs that reach the step are the same tensors."""
+    import copy
+    from tsg import nn as tnn
+    from tsg.train import TripletTrainer
+    corpus = synth.make_corpus("DD", 20, seed=3)
+    batches, compact = [], []
+    for b in range(3):
+        trip = synth.sample_triplets(corpus.y, 20, seed=b)
+        ids = np.concatenate([trip[:, 0], trip[:, 1], trip[:, 2]])
+        pk = synth.pack(corpus, ids)
+        tidx = torch.from_numpy(np.stack([np.arange(20), 20 + np.arange(20), 40 + np.arange(20)], 1).astype(np.int64))
+        batches.append(dict(x=torch.from_numpy(pk["x"]).pin_memory(), edge_index=torch.from_numpy(pk["edge_index"]).pin_memory(),
+                            node_ptr=pk["node_ptr"], triplets=tidx.pin_memory()))
+        sel = synth.select(corpus, ids)
+        compact.append(dict(label=torch.from_numpy(sel.node_label.astype(np.int32)).pin_memory(),
+                            row=torch.from_numpy(sel.row.astype(np.int32)).pin_memory(),
+                            col=torch.from_numpy(sel.col.astype(np.int32)).pin_memory(),
+                            node_ptr=sel.node_ptr.copy(), edge_ptr=sel.edge_ptr.copy(), triplets=tidx.pin_memory()))
+    torch.manual_seed(1)
+    base = tnn.PackedSAGNet(corpus.num_node_labels, 32, 32, 0.5, 0.0).to(cuda)
+    res = []
+    for mode in ("wire", "compact", "blocking"):
+        tr = TripletTrainer(copy.deepcopy(base))
+        if mode == "wire":
+            res.append(tr.run_from_host(batches, cuda))
+        elif mode == "compact":
+            res.append(tr.run_from_host_compact(compact, cuda, corpus.num_node_labels))
+        else:
+            res.append([tr.step_from_host(b["x"], b["edge_index"], b["node_ptr"], b["triplets"], cuda) for b in batches])
+    assert res[0] == res[1] == res[2] and len(res[0]) == 3
