@@ -209,10 +209,13 @@ class PackedSAGNet(torch.nn.Module):
 
     def head(self, z: torch.Tensor) -> torch.Tensor:
         """network.py:48-52: lin1 / ReLU / dropout / lin2 / ReLU / lin3 / log_softmax."""
-        z = F.relu(self.lin1(z))
+        # the three Linear layers run on the tall-skinny K3 kernels ([G, 64] operands: cuBLAS picks split-K SIMT
+        # GEMMs that cost 250 us per step here); parameters stay nn.Linear so the state_dict keys are the reference's
+        lin = lambda layer, t: ops.linear(t, layer.weight.t().contiguous(), layer.bias)
+        z = F.relu(lin(self.lin1, z))
         z = F.dropout(z, p=self.dropout_ratio, training=self.training)
-        z = F.relu(self.lin2(z))
-        return F.log_softmax(self.lin3(z), dim=-1)
+        z = F.relu(lin(self.lin2, z))
+        return F.log_softmax(lin(self.lin3, z), dim=-1)
 
 
 class PackedTripletNet(torch.nn.Module):
