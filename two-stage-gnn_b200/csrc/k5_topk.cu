@@ -6,7 +6,7 @@
 // first, -0.0 == +0.0, i.e. what torch's stable CPU sort produces.
 //
 // top-k = rank selection, one CTA per graph: the graph's keys are staged in shared memory as
-// order-preserving uint32, every thread owns a node and counts the keys that precede its own
+// order-preserving 64-bit composites (score key, ~index), every thread owns a node and counts the keys that precede its own
 // (broadcast shared-memory reads, no barriers in the hot loop, no atomics).  n_g is ~10^2..10^3,
 // so the O(n^2) compares (72k for a DD graph) cost less than the barriers of a sorting network.
 #include "common.cuh"
@@ -30,12 +30,15 @@ struct KofN {
 };
 
 constexpr int TOPK_THREADS = 128;
-constexpr int TOPK_SMEM_KEYS = 8192;   // 32 KB of keys; larger graphs read keys from global
+constexpr int TOPK_SMEM_KEYS = 4096;   // 32 KB of 64-bit keys; larger graphs keep their keys in global memory
 
+// Composite 64-bit key = (order-preserving score key << 32) | ~local index: one unsigned compare implements the
+// strict total order (score descending, node id ascending), all keys of a graph are distinct, and
+// rank(i) = #{j : key_j > key_i}.
 __global__ void __launch_bounds__(TOPK_THREADS)
 k_topk_rank(const float* __restrict__ score, const int64_t* __restrict__ gptr,
-            const int64_t* __restrict__ kptr, int64_t* __restrict__ perm, uint32_t* __restrict__ gkeys) {
-  __shared__ uint32_t skeys[TOPK_SMEM_KEYS];
+            const int64_t* __restrict__ kptr, int64_t* __restrict__ perm, unsigned long long* __restrict__ gkeys) {
+  __shared__ __align__(16) unsigned long long skeys[TOPK_SMEM_KEYS];
   const int g = blockIdx.x;
   const int64_t base = gptr[g];
   const int n = (int)(gptr[g + 1] - base);
@@ -43,21 +46,19 @@ k_topk_rank(const float* __restrict__ score, const int64_t* __restrict__ gptr,
   const int k = (int)(kptr[g + 1] - obase);
   if (n == 0 || k == 0) return;
   const bool in_smem = n <= TOPK_SMEM_KEYS;
-  uint32_t* keys = in_smem ? skeys : (gkeys + base);
-  for (int i = threadIdx.x; i < n; i += TOPK_THREADS) keys[i] = score_key(score[base + i]);
+  unsigned long long* keys = in_smem ? skeys : (gkeys + base);
+  for (int i = threadIdx.x; i < n; i += TOPK_THREADS)
+    keys[i] = ((unsigned long long)score_key(score[base + i]) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
   __syncthreads();    // (global path: writes by this block, read by this block after the barrier)
   for (int i = threadIdx.x; i < n; i += TOPK_THREADS) {
-    const uint32_t ki = keys[i];
+    const unsigned long long ki = keys[i];
     int rank = 0;
     int j = 0;
     for (; j + 4 <= n; j += 4) {
-      uint32_t a = keys[j], b = keys[j + 1], c = keys[j + 2], d = keys[j + 3];
-      rank += (a > ki) || (a == ki && j < i);
-      rank += (b > ki) || (b == ki && j + 1 < i);
-      rank += (c > ki) || (c == ki && j + 2 < i);
-      rank += (d > ki) || (d == ki && j + 3 < i);
+      const unsigned long long a = keys[j], b = keys[j + 1], c = keys[j + 2], d = keys[j + 3];
+      rank += (a > ki) + (b > ki) + (c > ki) + (d > ki);
     }
-    for (; j < n; ++j) { uint32_t a = keys[j]; rank += (a > ki) || (a == ki && j < i); }
+    for (; j < n; ++j) rank += keys[j] > ki;
     if (rank < k) perm[obase + rank] = base + i;
   }
 }
@@ -228,7 +229,7 @@ k_gate_gather_bwd(const float* __restrict__ dxo, const float* __restrict__ x,
 using namespace tsg;
 
 extern "C" size_t tsg_topk_workspace_bytes(int64_t N, int64_t G) {
-  return ws_bytes(scan_ws_ints(G), 4) + ws_bytes((size_t)N + 1, 4) + 512;
+  return ws_bytes(scan_ws_ints(G), 4) + ws_bytes((size_t)N + 1, 8) + 512;
 }
 
 extern "C" int tsg_topk_sizes(const int64_t* gptr, int64_t G, float ratio, int64_t* kptr,
@@ -246,7 +247,7 @@ extern "C" int tsg_topk(const float* score, const int64_t* gptr, const int64_t* 
   if (workspace_bytes < tsg_topk_workspace_bytes(N, G)) { set_error("topk: workspace too small"); return TSG_EWORKSPACE; }
   Workspace ws(workspace, workspace_bytes);
   ws.take<int>(scan_ws_ints(G));
-  uint32_t* gkeys = ws.take<uint32_t>(N + 1);
+  unsigned long long* gkeys = ws.take<unsigned long long>(N + 1);
   TSG_REQUIRE(G < (int64_t)0x7fffffff, "topk: too many graphs");
   k_topk_rank<<<(int)G, TOPK_THREADS, 0, (cudaStream_t)stream>>>(score, gptr, kptr, perm, gkeys);
   return check_launch("topk");
