@@ -105,6 +105,19 @@ int tsg_csr_build_graphs(const int64_t* row, const int64_t* col, const int64_t* 
                          int32_t* t_eid /*nullable*/,
                          void* workspace, size_t workspace_bytes, void* stream);
 
+/* K1c: the GCN CSR of a pooled level directly from the previous level's CSR: new row i = old row perm[i]
+ * restricted to surviving columns (inv_perm >= 0), relabelled, same order, renormalised -- bit-identical to
+ * tsg_csr_build_graphs(tsg_filter_adj(edges, perm)) (Code/sag/layers.py:20-23 followed by the next GCNConv's
+ * gcn_norm) without touching the edge list.  Output capacity: the old nnz.  tsg_inv_perm is filter_adj's
+ * relabelling table alone (inv_perm[v] = position of v in perm, or -1). */
+int tsg_inv_perm(const int64_t* perm, int64_t num_perm, int64_t num_nodes, int32_t* inv_perm, void* stream);
+size_t tsg_csr_filter_workspace_bytes(int64_t num_perm);
+int tsg_csr_filter(const int32_t* rowptr, const int32_t* colidx, const int32_t* t_rowptr, const int32_t* t_colidx,
+                   const int64_t* perm, const int32_t* inv_perm, int64_t num_perm,
+                   int32_t* out_rowptr, int32_t* out_colidx, float* out_val,
+                   int32_t* out_t_rowptr, int32_t* out_t_colidx, float* out_t_val,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * K2  CSR segment-sum SpMM:  Y[r,:] = sum_p val[p] * H[colidx[p],:]  (+ bias) (ReLU optional)
  *   replaces: the gather / mul / scatter_add of PyG GCNConv.propagate (Code/sag/network.py:34)

@@ -127,3 +127,38 @@ def test_spmm_hub_rows_and_empty_rows(cuda, exact, n):
     ref = R.spmm_coo_edge_order(ei, w, h, n)
     y = ops.spmm_raw(csr.rowptr, csr.colidx, csr.val, h.to(cuda), exact=exact)
     _check(y.cpu(), ref, exact)
+
+
+@pytest.mark.parametrize("shape,G,ratio", [("DD", 9, 0.5), ("PROTEINS", 33, 0.5), ("JANY", 4, 0.25), ("DD", 5, 1.0)])
+def test_k1c_csr_filter_equals_rebuild(cuda, shape, G, ratio):
+    """K1c(CSR, perm, inv) == K1b(filter_adj(edges, perm)): rowptr / colidx / val of both orientations, bit for bit."""
+    from tsg import ops
+    from tsg._lib import call, lib, ptr, stream_ptr, workspace
+    ei, nptr = _batch(shape, G)
+    n = int(nptr[-1])
+    batch = torch.from_numpy(np.repeat(np.arange(G), np.diff(nptr)))
+    score = torch.randn(n, generator=torch.Generator().manual_seed(G))
+    perm = R.topk(score, ratio, batch).to(cuda)
+    k = perm.numel()
+    el = ops.EdgeList.from_edge_index(ei.to(cuda))
+    gptr = torch.from_numpy(nptr).to(cuda)
+    old = ops.build_csr_graphs(el, gptr, n, int(np.diff(nptr).max()))
+    el2, inv = ops.filter_adj(el, perm, n)
+    kptr = ops.topk_sizes(gptr, ratio)
+    ref = ops.build_csr_graphs(el2, kptr, k, int(np.diff(nptr).max()))
+    inv2 = torch.empty(n, dtype=torch.int32, device=cuda)
+    call("tsg_inv_perm", ptr(perm), k, n, ptr(inv2), stream_ptr())
+    assert torch.equal(inv, inv2)
+    cap = int(old.rowptr[-1])
+    i32 = dict(dtype=torch.int32, device=cuda)
+    out = [torch.empty(k + 1, **i32), torch.empty(cap, **i32), torch.empty(cap, dtype=torch.float32, device=cuda),
+           torch.empty(k + 1, **i32), torch.empty(cap, **i32), torch.empty(cap, dtype=torch.float32, device=cuda)]
+    wsb = lib.tsg_csr_filter_workspace_bytes(k)
+    ws = workspace(wsb, cuda)
+    call("tsg_csr_filter", ptr(old.rowptr), ptr(old.colidx), ptr(old.t_rowptr), ptr(old.t_colidx), ptr(perm), ptr(inv2), k,
+         *[ptr(t) for t in out], ptr(ws), wsb, stream_ptr())
+    nnz = int(ref.rowptr[-1])
+    assert torch.equal(out[0], ref.rowptr) and torch.equal(out[3], ref.t_rowptr)
+    assert torch.equal(out[1][:nnz], ref.colidx[:nnz]) and torch.equal(out[4][:nnz], ref.t_colidx[:nnz])
+    assert torch.equal(out[2][:nnz].view(torch.int32), ref.val[:nnz].view(torch.int32))
+    assert torch.equal(out[5][:nnz].view(torch.int32), ref.t_val[:nnz].view(torch.int32))

@@ -9,11 +9,11 @@
 // saved tensors where the backward finds them; nothing is allocated, nothing synchronises.
 //
 //   per level l = 0..2 (n = n[l] rows in, k = n[l+1] rows out):
-//     CSR   = K1b(edges_l, level_ptr[l])                      conv_l and score_l share it
+//     CSR   = K1b(edges, level_ptr[0]) at l = 0; K1c(CSR_{l-1}, perm, inv) below -- conv_l and score_l share it
 //     h     = ReLU(A_hat (x_l W_l) + b_l)                     network.py:34,38,42
 //     score = A_hat (h ws_l) + bs_l                           layers.py:18
 //     perm  = topk(score)                                     layers.py:20
-//     edges_{l+1}, inv = filter_adj(edges_l, perm)            layers.py:23
+//     inv   = filter_adj's relabelling table                  layers.py:23 (the filtered list itself is never built)
 //     x_{l+1} = h[perm] * tanh(score[perm])                   layers.py:21
 //     out_l = [gmp(x_{l+1}) || gap(x_{l+1})]                  network.py:36,40,44
 //   z = out_0 + out_1 + out_2                                 network.py:46
@@ -28,7 +28,6 @@ struct LevelBuf {
   float *xw, *h, *sw, *score, *xg, *out;
   int64_t* perm;
   int32_t* inv;
-  int64_t *erow, *ecol, *ecount;     // edges surviving this level's pooling (input of the next level)
   int32_t* argmax;
 };
 
@@ -46,7 +45,7 @@ static size_t scratch_need(const tsg_sag_shape* sh) {
   for (int l = 0; l < 3; ++l) {
     up(tsg_csr_build_graphs_workspace_bytes(sh->num_graphs, sh->num_edges));
     up(tsg_topk_workspace_bytes(sh->n[l], sh->num_graphs));
-    up(tsg_filter_adj_workspace_bytes(sh->num_edges));
+    up(tsg_csr_filter_workspace_bytes(sh->n[l + 1]));
     up(tsg_colsum_workspace_bytes(sh->n[l], sh->hidden));
     up(tsg_linear_bwd_weight_workspace_bytes(l == 0 ? sh->in_feat : sh->hidden, sh->hidden));
     up(tsg_linear_bwd_weight_workspace_bytes(sh->hidden, 1));
@@ -75,8 +74,6 @@ static void layout(const tsg_sag_shape* sh, void* arena, SagArena* a) {
     b.sw = (float*)take(n * 4); b.score = (float*)take(n * 4);
     b.perm = (int64_t*)take((k > 0 ? k : 1) * 8);
     b.inv = (int32_t*)take((n > 0 ? n : 1) * 4);
-    b.erow = (int64_t*)take((E > 0 ? E : 1) * 8); b.ecol = (int64_t*)take((E > 0 ? E : 1) * 8);
-    b.ecount = (int64_t*)take(8);
     b.xg = (float*)take((k > 0 ? k : 1) * H * 4);
     b.out = (float*)take(G * 2 * H * 4);
     b.argmax = (int32_t*)take(G * H * 4);
@@ -131,26 +128,30 @@ extern "C" int tsg_sag_encoder_fwd(const tsg_sag_shape* sh, const float* x, cons
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t G = sh->num_graphs, H = sh->hidden, E = sh->num_edges;
   const float* xin = x;
-  const int64_t *erow = row, *ecol = col, *ecount = nullptr;
   for (int l = 0; l < 3; ++l) {
     LevelBuf& b = a.lv[l];
     const int64_t n = sh->n[l], k = sh->n[l + 1], fin = l == 0 ? sh->in_feat : H;
     const float *W = params[4 * l], *bias = params[4 * l + 1], *ws = params[4 * l + 2], *bs = params[4 * l + 3];
     const int64_t* ptr_l = level_ptr + (size_t)l * (G + 1);
     const int64_t* ptr_n = level_ptr + (size_t)(l + 1) * (G + 1);
-    TSG_TRY(tsg_edge_ptr(erow, E, ecount, ptr_l, G, b.eptr, stream));
-    TSG_TRY(tsg_csr_build_graphs(erow, ecol, b.eptr, ptr_l, G, n, E, sh->max_graph_nodes[l], b.rowptr, b.colidx, b.val,
-                                 nullptr, b.t_rowptr, b.t_colidx, b.t_val, nullptr, a.scratch, a.scratch_bytes, stream));
+    if (l == 0) {
+      TSG_TRY(tsg_edge_ptr(row, E, nullptr, ptr_l, G, b.eptr, stream));
+      TSG_TRY(tsg_csr_build_graphs(row, col, b.eptr, ptr_l, G, n, E, sh->max_graph_nodes[l], b.rowptr, b.colidx, b.val,
+                                   nullptr, b.t_rowptr, b.t_colidx, b.t_val, nullptr, a.scratch, a.scratch_bytes, stream));
+    } else {        // K1c: the pooled level's CSR straight from the previous level's CSR, perm and inv
+      const LevelBuf& pb = a.lv[l - 1];
+      TSG_TRY(tsg_csr_filter(pb.rowptr, pb.colidx, pb.t_rowptr, pb.t_colidx, pb.perm, pb.inv, n, b.rowptr, b.colidx, b.val,
+                             b.t_rowptr, b.t_colidx, b.t_val, a.scratch, a.scratch_bytes, stream));
+    }
     TSG_TRY(tsg_linear_fwd(xin, W, nullptr, b.xw, n, fin, H, 0, 0, stream));
     TSG_TRY(tsg_spmm(b.rowptr, b.colidx, b.val, b.xw, bias, b.h, n, H, TSG_SPMM_RELU, stream));
     TSG_TRY(tsg_linear_fwd(b.h, ws, nullptr, b.sw, n, H, 1, 0, 0, stream));
     TSG_TRY(tsg_spmm(b.rowptr, b.colidx, b.val, b.sw, bs, b.score, n, 1, 0, stream));
     TSG_TRY(tsg_topk(b.score, ptr_l, ptr_n, G, n, b.perm, a.scratch, a.scratch_bytes, stream));
-    TSG_TRY(tsg_filter_adj(erow, ecol, E, ecount, b.perm, k, n, b.inv, b.erow, b.ecol, b.ecount,
-                           a.scratch, a.scratch_bytes, stream));
+    TSG_TRY(tsg_inv_perm(b.perm, k, n, b.inv, stream));            // filter_adj's relabelling table (layers.py:23)
     TSG_TRY(tsg_gate_gather_fwd(b.h, b.score, b.perm, nullptr, b.xg, nullptr, k, H, stream));
     TSG_TRY(tsg_readout_fwd(b.xg, ptr_n, G, H, TSG_READOUT_MAX | TSG_READOUT_MEAN, b.out, 2 * H, b.argmax, stream));
-    xin = b.xg; erow = b.erow; ecol = b.ecol; ecount = b.ecount;
+    xin = b.xg;
   }
   const int64_t tot = G * 2 * H;
   k_add3<<<grid_for(tot, 256, 8), 256, 0, st>>>(a.lv[0].out, a.lv[1].out, a.lv[2].out, z, tot);
