@@ -144,6 +144,17 @@ int tsg_spmm_tiled(const int32_t* rowptr, const int32_t* colidx, const float* va
                    const float* H, const float* bias /*nullable*/, float* Y, const int64_t* tile_ptr,
                    int64_t num_tiles, int64_t num_rows, int64_t feat, int flags, void* stream);
 
+/* TMA-staged K2 for packed batches: tile_ptr[T+1] (int64, device) = graph boundaries; every tile (one graph)
+ * is copied into shared memory by `cp.async.bulk` (H rows, colidx / val slice, rowptr slice; two stages per
+ * CTA, producer warp + 31 consumer warps, mbarriers) and gathered from there; graphs that do not fit a stage are
+ * gathered from global memory by the same kernel.  Same arithmetic and order as tsg_spmm.  Needs feat % 4 == 0,
+ * feat <= 32, 16-byte aligned arrays with 16 readable bytes behind rowptr / colidx / val, and self-contained
+ * tiles (CSRs from tsg_csr_build_graphs / tsg_csr_filter).  Other shapes are forwarded to tsg_spmm.
+ * status_dev (int32, device, caller-zeroed) is set to 1 if a pipeline wait ever times out (hang guard). */
+int tsg_spmm_tma(const int32_t* rowptr, const int32_t* colidx, const float* val /*nullable => 1*/,
+                 const float* H, const float* bias /*nullable*/, float* Y, const int64_t* tile_ptr,
+                 int64_t num_tiles, int64_t num_rows, int64_t feat, int flags, int32_t* status_dev, void* stream);
+
 /* dY_masked = dY * (Y > 0): ReLU backward fused with the column sum that gives the bias gradient:
  * dbias[f] = sum_r dY_masked[r,f]  (deterministic two-stage reduction).  Y may be NULL (no ReLU).
  * workspace: tsg_colsum_workspace_bytes(num_rows, feat). */

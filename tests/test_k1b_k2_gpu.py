@@ -162,3 +162,23 @@ def test_k1c_csr_filter_equals_rebuild(cuda, shape, G, ratio):
     assert torch.equal(out[1][:nnz], ref.colidx[:nnz]) and torch.equal(out[4][:nnz], ref.t_colidx[:nnz])
     assert torch.equal(out[2][:nnz].view(torch.int32), ref.val[:nnz].view(torch.int32))
     assert torch.equal(out[5][:nnz].view(torch.int32), ref.t_val[:nnz].view(torch.int32))
+
+
+@pytest.mark.parametrize("exact", [True, False])
+@pytest.mark.parametrize("shape,G,F", [("DD", 40, 32), ("DD", 300, 32), ("PROTEINS", 500, 16), ("JANY", 30, 8), ("DD", 9, 24)])
+def test_spmm_tma_equals_spmm(cuda, exact, shape, G, F):
+    """TMA-staged tile kernel == k_spmm_g bit for bit (same order, same rounding), forward and transposed, incl.
+    graphs that exceed the stage capacity (DD graphs > 544 rows take the in-kernel global path)."""
+    from tsg import ops
+    ei, nptr = _batch(shape, G)
+    n = int(nptr[-1])
+    el = ops.EdgeList.from_edge_index(ei.to(cuda))
+    gptr = torch.from_numpy(nptr).to(cuda)
+    csr = ops.build_csr_graphs(el, gptr, n, int(np.diff(nptr).max()))
+    g = torch.Generator().manual_seed(F + G)
+    h = torch.randn(n, F, generator=g).to(cuda)
+    bias = torch.randn(F, generator=g).to(cuda)
+    for rp, ci, v in ((csr.rowptr, csr.colidx, csr.val), (csr.t_rowptr, csr.t_colidx, csr.t_val), (csr.rowptr, csr.colidx, None)):
+        ref = ops.spmm_raw(rp, ci, v, h, bias, relu=True, exact=exact)
+        got = ops.spmm_raw(rp, ci, v, h, bias, relu=True, exact=exact, tile_ptr=gptr, tma=True)
+        assert torch.equal(got, ref)

@@ -258,7 +258,8 @@ k_spmm_tiled(const int* __restrict__ rowptr, const int* __restrict__ colidx, con
 // the launch geometry.  FMA = false rounds the product before the add (bit-identical to index_add_
 // in COO order: flag TSG_SPMM_EXACT); FMA = true (default) fuses it: <= 1 ulp per term.
 // Negative results kept out of the tree: warp-private cp.async staging of the CSR slice (153-200 us),
-// a producer warp issuing per-line L2 prefetches (126 us), L1 evict_first / evict_last hints (+10 %).
+// a producer warp issuing per-line L2 prefetches (126 us), L1 evict_first / evict_last hints (+10 %),
+// two float4 per lane with 4 lanes per row (fewer instructions, less memory parallelism: 123-160 us).
 // ------------------------------------------------------------------------------------------
 // TMA bulk prefetch into L2 of [p, p + bytes): address aligned down / size rounded up to 16 bytes
 __device__ __forceinline__ void bulk_prefetch_l2(const void* p, size_t bytes) {
@@ -355,6 +356,174 @@ k_spmm_g(const int* __restrict__ rowptr, const int* __restrict__ colidx,
       Y[(size_t)r * F4 + f] = acc;
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// k_spmm_tma: whole-graph tiles staged in shared memory by the TMA engine, double buffered.
+//
+// k_spmm_g is bound by the latency of gathers that go through L1 tags / L2 (long_scoreboard 18 warp-cycles per
+// issue; fewer instructions per neighbour made it SLOWER, more memory parallelism is what it lacks).  A packed
+// batch is block diagonal, so a graph's rows only gather rows of the same graph: one CTA per SM keeps TWO tile
+// stages (H rows, colidx / val slice, rowptr slice of one graph each) in shared memory; a producer warp
+// fills stage i+1 with four `cp.async.bulk` copies on a tx-count mbarrier while 31 consumer warps compute
+// stage i with every index load an LDS and every gather an LDS.128 (no tags, no first-touch stall);
+// consumers release a stage by arriving on its `empty` mbarrier.  Graphs that do not fit a stage
+// (rows > cap or nnz > cap) are processed by the same consumers straight from global memory.
+// Arithmetic and order identical to k_spmm_g.  Requires 16 readable bytes of slack behind rowptr / colidx /
+// val (the copies are rounded to 16 bytes) and tiles that are self-contained (guaranteed for CSRs built by
+// K1b / K1c from a packed batch, which trap on an edge that leaves its graph).
+// ------------------------------------------------------------------------------------------
+constexpr int TT_THREADS = 1024;
+constexpr int TT_CWARPS = TT_THREADS / 32 - 1;          // 31 consumer warps + 1 producer warp
+constexpr int TT_STAGE_BYTES = 104 * 1024;
+constexpr int TT_SPIN = 1 << 20;
+
+__device__ __forceinline__ uint32_t tt_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ bool tt_wait(uint32_t bar, uint32_t parity) {
+  for (int spin = 0; spin < TT_SPIN; ++spin) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) return true;
+  }
+  return false;
+}
+__device__ __forceinline__ void tt_tma(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+struct TileHdr { int r0, rows, p0a, dr, staged; };     // dr = r0 - (r0 & ~3): offset of the tile's first rowptr entry
+
+template <int LPR, bool HAS_VAL, bool FMA>
+__global__ void __launch_bounds__(TT_THREADS, 1)
+k_spmm_tma(const int* __restrict__ rowptr, const int* __restrict__ colidx, const float* __restrict__ val,
+           const float4* __restrict__ H, const float4* __restrict__ bias, float4* __restrict__ Y,
+           const int64_t* __restrict__ tile_ptr, int num_tiles, int F4, int row_cap, int nnz_cap, int relu,
+           int* __restrict__ err) {
+  extern __shared__ __align__(128) char tt_smem_buf[];
+  __shared__ __align__(8) uint64_t bar_full[2], bar_empty[2];
+  __shared__ TileHdr hdr[2];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned row_bytes = (unsigned)F4 * 16u;
+  // stage layout: H rows | colidx | val | rowptr
+  const int h_bytes = row_cap * (int)row_bytes;
+  const int c_bytes = (nnz_cap + 8) * 4;
+  const int r_off = h_bytes + 2 * c_bytes;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(tt_smem(&bar_full[i])), "r"(1u) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(tt_smem(&bar_empty[i])), "r"((uint32_t)TT_CWARPS) : "memory");
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int my_tiles = blockIdx.x < num_tiles ? (num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  bool ok = true;
+  if (warp == TT_CWARPS) {
+    // ---------------- producer
+    if (lane == 0) {
+      // tile metadata (tile_ptr pair -> rowptr pair: two dependent global loads) is fetched one tile ahead so
+      // its latency hides behind the wait for the stage
+      auto meta = [&](int i, int& r0, int& r1, int& p0, int& p1) {
+        r0 = r1 = p0 = p1 = 0;
+        if (i < my_tiles) {
+          const int t = blockIdx.x + i * gridDim.x;
+          r0 = (int)tile_ptr[t]; r1 = (int)tile_ptr[t + 1];
+          if (r1 > r0) { p0 = __ldg(rowptr + r0); p1 = __ldg(rowptr + r1); }
+        }
+      };
+      int nr0, nr1, np0, np1;
+      meta(0, nr0, nr1, np0, np1);
+      for (int i = 0; i < my_tiles && ok; ++i) {
+        const int s = i & 1;
+        const int r0 = nr0, r1 = nr1, p0 = np0, p1 = np1;
+        meta(i + 1, nr0, nr1, np0, np1);
+        if (i >= 2) ok = tt_wait(tt_smem(&bar_empty[s]), (uint32_t)(((i >> 1) - 1) & 1));   // consumers left stage s
+        const int rows = r1 - r0;
+        const int p0a = p0 & ~3, r0a = r0 & ~3;
+        const bool fits = rows > 0 && rows <= row_cap && (p1 - p0a) <= nnz_cap;
+        hdr[s].r0 = r0; hdr[s].rows = rows; hdr[s].p0a = p0a; hdr[s].dr = r0 - r0a; hdr[s].staged = fits ? 1 : 0;
+        const uint32_t bar = tt_smem(&bar_full[s]);
+        if (fits) {
+          char* st = tt_smem_buf + (size_t)s * TT_STAGE_BYTES;
+          const uint32_t bh = (uint32_t)rows * row_bytes;
+          const uint32_t bc = (uint32_t)(((p1 - p0a) * 4 + 15) & ~15);
+          const uint32_t br = (uint32_t)(((r1 - r0a + 1) * 4 + 15) & ~15);
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                       :: "r"(bar), "r"(bh + bc * (HAS_VAL ? 2u : 1u) + br) : "memory");
+          tt_tma(tt_smem(st), reinterpret_cast<const char*>(H) + (size_t)r0 * row_bytes, bh, bar);
+          tt_tma(tt_smem(st + h_bytes), colidx + p0a, bc, bar);
+          if (HAS_VAL) tt_tma(tt_smem(st + h_bytes + c_bytes), val + p0a, bc, bar);
+          tt_tma(tt_smem(st + r_off), rowptr + r0a, br, bar);
+        } else {
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");   // header only
+        }
+      }
+    }
+  } else {
+    // ---------------- consumers: LPR lanes x float4 per row, 32 / LPR rows per warp
+    const int l = lane % LPR, sub = lane / LPR;
+    constexpr int RPW = 32 / LPR;
+    const bool fok = l < F4;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 b4 = zero4;
+    if (bias != nullptr && fok) b4 = __ldg(bias + l);
+    for (int i = 0; i < my_tiles && ok; ++i) {
+      const int s = i & 1;
+      ok = tt_wait(tt_smem(&bar_full[s]), (uint32_t)((i >> 1) & 1));
+      const TileHdr h = hdr[s];
+      const char* st = tt_smem_buf + (size_t)s * TT_STAGE_BYTES;
+      const float4* sH = reinterpret_cast<const float4*>(st);
+      const int* sC = reinterpret_cast<const int*>(st + h_bytes);
+      const float* sV = reinterpret_cast<const float*>(st + h_bytes + c_bytes);
+      const int* sR = reinterpret_cast<const int*>(st + r_off) + h.dr;
+#define TSG_ACC(hh, v)                                                                                    \
+      if (FMA) { acc.x = fmaf(v, hh.x, acc.x); acc.y = fmaf(v, hh.y, acc.y);                              \
+                 acc.z = fmaf(v, hh.z, acc.z); acc.w = fmaf(v, hh.w, acc.w); }                            \
+      else { acc.x = __fadd_rn(acc.x, __fmul_rn(v, hh.x)); acc.y = __fadd_rn(acc.y, __fmul_rn(v, hh.y));  \
+             acc.z = __fadd_rn(acc.z, __fmul_rn(v, hh.z)); acc.w = __fadd_rn(acc.w, __fmul_rn(v, hh.w)); }
+      for (int rl = warp * RPW + sub; rl < h.rows; rl += TT_CWARPS * RPW) {
+        float4 acc = zero4;
+        if (h.staged) {
+          const int ps = sR[rl] - h.p0a, pe = sR[rl + 1] - h.p0a;
+          const float4* Hl = sH + l - (size_t)h.r0 * F4;                  // gathers index by GLOBAL column id
+          int p = ps;
+          for (; p + 4 <= pe; p += 4) {
+            const int c0 = sC[p], c1 = sC[p + 1], c2 = sC[p + 2], c3 = sC[p + 3];
+            float v0 = 1.f, v1 = 1.f, v2 = 1.f, v3 = 1.f;
+            if (HAS_VAL) { v0 = sV[p]; v1 = sV[p + 1]; v2 = sV[p + 2]; v3 = sV[p + 3]; }
+            if (fok) {
+              const float4 h0 = Hl[(size_t)c0 * F4], h1 = Hl[(size_t)c1 * F4], h2 = Hl[(size_t)c2 * F4], h3 = Hl[(size_t)c3 * F4];
+              TSG_ACC(h0, v0) TSG_ACC(h1, v1) TSG_ACC(h2, v2) TSG_ACC(h3, v3)
+            }
+          }
+          for (; p < pe; ++p) {
+            const int c0 = sC[p];
+            const float v0 = HAS_VAL ? sV[p] : 1.f;
+            if (fok) { const float4 h0 = Hl[(size_t)c0 * F4]; TSG_ACC(h0, v0) }
+          }
+        } else {                                                            // oversize graph: global gathers
+          const int r = h.r0 + rl;
+          const int ps = __ldg(rowptr + r), pe = __ldg(rowptr + r + 1);
+          for (int p = ps; p < pe; ++p) {
+            const float v0 = HAS_VAL ? __ldg(val + p) : 1.f;
+            if (fok) { const float4 h0 = __ldg(H + (size_t)__ldg(colidx + p) * F4 + l); TSG_ACC(h0, v0) }
+          }
+        }
+#undef TSG_ACC
+        if (bias != nullptr) {
+          acc.x = __fadd_rn(acc.x, b4.x); acc.y = __fadd_rn(acc.y, b4.y);
+          acc.z = __fadd_rn(acc.z, b4.z); acc.w = __fadd_rn(acc.w, b4.w);
+        }
+        if (relu) { acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f); }
+        if (fok) Y[(size_t)(h.r0 + rl) * F4 + l] = acc;
+      }
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(tt_smem(&bar_empty[s])) : "memory");
+    }
+  }
+  if (!ok) atomicExch(err, 1);
 }
 
 static int env_int(const char* name, int dflt) {
@@ -505,6 +674,42 @@ extern "C" int tsg_spmm_tiled(const int32_t* rowptr, const int32_t* colidx, cons
 #undef TSG_SW
 #undef TSG_GO
   return check_launch("spmm_tiled");
+}
+
+extern "C" int tsg_spmm_tma(const int32_t* rowptr, const int32_t* colidx, const float* val,
+                            const float* H, const float* bias, float* Y, const int64_t* tile_ptr,
+                            int64_t num_tiles, int64_t num_rows, int64_t feat, int flags, int32_t* status_dev,
+                            void* stream) {
+  TSG_REQUIRE(num_rows >= 0 && feat > 0 && num_tiles >= 0, "spmm_tma: bad shape");
+  TSG_REQUIRE(num_rows < (int64_t)0x7fffffff && num_tiles < (int64_t)0x7fffffff, "spmm_tma: too large");
+  if (num_rows == 0 || num_tiles == 0) return TSG_OK;
+  TSG_REQUIRE(rowptr && colidx && H && Y && tile_ptr && status_dev, "spmm_tma: null pointer");
+  const bool ok_shape = (feat % 4 == 0) && feat <= 32 &&
+                        ((((uintptr_t)H) | ((uintptr_t)Y) | ((uintptr_t)rowptr) | ((uintptr_t)colidx) | ((uintptr_t)val) |
+                          ((uintptr_t)bias)) & 15) == 0;
+  if (!ok_shape) return tsg_spmm(rowptr, colidx, val, H, bias, Y, num_rows, feat, flags, stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int relu = (flags & TSG_SPMM_RELU) ? 1 : 0;
+  const bool exact = (flags & TSG_SPMM_EXACT) != 0;
+  const int F4 = (int)(feat / 4);
+  int lpr = 1; while (lpr < F4) lpr <<= 1;
+  // stage budget: H rows + (colidx, val) + rowptr; ~6.5 entries per row => split the budget accordingly
+  const int row_bytes = F4 * 16;
+  const int row_cap = (TT_STAGE_BYTES - 4096) / (row_bytes + 7 * 8 + 4) & ~3;
+  const int nnz_cap = ((TT_STAGE_BYTES - 1024 - row_cap * (row_bytes + 4)) / 8 - 8) & ~3;
+  const size_t smem = 2 * (size_t)TT_STAGE_BYTES;
+  int grid = (int)(num_tiles < TSG_NUM_SMS ? num_tiles : TSG_NUM_SMS);
+#define TSG_TT(L, V, FM)                                                                                          \
+  { cudaFuncSetAttribute(k_spmm_tma<L, V, FM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);              \
+    k_spmm_tma<L, V, FM><<<grid, TT_THREADS, smem, st>>>(rowptr, colidx, val, (const float4*)H, (const float4*)bias, \
+        (float4*)Y, tile_ptr, (int)num_tiles, F4, row_cap, nnz_cap, relu, status_dev); }
+#define TSG_TTF(L, V) if (exact) TSG_TT(L, V, false) else TSG_TT(L, V, true)
+#define TSG_TTV(L) if (val) { TSG_TTF(L, true) } else { TSG_TTF(L, false) }
+  switch (lpr) { case 1: TSG_TTV(1) break; case 2: TSG_TTV(2) break; case 4: TSG_TTV(4) break; default: TSG_TTV(8) break; }
+#undef TSG_TTV
+#undef TSG_TTF
+#undef TSG_TT
+  return check_launch("spmm_tma");
 }
 
 static int colsum_blocks(int64_t N) {

@@ -31,6 +31,7 @@ _PROTOTYPES = {
     "tsg_csr_filter_workspace_bytes": (SZ, [I64]),
     "tsg_csr_filter": (I, [P, P, P, P, P, P, I64, P, P, P, P, P, P, P, SZ, P]),
     "tsg_spmm": (I, [P, P, P, P, P, P, I64, I64, I, P]),
+    "tsg_spmm_tma": (I, [P, P, P, P, P, P, P, I64, I64, I64, I, P, P]),
     "tsg_spmm_tiled": (I, [P, P, P, P, P, P, P, I64, I64, I64, I, P]),
     "tsg_colsum_workspace_bytes": (SZ, [I64, I64]),
     "tsg_relu_bwd_colsum": (I, [P, P, P, P, I64, I64, P, SZ, P]),

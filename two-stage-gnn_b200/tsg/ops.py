@@ -63,6 +63,7 @@ class CSR:
     t_eid: Optional[torch.Tensor]
     num_nodes: int
     tile_ptr: Optional[torch.Tensor] = None     # int64 [T+1]: self-contained row runs (whole graphs)
+    tma_ok: bool = False                        # arrays have the 16-byte slack the TMA-staged K2 needs
 
 
 def build_csr(edges: EdgeList, num_nodes: int, mode: int = CSR_GCN, transposed: bool = True,
@@ -107,14 +108,15 @@ def build_csr_graphs(edges: EdgeList, node_ptr: torch.Tensor, num_nodes: int, ma
     E, N, G = edges.cap, int(num_nodes), node_ptr.numel() - 1
     cap = E + N
     i32 = dict(dtype=torch.int32, device=dev)
-    rowptr = torch.empty(N + 1, **i32)
-    colidx = torch.empty(cap, **i32)
-    val = torch.empty(cap, dtype=torch.float32, device=dev)
+    # 16 bytes of slack behind every array: the TMA-staged K2 rounds its bulk copies up to 16 bytes
+    rowptr = torch.empty(N + 1 + 4, **i32)[:N + 1]
+    colidx = torch.empty(cap + 4, **i32)[:cap]
+    val = torch.empty(cap + 4, dtype=torch.float32, device=dev)[:cap]
     eid = torch.empty(cap, **i32) if want_eid else None
     if transposed:
-        t_rowptr = torch.empty(N + 1, **i32)
-        t_colidx = torch.empty(cap, **i32)
-        t_val = torch.empty(cap, dtype=torch.float32, device=dev)
+        t_rowptr = torch.empty(N + 1 + 4, **i32)[:N + 1]
+        t_colidx = torch.empty(cap + 4, **i32)[:cap]
+        t_val = torch.empty(cap + 4, dtype=torch.float32, device=dev)[:cap]
         t_eid = torch.empty(cap, **i32) if want_eid else None
     else:
         t_rowptr = t_colidx = t_val = t_eid = None
@@ -125,17 +127,25 @@ def build_csr_graphs(edges: EdgeList, node_ptr: torch.Tensor, num_nodes: int, ma
     call("tsg_csr_build_graphs", ptr(edges.row), ptr(edges.col), ptr(eptr), ptr(node_ptr), G, N, E,
          int(max_graph_nodes), ptr(rowptr), ptr(colidx), ptr(val), ptr(eid), ptr(t_rowptr), ptr(t_colidx),
          ptr(t_val), ptr(t_eid), ptr(ws), wsb, stream_ptr())
-    return CSR(rowptr, colidx, val, eid, t_rowptr, t_colidx, t_val, t_eid, N)
+    csr = CSR(rowptr, colidx, val, eid, t_rowptr, t_colidx, t_val, t_eid, N)
+    csr.tile_ptr = node_ptr            # graph boundaries = self-contained tiles (K1b traps on a leaving edge)
+    csr.tma_ok = True                  # arrays carry the 16-byte slack tsg_spmm_tma needs
+    return csr
 
 
 def spmm_raw(rowptr, colidx, val, H: torch.Tensor, bias=None, relu: bool = False,
-             tile_ptr: Optional[torch.Tensor] = None, exact: Optional[bool] = None) -> torch.Tensor:
+             tile_ptr: Optional[torch.Tensor] = None, exact: Optional[bool] = None, tma: bool = False) -> torch.Tensor:
     """exact=True rounds every product before the add (bit-identical to index_add_ in COO order);
     the default (SPMM_EXACT_DEFAULT = False) fuses it (FFMA): same order, <= 1 ulp per term."""
     n = rowptr.numel() - 1
     H = H.contiguous()
     Y = torch.empty(n, H.size(1), dtype=torch.float32, device=H.device)
     flags = (SPMM_RELU if relu else 0) | (SPMM_EXACT if (SPMM_EXACT_DEFAULT if exact is None else exact) else 0)
+    if tma and tile_ptr is not None and H.size(1) % 4 == 0 and H.size(1) <= 32:
+        status = torch.zeros(1, dtype=torch.int32, device=H.device)
+        call("tsg_spmm_tma", ptr(rowptr), ptr(colidx), ptr(val), ptr(H), ptr(bias), ptr(Y), ptr(tile_ptr),
+             tile_ptr.numel() - 1, n, H.size(1), flags, ptr(status), stream_ptr())
+        return Y
     if USE_TILED_SPMM and tile_ptr is not None and H.size(1) % 4 == 0:
         call("tsg_spmm_tiled", ptr(rowptr), ptr(colidx), ptr(val), ptr(H), ptr(bias), ptr(Y), ptr(tile_ptr),
              tile_ptr.numel() - 1, n, H.size(1), flags, stream_ptr())
