@@ -17,6 +17,7 @@
 // Plain FP32 FFMA; no tensor cores (TF32 would break the 1e-5 parity bar; DiffPool's contractions
 // use the 3xTF32 split on tcgen05 in k7).
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace tsg {
 
@@ -191,6 +192,94 @@ k_linear_fwd(const float* __restrict__ X, const float* __restrict__ W, const flo
       }
     }
     __syncthreads();                             // everyone is done with Xcur before it is refilled
+    buf ^= 1;
+  }
+}
+
+// Dense-input variant (K % 4 == 0): no per-k zero test (the warp vote + scalar LDS per k made the K = 32 products
+// of the pooled levels and of the backward issue bound: 62 us for 124 MB), x read as float4, 4 rows x 4 columns
+// of register blocking per thread.  Same k-ascending FMA sequence per output as k_linear_fwd, so the two kernels
+// agree bit for bit (a skipped zero term is fma(0, w, acc) = acc).
+constexpr int LIND_RPT = 4;
+template <int CG>
+__global__ void __launch_bounds__(LIN_THREADS)
+k_linear_fwd_dense(const float* __restrict__ X, const float* __restrict__ W, const float* __restrict__ bias,
+                   float* __restrict__ Y, int N, int K, int M, int ldw, int ldy, int w_transposed, int flags) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int RS = LIN_THREADS / CG;
+  constexpr int R = RS * LIND_RPT;
+  const int Mp = CG * 4;
+  const int pitch = K + 4;
+  float* Ws = smem;                              // [K][Mp]
+  float* Xs = smem + (size_t)K * Mp;             // 2 x [R][pitch]
+  const int cg = threadIdx.x % CG, rs = threadIdx.x / CG;
+  const unsigned gmask = CG == 32 ? 0xffffffffu : (((1u << CG) - 1u) << (((threadIdx.x & 31) / CG) * CG));
+  for (int i = threadIdx.x; i < K * Mp; i += LIN_THREADS) {
+    int k = i / Mp, m = i - k * Mp;
+    float w = 0.f;
+    if (m < M) w = w_transposed ? W[(size_t)m * ldw + k] : W[(size_t)k * ldw + m];
+    Ws[i] = w;
+  }
+  bool ok[4]; float b4[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    ok[c] = cg * 4 + c < M;
+    b4[c] = (bias != nullptr && ok[c]) ? bias[cg * 4 + c] : 0.f;
+  }
+  const int num_tiles = (N + R - 1) / R;
+  int buf = 0;
+  if ((int)blockIdx.x < num_tiles) stage_rows_async(Xs, X, blockIdx.x * R, R, N, K, pitch);
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int r0 = tile * R;
+    const int rows = min(R, N - r0);
+    const int next = tile + gridDim.x;
+    const float* Xcur = Xs + (size_t)buf * R * pitch;
+    if (next < num_tiles) {
+      stage_rows_async(Xs + (size_t)(buf ^ 1) * R * pitch, X, next * R, R, N, K, pitch);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    float acc[LIND_RPT][4];
+#pragma unroll
+    for (int j = 0; j < LIND_RPT; ++j)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[j][c] = 0.f;
+    for (int k = 0; k < K; k += 4) {
+      float4 w[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) w[q] = *reinterpret_cast<const float4*>(Ws + (k + q) * Mp + cg * 4);
+#pragma unroll
+      for (int j = 0; j < LIND_RPT; ++j) {
+        const float4 a = *reinterpret_cast<const float4*>(Xcur + (rs + j * RS) * pitch + k);
+        acc[j][0] = fmaf(a.x, w[0].x, acc[j][0]); acc[j][1] = fmaf(a.x, w[0].y, acc[j][1]);
+        acc[j][2] = fmaf(a.x, w[0].z, acc[j][2]); acc[j][3] = fmaf(a.x, w[0].w, acc[j][3]);
+        acc[j][0] = fmaf(a.y, w[1].x, acc[j][0]); acc[j][1] = fmaf(a.y, w[1].y, acc[j][1]);
+        acc[j][2] = fmaf(a.y, w[1].z, acc[j][2]); acc[j][3] = fmaf(a.y, w[1].w, acc[j][3]);
+        acc[j][0] = fmaf(a.z, w[2].x, acc[j][0]); acc[j][1] = fmaf(a.z, w[2].y, acc[j][1]);
+        acc[j][2] = fmaf(a.z, w[2].z, acc[j][2]); acc[j][3] = fmaf(a.z, w[2].w, acc[j][3]);
+        acc[j][0] = fmaf(a.w, w[3].x, acc[j][0]); acc[j][1] = fmaf(a.w, w[3].y, acc[j][1]);
+        acc[j][2] = fmaf(a.w, w[3].z, acc[j][2]); acc[j][3] = fmaf(a.w, w[3].w, acc[j][3]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < LIND_RPT; ++j) {
+      const int r = rs + j * RS;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[j][c] += b4[c];
+      if (flags) row_epilogue<CG>(acc[j], ok, M, flags, gmask);
+      if (r < rows) {
+        float* dst = Y + (size_t)(r0 + r) * ldy + cg * 4;
+        if ((M & 3) == 0 && (ldy & 3) == 0) {
+          if (ok[0]) *reinterpret_cast<float4*>(dst) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) if (ok[c]) dst[c] = acc[j][c];
+        }
+      }
+    }
+    __syncthreads();
     buf ^= 1;
   }
 }
@@ -554,15 +643,31 @@ extern "C" int tsg_linear_fwd(const float* X, const float* W, const float* bias,
   for (int64_t m0 = 0; m0 < M; m0 += 128) {
     int64_t mc = M - m0 < 128 ? M - m0 : 128;
     int cg = pick_cg(mc, K);
-    size_t smem = lin_smem_bytes(cg, K);
-    int R = (LIN_THREADS / cg) * LIN_RPT;
-    int tiles = (int)((N + R - 1) / R);
-    int grid = tiles < TSG_NUM_SMS * 4 ? tiles : TSG_NUM_SMS * 4;
     const float* Wc = w_transposed ? W + m0 * K : W + m0;
     int ldw = w_transposed ? (int)K : (int)M;
     const float* bc = bias ? bias + m0 : nullptr;
     float* Yc = Y + m0;
     int rc;
+    static const bool no_dense = getenv("TSG_LIN_NODENSE") != nullptr;
+    const size_t smem_d = ((size_t)K * cg * 4 + 2 * (size_t)(LIN_THREADS / cg) * LIND_RPT * (K + 4)) * sizeof(float);
+    if (!no_dense && (K & 3) == 0 && (((uintptr_t)X) & 15) == 0 && smem_d <= 100 * 1024) {
+      int Rd = (LIN_THREADS / cg) * LIND_RPT;
+      int tiles_d = (int)((N + Rd - 1) / Rd);
+      int grid_d = tiles_d < TSG_NUM_SMS * 4 ? tiles_d : TSG_NUM_SMS * 4;
+#define TSG_GOD(C)                                                                                  \
+      rc = set_smem(k_linear_fwd_dense<C>, smem_d, "linear_fwd(dense)"); if (rc) return rc;           \
+      k_linear_fwd_dense<C><<<grid_d, LIN_THREADS, smem_d, st>>>(X, Wc, bc, Yc, (int)N, (int)K, (int)mc, ldw, (int)M, w_transposed, flags)
+      switch (cg) {
+        case 1: TSG_GOD(1); break; case 2: TSG_GOD(2); break; case 4: TSG_GOD(4); break;
+        case 8: TSG_GOD(8); break; case 16: TSG_GOD(16); break; default: TSG_GOD(32); break;
+      }
+#undef TSG_GOD
+      continue;
+    }
+    size_t smem = lin_smem_bytes(cg, K);
+    int R = (LIN_THREADS / cg) * LIN_RPT;
+    int tiles = (int)((N + R - 1) / R);
+    int grid = tiles < TSG_NUM_SMS * 4 ? tiles : TSG_NUM_SMS * 4;
 #define TSG_GO(C)                                                                                  \
     rc = set_smem(k_linear_fwd<C>, smem, "linear_fwd"); if (rc) return rc;                          \
     k_linear_fwd<C><<<grid, LIN_THREADS, smem, st>>>(X, Wc, bc, Yc, (int)N, (int)K, (int)mc, ldw, (int)M, w_transposed, flags)
