@@ -498,6 +498,77 @@ k_linear_bwd_weight(const float* __restrict__ X, const float* __restrict__ dY, f
   }
 }
 
+// Dense-operand variant of dW = X^T dY for K % 4 == 0, M % 4 == 0, (K/4)(M/4) <= 256 (the 32x32 products of the
+// pooled levels: the warp-per-row kernel above spends 32 shuffles + 32 FMAs per row per lane there, 81 us for
+// 124 MB).  Row tiles of X and dY are staged in shared memory with 16-byte cp.async (double buffered); a thread
+// owns a 4x4 block of dW and one of G = 256 / blocks row groups: two LDS.128 feed 16 FMAs.  Fixed partition
+// (CTA row range, row group, k-ascending rows) => deterministic; groups then CTAs are combined in index order.
+constexpr int LBWD_ROWS = 128;
+__global__ void __launch_bounds__(256)
+k_linear_bwd_weight_dense(const float* __restrict__ X, const float* __restrict__ dY, float* __restrict__ part,
+                          int N, int K, int M) {
+  extern __shared__ __align__(16) float smem[];
+  const int KB = K >> 2, MB = M >> 2, NB = KB * MB;
+  const int groups = 256 / NB;                       // >= 1
+  const int blk = threadIdx.x % NB, grp = threadIdx.x / NB;
+  const int kb = blk / MB, mb = blk - kb * MB;
+  const bool active = grp < groups;
+  float* Xs = smem;                                  // 2 x [ROWS][K]
+  float* Ys = smem + 2 * LBWD_ROWS * K;              // 2 x [ROWS][M]
+  const int rows_per_cta = (N + gridDim.x - 1) / gridDim.x;
+  const int r_begin = blockIdx.x * rows_per_cta;
+  const int r_end = min(N, r_begin + rows_per_cta);
+  auto stage = [&](int buf, int r0) {
+    const int rows = max(0, min(LBWD_ROWS, r_end - r0));
+    const float* xs = X + (size_t)r0 * K; const float* ys = dY + (size_t)r0 * M;
+    float* xd = Xs + buf * LBWD_ROWS * K; float* yd = Ys + buf * LBWD_ROWS * M;
+    for (int i = threadIdx.x * 4; i < rows * K; i += 256 * 4) cp_async16(xd + i, xs + i);
+    for (int i = threadIdx.x * 4; i < rows * M; i += 256 * 4) cp_async16(yd + i, ys + i);
+    cp_async_commit();
+  };
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+  int buf = 0;
+  if (r_begin < r_end) stage(0, r_begin);
+  for (int r0 = r_begin; r0 < r_end; r0 += LBWD_ROWS) {
+    const int rows = min(LBWD_ROWS, r_end - r0);
+    if (r0 + LBWD_ROWS < r_end) { stage(buf ^ 1, r0 + LBWD_ROWS); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    __syncthreads();
+    if (active) {
+      const float* xb = Xs + buf * LBWD_ROWS * K + kb * 4;
+      const float* yb = Ys + buf * LBWD_ROWS * M + mb * 4;
+      for (int r = grp; r < rows; r += groups) {
+        const float4 a = *reinterpret_cast<const float4*>(xb + r * K);
+        const float4 b = *reinterpret_cast<const float4*>(yb + r * M);
+        acc[0][0] = fmaf(a.x, b.x, acc[0][0]); acc[0][1] = fmaf(a.x, b.y, acc[0][1]); acc[0][2] = fmaf(a.x, b.z, acc[0][2]); acc[0][3] = fmaf(a.x, b.w, acc[0][3]);
+        acc[1][0] = fmaf(a.y, b.x, acc[1][0]); acc[1][1] = fmaf(a.y, b.y, acc[1][1]); acc[1][2] = fmaf(a.y, b.z, acc[1][2]); acc[1][3] = fmaf(a.y, b.w, acc[1][3]);
+        acc[2][0] = fmaf(a.z, b.x, acc[2][0]); acc[2][1] = fmaf(a.z, b.y, acc[2][1]); acc[2][2] = fmaf(a.z, b.z, acc[2][2]); acc[2][3] = fmaf(a.z, b.w, acc[2][3]);
+        acc[3][0] = fmaf(a.w, b.x, acc[3][0]); acc[3][1] = fmaf(a.w, b.y, acc[3][1]); acc[3][2] = fmaf(a.w, b.z, acc[3][2]); acc[3][3] = fmaf(a.w, b.w, acc[3][3]);
+      }
+    }
+    __syncthreads();
+    buf ^= 1;
+  }
+  // combine the row groups in index order through shared memory (reuse the staging buffers)
+  float* red = smem;                                  // [groups][K*M]
+  if (active) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) red[(size_t)grp * K * M + (kb * 4 + a) * M + mb * 4 + b] = acc[a][b];
+  }
+  __syncthreads();
+  float* mypart = part + (size_t)blockIdx.x * K * M;
+  for (int i = threadIdx.x; i < K * M; i += 256) {
+    float t = red[i];
+    for (int g2 = 1; g2 < groups; ++g2) t += red[(size_t)g2 * K * M + i];
+    mypart[i] = t;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // Narrow outputs (M <= 4: SAGPool's score layer is F -> 1): GEMV-shaped, pure streaming of X.
 //   fwd : LPR = K/4 lanes read one row as float4s, M dot products, width-LPR shuffle reduction.
@@ -744,6 +815,19 @@ extern "C" int tsg_linear_bwd_weight(const float* X, const float* dY, float* dW,
 #undef TSG_GOS
       launch_partial_sum_final(part, dW, (int)(K * M), nullptr, grid, (int)(K * M), st);
       return check_launch("linear_bwd_weight(small)");
+    }
+  }
+  static const bool no_dense = getenv("TSG_LIN_NODENSE") != nullptr;
+  if (!no_dense && (K & 3) == 0 && (M & 3) == 0 && (K / 4) * (M / 4) <= 256 && M > 4 &&
+      ((((uintptr_t)X) | ((uintptr_t)dY)) & 15) == 0) {
+    size_t smem_d = (size_t)2 * LBWD_ROWS * (K + M) * sizeof(float);
+    const size_t red = (size_t)(256 / ((K / 4) * (M / 4))) * K * M * sizeof(float);
+    if (red > smem_d) smem_d = red;
+    if (smem_d <= 200 * 1024) {
+      int rc = set_smem(k_linear_bwd_weight_dense, smem_d, "linear_bwd_weight(dense)"); if (rc) return rc;
+      k_linear_bwd_weight_dense<<<LBW_GRID, 256, smem_d, st>>>(X, dY, part, (int)N, (int)K, (int)M);
+      launch_partial_sum_final(part, dW, (int)(K * M), nullptr, LBW_GRID, (int)(K * M), st);
+      return check_launch("linear_bwd_weight(dense)");
     }
   }
   TSG_REQUIRE(K <= 256, "linear_bwd_weight: in_feat %lld > 256 not supported", (long long)K);
