@@ -217,10 +217,13 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: tsg has no CPU path")
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    # stdout carries exactly ONE JSON line: keep a private copy of the real stdout for it and point fd 1 at stderr,
+    # so nothing else (NCCL's C-level "NCCL version ..." banner, library chatter) can land there
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"       # keep NCCL's version banner off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=dev)
 
     from tsg import _lib, nn as tnn, ops
@@ -423,7 +426,8 @@ def main():
                                                 "triplets, tsg_pack_batch assembles x/edge_index on the GPU"},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
                 "cpu_baseline": cpu_baseline}
-        print(json.dumps(line), flush=True)
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+    os.close(json_fd)
     if world > 1:
         dist.destroy_process_group()
 
