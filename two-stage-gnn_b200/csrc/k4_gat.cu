@@ -68,6 +68,46 @@ k_gat_aggregate(const int* __restrict__ rowptr, const int* __restrict__ colidx, 
   }
 }
 
+// float4 variant of the aggregation for F % 4 == 0: LPR = heads*F/4 lanes per row (rounded up to a power of two),
+// one 128-bit gather per neighbour per lane, 32 / LPR rows per warp (the scalar kernel above used 32 lanes per
+// 64-wide row and recomputed alpha in every lane for every column).
+template <int LPR>
+__global__ void __launch_bounds__(256)
+k_gat_aggregate_v4(const int* __restrict__ rowptr, const int* __restrict__ colidx, const float4* __restrict__ h,
+                   const float* __restrict__ s1, const float* __restrict__ s2, const float* __restrict__ mx,
+                   const float* __restrict__ zs, int n, int heads, int F4, float slope, float4* __restrict__ hp) {
+  const int l = threadIdx.x % LPR;
+  const int W4 = heads * F4;
+  const int rpc = (n + gridDim.x - 1) / gridDim.x;
+  const int r_begin = blockIdx.x * rpc, r_end = min(n, r_begin + rpc);
+  for (int i = r_begin + threadIdx.x / LPR; i < r_end; i += 256 / LPR) {
+    const int p0 = rowptr[i], p1 = rowptr[i + 1];
+    for (int f = l; f < W4; f += LPR) {
+      const int hd = f / F4;
+      const float si = s1[(int64_t)i * heads + hd];
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      int p = p0;
+      for (; p + 2 <= p1; p += 2) {
+        const int j0 = colidx[p], j1 = colidx[p + 1];
+        const int64_t a0 = (int64_t)j0 * heads + hd, a1 = (int64_t)j1 * heads + hd;
+        const float e0 = lrelu(si + s2[a0], slope) - mx[a0], e1 = lrelu(si + s2[a1], slope) - mx[a1];
+        const float4 h0 = h[(int64_t)j0 * W4 + f], h1 = h[(int64_t)j1 * W4 + f];
+        const float w0 = expf(e0) / zs[a0], w1 = expf(e1) / zs[a1];
+        acc.x = fmaf(w0, h0.x, acc.x); acc.y = fmaf(w0, h0.y, acc.y); acc.z = fmaf(w0, h0.z, acc.z); acc.w = fmaf(w0, h0.w, acc.w);
+        acc.x = fmaf(w1, h1.x, acc.x); acc.y = fmaf(w1, h1.y, acc.y); acc.z = fmaf(w1, h1.z, acc.z); acc.w = fmaf(w1, h1.w, acc.w);
+      }
+      if (p < p1) {
+        const int j0 = colidx[p];
+        const int64_t a0 = (int64_t)j0 * heads + hd;
+        const float w0 = expf(lrelu(si + s2[a0], slope) - mx[a0]) / zs[a0];
+        const float4 h0 = h[(int64_t)j0 * W4 + f];
+        acc.x = fmaf(w0, h0.x, acc.x); acc.y = fmaf(w0, h0.y, acc.y); acc.z = fmaf(w0, h0.z, acc.z); acc.w = fmaf(w0, h0.w, acc.w);
+      }
+      hp[(int64_t)i * W4 + f] = acc;
+    }
+  }
+}
+
 // warp per column j.  Two sweeps over the column's entries; d_alpha kept per (slot, head) in `dal`.
 __global__ void __launch_bounds__(256)
 k_gat_bwd_col(const int* __restrict__ t_rowptr, const int* __restrict__ t_colidx, const int* __restrict__ t_eid,
@@ -253,6 +293,18 @@ extern "C" int tsg_gat_fwd(const int32_t* rowptr, const int32_t* colidx, const i
   cudaStream_t st = (cudaStream_t)stream;
   k_gat_colstats<<<grid_for(n * heads, 256), 256, 0, st>>>(t_rowptr, t_colidx, s1, s2, (int)n, (int)heads, slope, mx, zs);
   int W = (int)(heads * F);
+  if (F % 4 == 0 && ((((uintptr_t)h) | ((uintptr_t)hp)) & 15) == 0) {
+    int W4 = W / 4;
+    int l4 = 1; while (l4 < W4 && l4 < 32) l4 <<= 1;
+    int grid4 = grid_for(n, 256 / l4, 32);
+#define TSG_GO4(L) k_gat_aggregate_v4<L><<<grid4, 256, 0, st>>>(rowptr, colidx, (const float4*)h, s1, s2, mx, zs, (int)n, (int)heads, (int)(F / 4), slope, (float4*)hp)
+    switch (l4) {
+      case 1: TSG_GO4(1); break; case 2: TSG_GO4(2); break; case 4: TSG_GO4(4); break;
+      case 8: TSG_GO4(8); break; case 16: TSG_GO4(16); break; default: TSG_GO4(32); break;
+    }
+#undef TSG_GO4
+    return check_launch("gat_fwd");
+  }
   int lpr = 1; while (lpr < W && lpr < 32) lpr <<= 1;
   int grid = grid_for(n, 256 / lpr, 32);
 #define TSG_GO(L) k_gat_aggregate<L><<<grid, 256, 0, st>>>(rowptr, colidx, h, s1, s2, mx, zs, (int)n, (int)heads, (int)F, slope, hp)
