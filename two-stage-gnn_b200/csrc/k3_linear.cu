@@ -721,7 +721,7 @@ extern "C" int tsg_linear_fwd(const float* X, const float* W, const float* bias,
     int rc;
     static const bool no_dense = getenv("TSG_LIN_NODENSE") != nullptr;
     const size_t smem_d = ((size_t)K * cg * 4 + 2 * (size_t)(LIN_THREADS / cg) * LIND_RPT * (K + 4)) * sizeof(float);
-    if (!no_dense && (K & 3) == 0 && (((uintptr_t)X) & 15) == 0 && smem_d <= 100 * 1024) {
+    if (!no_dense && (K & 3) == 0 && (((uintptr_t)X) & 15) == 0 && smem_d <= 160 * 1024) {
       int Rd = (LIN_THREADS / cg) * LIND_RPT;
       int tiles_d = (int)((N + Rd - 1) / Rd);
       int grid_d = tiles_d < TSG_NUM_SMS * 4 ? tiles_d : TSG_NUM_SMS * 4;

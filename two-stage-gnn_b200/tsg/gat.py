@@ -82,8 +82,13 @@ class DGATLayer(nn.Module):
         wcat = torch.cat([h.w for h in hs], dim=1)                              # [Fin, Hd*Fo]
         a1 = torch.stack([h.a[:Fo, 0] for h in hs]); a2 = torch.stack([h.a[Fo:, 0] for h in hs])
         h = ops.linear(x, wcat)                                                 # encoders_GAT.py:32
-        hv = h.view(-1, Hd, Fo)
-        s1 = (hv * a1).sum(-1); s2 = (hv * a2).sum(-1)                          # :35-36 in closed form
+        # :35-36 in closed form: s1[i,hd] = h[i,hd,:] . a[:F], s2 = h . a[F:], as ONE tall-skinny product with the
+        # block-diagonal [Hd*Fo, 2*Hd] matrix of the attention vectors (K3's GEMV-shaped kernels, fwd and bwd)
+        eye = torch.eye(Hd, device=x.device, dtype=x.dtype)
+        amat = torch.cat([(a1.unsqueeze(2) * eye.unsqueeze(1)).reshape(Hd * Fo, Hd),
+                          (a2.unsqueeze(2) * eye.unsqueeze(1)).reshape(Hd * Fo, Hd)], dim=1)
+        s12 = ops.linear(h, amat)
+        s1, s2 = s12[:, :Hd].contiguous(), s12[:, Hd:].contiguous()
         raw = _GatAggregate.apply(h, s1, s2, csr, Hd, Fo, self.slope)           # :38-43 on the edges
         # columns without edges: uniform 1/N over all N rows (:39-41 with every entry masked)
         h_pad = x_pad @ wcat                                                    # [G, Hd*Fo]
