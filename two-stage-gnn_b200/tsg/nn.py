@@ -168,8 +168,7 @@ class PackedSAGNet(torch.nn.Module):
         computed without a device round trip)."""
         dev = x.device
         edges = edge_index if isinstance(edge_index, EdgeList) else EdgeList.from_edge_index(edge_index)
-        plan = host_level_ptrs(np.asarray(node_ptr_host), self.pooling_ratio)
-        ptrs = torch.from_numpy(plan).pin_memory().to(dev, non_blocking=True)
+        plan, ptrs = self._level_plan(node_ptr_host, dev)
         # K2 shared-memory tiles: runs of whole graphs per pooling level (block-diagonal => self-contained)
         tiles = ([torch.from_numpy(ops.make_tiles(plan[l])).pin_memory().to(dev, non_blocking=True)
                   for l in range(3)] if ops.USE_TILED_SPMM else [None] * 3)
@@ -206,6 +205,22 @@ class PackedSAGNet(torch.nn.Module):
                 aux["perm"].append(perm); aux["edges"].append(edges); aux["score"].append(score)
         z = self.head(outs[0] + outs[1] + outs[2])                        # network.py:46
         return (z, aux) if return_aux else z
+
+    def _level_plan(self, node_ptr_host, dev):
+        """(host plan int64 [4, G+1], the same on the device).  Batches that come round again (an epoch over a fixed
+        set of packed batches) reuse their device copy: keyed on the host array's identity, size and checksum."""
+        arr = np.asarray(node_ptr_host)
+        key = (id(node_ptr_host), arr.shape[0], int(arr[-1]), int(arr.sum()), str(dev), self.pooling_ratio)
+        cache = self.__dict__.setdefault("_plan_cache", {})
+        hit = cache.get(key)
+        if hit is not None:
+            return hit
+        plan = host_level_ptrs(arr, self.pooling_ratio)
+        ptrs = torch.from_numpy(plan).pin_memory().to(dev, non_blocking=True)
+        if len(cache) >= 16:
+            cache.pop(next(iter(cache)))
+        cache[key] = (plan, ptrs)
+        return plan, ptrs
 
     def head(self, z: torch.Tensor) -> torch.Tensor:
         """network.py:48-52: lin1 / ReLU / dropout / lin2 / ReLU / lin3 / log_softmax."""
