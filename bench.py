@@ -56,6 +56,9 @@ def parse():
     ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="print per-entry-point device time shares to stderr")
+    ap.add_argument("--profile-step", default="", choices=["", "dense", "compact"],
+                    help="run only warmup + steps of the device-resident step in that input form and exit without a JSON "
+                         "line (the command profiles/ launch lists are taken with under ncu)")
     return ap.parse_args()
 
 
@@ -267,6 +270,20 @@ def main():
         b = batches[i % len(batches)]
         trainer.step_from_host(b["x"], b["edge_index"], b["node_ptr"], b["triplets"], dev)
 
+    if a.profile_step:
+        t = lambda v: (torch.from_numpy(v) if isinstance(v, np.ndarray) else v).to(dev)
+        cbs = [ops.CompactBatch(t(c["label"]), t(c["row"]), t(c["col"]), t(c["node_ptr"]), t(c["edge_ptr"]),
+                                corpus.num_node_labels) for c in compact]
+        for i in range(a.warmup + a.steps):
+            b = dev_batches[i % 2]
+            if a.profile_step == "compact":
+                trainer.step(cbs[i % 2], None, b["node_ptr"], b["triplets"])
+            else:
+                trainer.step(b["x"], b["edge_index"], b["node_ptr"], b["triplets"])
+        torch.cuda.synchronize()
+        os.close(json_fd)
+        return
+
     # ---- device-resident throughput (value)
     for i in range(max(a.warmup, 3)):
         step_resident(i)
@@ -278,6 +295,23 @@ def main():
     launches = _lib.kernel_launches - k0
     clocks = sampler.finish()
     value = world * graphs_per_step * a.steps / (ms / 1000.0)
+
+    # ---- same step, inputs resident in HBM in the COMPACT form (labels + local int32 endpoints): conv1 runs as the
+    #      K3c gather / segment sum and K1b reads int32 ids, identical forward results (tests/test_compact_gpu.py)
+    dev_compact = []
+    for cbh, b in zip(compact, dev_batches):
+        t = lambda v: (torch.from_numpy(v) if isinstance(v, np.ndarray) else v).to(dev)
+        dev_compact.append((ops.CompactBatch(t(cbh["label"]), t(cbh["row"]), t(cbh["col"]), t(cbh["node_ptr"]),
+                                             t(cbh["edge_ptr"]), corpus.num_node_labels), cbh["node_ptr"], b["triplets"]))
+
+    def step_resident_compact(i):
+        cb, nptr, trip = dev_compact[i % len(dev_compact)]
+        trainer.step(cb, None, nptr, trip)
+
+    for i in range(3):
+        step_resident_compact(i)
+    ms_cres = timed(step_resident_compact, a.steps)
+    value_compact = world * graphs_per_step * a.steps / (ms_cres / 1000.0)
 
     # ---- end to end with host buffers: per-step blocking call, and the pipelined loop (H2D of batch i+1
     #      overlaps the step on batch i; every step still uploads its own inputs and reads its loss back)
@@ -294,7 +328,7 @@ def main():
     e2e_blocking_val = world * graphs_per_step * a.steps / (ms_e2e_blocking / 1000.0)
 
     # ---- end to end from COMPACT host batches (node labels + local int32 edge lists: what the TU files store);
-    #      K0 expands them on the GPU into the same x / edge_index tensors
+    #      they go to the executor as they are (CompactBatch): no one-hot x, no int64 edge_index on the GPU either
     def run_compact(steps):
         return trainer.run_from_host_compact((compact[i % len(compact)] for i in range(steps)), dev,
                                              corpus.num_node_labels)
@@ -302,6 +336,14 @@ def main():
     run_compact(2)
     ms_e2e = timed(lambda i: run_compact(a.steps) if i == 0 else None, 1)
     e2e_val = world * graphs_per_step * a.steps / (ms_e2e / 1000.0)
+
+    def run_compact_expanded(steps):      # the same host batches, expanded to x / edge_index on the GPU by K0 first
+        return trainer.run_from_host_compact((compact[i % len(compact)] for i in range(steps)), dev,
+                                             corpus.num_node_labels, expand=True)
+
+    run_compact_expanded(2)
+    ms_e2e_exp = timed(lambda i: run_compact_expanded(a.steps) if i == 0 else None, 1)
+    e2e_exp_val = world * graphs_per_step * a.steps / (ms_e2e_exp / 1000.0)
     c0 = compact[0]
     h2d_compact = (c0["label"].numel() * 4 + c0["row"].numel() * 8 + c0["triplets"].numel() * 8
                    + 8 * (3 * (graphs_per_step + 1)))
@@ -411,8 +453,17 @@ def main():
                 "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": ms_e2e / a.steps,
                         "h2d_bytes_per_step": int(h2d_compact), "d2h_bytes_per_step": 4,
                         "api": "TripletTrainer.run_from_host_compact: pinned host node labels[i32 N] + local edge lists"
-                               "[i32 2,E] + offsets + triplets per step (what the TU files store); K0 expands to x[f32 N,89] "
-                               "/ edge_index[i64 2,E] on the GPU; copy-stream double buffering, loss read back every step"},
+                               "[i32 2,E] + offsets + triplets per step (what the TU files store), consumed as they are by the "
+                               "executor's compact entries (conv1 = K3c row gather / segment sum, K1b on local int32 ids); "
+                               "copy-stream double buffering, loss read back every step"},
+                "e2e_compact_expanded": {"value": e2e_exp_val, "unit": UNIT, "ms_per_step": ms_e2e_exp / a.steps,
+                                         "h2d_bytes_per_step": int(h2d_compact), "d2h_bytes_per_step": 4,
+                                         "api": "same host batches, expand=True: K0 (tsg_pack_batch) materialises x[f32 N,89] / "
+                                                "edge_index[i64 2,E] on the GPU, then the dense-input step"},
+                "value_compact_input": {"value": value_compact, "unit": UNIT, "ms_per_step": ms_cres / a.steps,
+                                        "note": "device-resident step on the compact input form (labels + local int32 endpoints "
+                                                "in HBM); `value` itself is measured on the PyG wire format (fp32 one-hot x, int64 "
+                                                "edge_index)"},
                 "e2e_fp32_wire": {"value": e2e_wire_val, "unit": UNIT, "ms_per_step": ms_e2e_wire / a.steps,
                                   "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
                                   "api": "TripletTrainer.run_from_host: pinned host x[f32 N,89] / edge_index[i64 2,E] / triplets "

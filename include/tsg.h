@@ -59,6 +59,12 @@ int tsg_pack_batch(const int64_t* ids, const int64_t* out_node_ptr, const int64_
                    const int32_t* corpus_row, const int32_t* corpus_col,
                    const int32_t* corpus_label /*nullable*/, const float* corpus_x /*nullable*/,
                    int64_t feat, float* x_out, int64_t* row_out, int64_t* col_out, void* stream);
+/* Same gather in the compact form the executor's *_compact entries consume: labels and graph-LOCAL int32 endpoints
+ * (out_edge_ptr doubles as their per-graph edge offsets); 4N + 8E bytes written instead of 4NL + 16E. */
+int tsg_pack_batch_compact(const int64_t* ids, const int64_t* out_node_ptr, const int64_t* out_edge_ptr,
+                           int64_t batch_graphs, const int64_t* corpus_node_ptr, const int64_t* corpus_edge_ptr,
+                           const int32_t* corpus_row, const int32_t* corpus_col, const int32_t* corpus_label,
+                           int32_t* label_out, int32_t* row_out, int32_t* col_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * K1  CSR construction + GCN normalisation
@@ -98,6 +104,15 @@ int tsg_edge_ptr(const int64_t* row, int64_t num_edges, const int64_t* num_edges
                  const int64_t* node_ptr, int64_t num_graphs, int64_t* edge_ptr, void* stream);
 size_t tsg_csr_build_graphs_workspace_bytes(int64_t num_graphs, int64_t num_edges_cap);
 int tsg_csr_build_graphs(const int64_t* row, const int64_t* col, const int64_t* edge_ptr,
+                         const int64_t* node_ptr, int64_t num_graphs, int64_t num_nodes,
+                         int64_t num_edges_cap, int64_t max_graph_nodes,
+                         int32_t* rowptr, int32_t* colidx, float* val, int32_t* eid /*nullable*/,
+                         int32_t* t_rowptr /*nullable*/, int32_t* t_colidx, float* t_val,
+                         int32_t* t_eid /*nullable*/,
+                         void* workspace, size_t workspace_bytes, void* stream);
+/* Same result from graph-LOCAL int32 endpoints (ids in [0, n_g), the form the TU files and the compact feeder
+ * hold) with the per-graph edge offsets given: no int64 edge_index has to be materialised. */
+int tsg_csr_build_graphs_local(const int32_t* local_row, const int32_t* local_col, const int64_t* edge_ptr,
                          const int64_t* node_ptr, int64_t num_graphs, int64_t num_nodes,
                          int64_t num_edges_cap, int64_t max_graph_nodes,
                          int32_t* rowptr, int32_t* colidx, float* val, int32_t* eid /*nullable*/,
@@ -432,6 +447,31 @@ int tsg_sag_encoder_fwd(const tsg_sag_shape* shape, const float* x, const int64_
 int tsg_sag_encoder_bwd(const tsg_sag_shape* shape, const float* x, const int64_t* level_ptr,
                         const float* const* params, const float* dz, float* const* grads,
                         void* arena, size_t arena_bytes, void* stream);
+
+/* Compact level-0 input (SURVEY 8f n1 feeder): the batch as the dataset stores it -- one categorical label per node
+ * (the one-hot x of Code/sag/train.py:34 / load_data.py:74-87 is onehot(label), in_feat = number of labels) and
+ * graph-local int32 edge endpoints with per-graph offsets edge_ptr [G+1] (device).  conv1's x @ W becomes a row gather
+ * of W (K3c), its dW a segment sum, K1b reads the local endpoints: z is bit-identical to tsg_sag_encoder_fwd on the
+ * expanded batch (tsg_pack_batch), gradients agree to fp32 summation order (level-0 dW only; all others bit-identical).
+ * Same arena (tsg_sag_arena_bytes) and the same level_ptr / params / grads as above. */
+int tsg_sag_encoder_fwd_compact(const tsg_sag_shape* shape, const int32_t* label, const int32_t* local_row,
+                                const int32_t* local_col, const int64_t* edge_ptr, const int64_t* level_ptr,
+                                const float* const* params, float* z, void* arena, size_t arena_bytes, void* stream);
+int tsg_sag_encoder_bwd_compact(const tsg_sag_shape* shape, const int32_t* label, const int64_t* level_ptr,
+                                const float* const* params, const float* dz, float* const* grads,
+                                void* arena, size_t arena_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K3c  level-0 products for one-hot node-label features (x = onehot(label), never materialised)
+ *   replaces x @ W1 / x^T dY of Code/sag/network.py:34 (GCNConv.lin on data.x) for label-featured datasets.
+ *   out[i, :] = W[label[i], :] (zero row for a label outside [0, K));  dW[k, :] = sum_{label[i] == k} dY[i, :],
+ *   fixed summation order.  tsg_embed_bwd_weight_workspace_bytes returns 0 when a K x M table does not fit
+ *   shared memory (use tsg_pack_batch + the dense K3 entries then).
+ * ------------------------------------------------------------------------------------------ */
+int tsg_embed_fwd(const float* W, const int32_t* label, float* out, int64_t N, int64_t K, int64_t M, void* stream);
+size_t tsg_embed_bwd_weight_workspace_bytes(int64_t K, int64_t M);
+int tsg_embed_bwd_weight(const int32_t* label, const float* dY, float* dW, int64_t N, int64_t K, int64_t M,
+                         void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -50,8 +50,10 @@ def test_executor_single_node_graphs(cuda):
 
 
 def test_host_feeders_agree(cuda):
-    """fp32-wire feeder (x / edge_index from the host), compact feeder (labels + local int32 edges, expanded by K0)
-    and the blocking per-step call produce identical losses: the inputs that reach the step are the same tensors."""
+    """fp32-wire feeder (x / edge_index from the host), compact feeder with K0 expansion and the blocking per-step call
+    produce identical losses: the inputs that reach the step are the same tensors.  The compact feeder's direct path
+    (labels + local endpoints into the executor, nothing expanded) has the identical first loss -- its forward is
+    bit-identical -- and stays within fp32 summation-order distance afterwards (conv1's dW is a segment sum there)."""
     import copy
     from tsg import nn as tnn
     from tsg.train import TripletTrainer
@@ -72,12 +74,16 @@ def test_host_feeders_agree(cuda):
     torch.manual_seed(1)
     base = tnn.PackedSAGNet(corpus.num_node_labels, 32, 32, 0.5, 0.0).to(cuda)
     res = []
-    for mode in ("wire", "compact", "blocking"):
+    for mode in ("wire", "compact", "blocking", "direct"):
         tr = TripletTrainer(copy.deepcopy(base))
         if mode == "wire":
             res.append(tr.run_from_host(batches, cuda))
         elif mode == "compact":
+            res.append(tr.run_from_host_compact(compact, cuda, corpus.num_node_labels, expand=True))
+        elif mode == "direct":
             res.append(tr.run_from_host_compact(compact, cuda, corpus.num_node_labels))
         else:
             res.append([tr.step_from_host(b["x"], b["edge_index"], b["node_ptr"], b["triplets"], cuda) for b in batches])
     assert res[0] == res[1] == res[2] and len(res[0]) == 3
+    assert res[3][0] == res[0][0]
+    np.testing.assert_allclose(res[3], res[0], rtol=1e-5, atol=1e-6)

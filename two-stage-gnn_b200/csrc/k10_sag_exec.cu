@@ -50,6 +50,7 @@ static size_t scratch_need(const tsg_sag_shape* sh) {
     up(tsg_linear_bwd_weight_workspace_bytes(l == 0 ? sh->in_feat : sh->hidden, sh->hidden));
     up(tsg_linear_bwd_weight_workspace_bytes(sh->hidden, 1));
   }
+  up(tsg_embed_bwd_weight_workspace_bytes(sh->in_feat, sh->hidden));
   return align_up(m, 256) + 256;
 }
 
@@ -93,6 +94,16 @@ k_add3(const float* __restrict__ a, const float* __restrict__ b, const float* __
     o[i] = (a[i] + b[i]) + c[i];
 }
 
+// Level-0 input: either the PyG wire format (dense x [n0, in_feat] fp32 + global int64 edge_index) or the compact
+// one (one categorical label per node = the one-hot x, graph-local int32 endpoints + per-graph edge offsets).
+struct SagInput {
+  const float* x;
+  const int64_t *row, *col;
+  const int32_t* label;
+  const int32_t *lrow, *lcol;
+  const int64_t* edge_ptr;
+};
+
 static bool shape_ok(const tsg_sag_shape* sh) {
   if (!sh || sh->num_graphs <= 0 || sh->in_feat <= 0 || sh->hidden <= 0 || sh->num_edges < 0) return false;
   for (int l = 0; l < 4; ++l) if (sh->n[l] <= 0) return false;
@@ -117,33 +128,35 @@ extern "C" size_t tsg_sag_arena_bytes(const tsg_sag_shape* shape) {
   return a.total;
 }
 
-extern "C" int tsg_sag_encoder_fwd(const tsg_sag_shape* sh, const float* x, const int64_t* row, const int64_t* col,
-                                   const int64_t* level_ptr, const float* const* params, float* z,
-                                   void* arena, size_t arena_bytes, void* stream) {
-  TSG_REQUIRE(shape_ok(sh), "sag_encoder_fwd: bad shape");
-  TSG_REQUIRE(x && level_ptr && params && z && arena && (sh->num_edges == 0 || (row && col)), "sag_encoder_fwd: null pointer");
+static int sag_fwd(const tsg_sag_shape* sh, const SagInput& in, const int64_t* level_ptr, const float* const* params,
+                   float* z, void* arena, size_t arena_bytes, void* stream) {
   SagArena a;
   layout(sh, arena, &a);
   if (arena_bytes < a.total) { set_error("sag_encoder_fwd: arena too small (%zu < %zu)", arena_bytes, a.total); return TSG_EWORKSPACE; }
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t G = sh->num_graphs, H = sh->hidden, E = sh->num_edges;
-  const float* xin = x;
+  const float* xin = in.x;
   for (int l = 0; l < 3; ++l) {
     LevelBuf& b = a.lv[l];
     const int64_t n = sh->n[l], k = sh->n[l + 1], fin = l == 0 ? sh->in_feat : H;
     const float *W = params[4 * l], *bias = params[4 * l + 1], *ws = params[4 * l + 2], *bs = params[4 * l + 3];
     const int64_t* ptr_l = level_ptr + (size_t)l * (G + 1);
     const int64_t* ptr_n = level_ptr + (size_t)(l + 1) * (G + 1);
-    if (l == 0) {
-      TSG_TRY(tsg_edge_ptr(row, E, nullptr, ptr_l, G, b.eptr, stream));
-      TSG_TRY(tsg_csr_build_graphs(row, col, b.eptr, ptr_l, G, n, E, sh->max_graph_nodes[l], b.rowptr, b.colidx, b.val,
+    if (l == 0 && in.label) {
+      TSG_TRY(tsg_csr_build_graphs_local(in.lrow, in.lcol, in.edge_ptr, ptr_l, G, n, E, sh->max_graph_nodes[l], b.rowptr,
+                                         b.colidx, b.val, nullptr, b.t_rowptr, b.t_colidx, b.t_val, nullptr, a.scratch,
+                                         a.scratch_bytes, stream));
+    } else if (l == 0) {
+      TSG_TRY(tsg_edge_ptr(in.row, E, nullptr, ptr_l, G, b.eptr, stream));
+      TSG_TRY(tsg_csr_build_graphs(in.row, in.col, b.eptr, ptr_l, G, n, E, sh->max_graph_nodes[l], b.rowptr, b.colidx, b.val,
                                    nullptr, b.t_rowptr, b.t_colidx, b.t_val, nullptr, a.scratch, a.scratch_bytes, stream));
     } else {        // K1c: the pooled level's CSR straight from the previous level's CSR, perm and inv
       const LevelBuf& pb = a.lv[l - 1];
       TSG_TRY(tsg_csr_filter(pb.rowptr, pb.colidx, pb.t_rowptr, pb.t_colidx, pb.perm, pb.inv, n, b.rowptr, b.colidx, b.val,
                              b.t_rowptr, b.t_colidx, b.t_val, a.scratch, a.scratch_bytes, stream));
     }
-    TSG_TRY(tsg_linear_fwd(xin, W, nullptr, b.xw, n, fin, H, 0, 0, stream));
+    if (l == 0 && in.label) TSG_TRY(tsg_embed_fwd(W, in.label, b.xw, n, fin, H, stream));     // onehot(label) @ W
+    else TSG_TRY(tsg_linear_fwd(xin, W, nullptr, b.xw, n, fin, H, 0, 0, stream));
     TSG_TRY(tsg_spmm(b.rowptr, b.colidx, b.val, b.xw, bias, b.h, n, H, TSG_SPMM_RELU, stream));
     TSG_TRY(tsg_linear_fwd(b.h, ws, nullptr, b.sw, n, H, 1, 0, 0, stream));
     TSG_TRY(tsg_spmm(b.rowptr, b.colidx, b.val, b.sw, bs, b.score, n, 1, 0, stream));
@@ -158,11 +171,31 @@ extern "C" int tsg_sag_encoder_fwd(const tsg_sag_shape* sh, const float* x, cons
   return check_launch("sag_encoder_fwd");
 }
 
-extern "C" int tsg_sag_encoder_bwd(const tsg_sag_shape* sh, const float* x, const int64_t* level_ptr,
-                                   const float* const* params, const float* dz, float* const* grads,
+extern "C" int tsg_sag_encoder_fwd(const tsg_sag_shape* sh, const float* x, const int64_t* row, const int64_t* col,
+                                   const int64_t* level_ptr, const float* const* params, float* z,
                                    void* arena, size_t arena_bytes, void* stream) {
-  TSG_REQUIRE(shape_ok(sh), "sag_encoder_bwd: bad shape");
-  TSG_REQUIRE(x && level_ptr && params && dz && grads && arena, "sag_encoder_bwd: null pointer");
+  TSG_REQUIRE(shape_ok(sh), "sag_encoder_fwd: bad shape");
+  TSG_REQUIRE(x && level_ptr && params && z && arena && (sh->num_edges == 0 || (row && col)), "sag_encoder_fwd: null pointer");
+  const SagInput in{x, row, col, nullptr, nullptr, nullptr, nullptr};
+  return sag_fwd(sh, in, level_ptr, params, z, arena, arena_bytes, stream);
+}
+
+extern "C" int tsg_sag_encoder_fwd_compact(const tsg_sag_shape* sh, const int32_t* label, const int32_t* local_row,
+                                           const int32_t* local_col, const int64_t* edge_ptr, const int64_t* level_ptr,
+                                           const float* const* params, float* z, void* arena, size_t arena_bytes,
+                                           void* stream) {
+  TSG_REQUIRE(shape_ok(sh), "sag_encoder_fwd_compact: bad shape");
+  TSG_REQUIRE(label && edge_ptr && level_ptr && params && z && arena && (sh->num_edges == 0 || (local_row && local_col)),
+              "sag_encoder_fwd_compact: null pointer");
+  TSG_REQUIRE(tsg_embed_bwd_weight_workspace_bytes(sh->in_feat, sh->hidden) > 0,
+              "sag_encoder_fwd_compact: %lld labels x %lld hidden does not fit the label-table kernels; expand with tsg_pack_batch",
+              (long long)sh->in_feat, (long long)sh->hidden);
+  const SagInput in{nullptr, nullptr, nullptr, label, local_row, local_col, edge_ptr};
+  return sag_fwd(sh, in, level_ptr, params, z, arena, arena_bytes, stream);
+}
+
+static int sag_bwd(const tsg_sag_shape* sh, const SagInput& in, const int64_t* level_ptr, const float* const* params,
+                   const float* dz, float* const* grads, void* arena, size_t arena_bytes, void* stream) {
   SagArena a;
   layout(sh, arena, &a);
   if (arena_bytes < a.total) { set_error("sag_encoder_bwd: arena too small (%zu < %zu)", arena_bytes, a.total); return TSG_EWORKSPACE; }
@@ -173,7 +206,7 @@ extern "C" int tsg_sag_encoder_bwd(const tsg_sag_shape* sh, const float* x, cons
     const int64_t n = sh->n[l], k = sh->n[l + 1], fin = l == 0 ? sh->in_feat : H;
     const float *W = params[4 * l], *ws = params[4 * l + 2];
     float *dW = grads[4 * l], *dbias = grads[4 * l + 1], *dws = grads[4 * l + 2], *dbs = grads[4 * l + 3];
-    const float* xin = l == 0 ? x : a.lv[l - 1].xg;
+    const float* xin = l == 0 ? in.x : a.lv[l - 1].xg;
     const int64_t* ptr_n = level_ptr + (size_t)(l + 1) * (G + 1);
     // d(x_{l+1}) = readout backward (+ the next level's input gradient)
     //   (the next level's linear backward already wrote its dX into a.dxg: accumulate in place)
@@ -188,7 +221,26 @@ extern "C" int tsg_sag_encoder_bwd(const tsg_sag_shape* sh, const float* x, cons
     TSG_TRY(tsg_relu_bwd_colsum_rank1(a.dh, b.h, a.dsw, ws, a.dhm, dbias, n, H, a.scratch, a.scratch_bytes, stream));
     TSG_TRY(tsg_spmm(b.t_rowptr, b.t_colidx, b.t_val, a.dhm, nullptr, a.dxw, n, H, 0, stream));
     if (l > 0) TSG_TRY(tsg_linear_fwd(a.dxw, W, nullptr, a.dxg, n, H, fin, 1, 0, stream));   // d(x_l), k_{l-1} = n rows
-    TSG_TRY(tsg_linear_bwd_weight(xin, a.dxw, dW, nullptr, n, fin, H, a.scratch, a.scratch_bytes, stream));
+    if (l == 0 && in.label) TSG_TRY(tsg_embed_bwd_weight(in.label, a.dxw, dW, n, fin, H, a.scratch, a.scratch_bytes, stream));
+    else TSG_TRY(tsg_linear_bwd_weight(xin, a.dxw, dW, nullptr, n, fin, H, a.scratch, a.scratch_bytes, stream));
   }
   return check_launch("sag_encoder_bwd");
+}
+
+extern "C" int tsg_sag_encoder_bwd(const tsg_sag_shape* sh, const float* x, const int64_t* level_ptr,
+                                   const float* const* params, const float* dz, float* const* grads,
+                                   void* arena, size_t arena_bytes, void* stream) {
+  TSG_REQUIRE(shape_ok(sh), "sag_encoder_bwd: bad shape");
+  TSG_REQUIRE(x && level_ptr && params && dz && grads && arena, "sag_encoder_bwd: null pointer");
+  const SagInput in{x, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  return sag_bwd(sh, in, level_ptr, params, dz, grads, arena, arena_bytes, stream);
+}
+
+extern "C" int tsg_sag_encoder_bwd_compact(const tsg_sag_shape* sh, const int32_t* label, const int64_t* level_ptr,
+                                           const float* const* params, const float* dz, float* const* grads,
+                                           void* arena, size_t arena_bytes, void* stream) {
+  TSG_REQUIRE(shape_ok(sh), "sag_encoder_bwd_compact: bad shape");
+  TSG_REQUIRE(label && level_ptr && params && dz && grads && arena, "sag_encoder_bwd_compact: null pointer");
+  const SagInput in{nullptr, nullptr, nullptr, label, nullptr, nullptr, nullptr};
+  return sag_bwd(sh, in, level_ptr, params, dz, grads, arena, arena_bytes, stream);
 }

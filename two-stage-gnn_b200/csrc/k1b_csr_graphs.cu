@@ -14,6 +14,7 @@
 //     twice (second time from L2) and each CSR array once.  Integer atomics only (order independent),
 //     ranks make the result deterministic and bit-identical to the generic K1.
 // Graphs that exceed the shared-memory budget make the caller fall back to the generic K1.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace tsg {
@@ -33,15 +34,22 @@ __global__ void k_edge_ptr(const int64_t* __restrict__ row, int64_t E_cap, const
   }
 }
 
+// Edge endpoints come either as the batch's global int64 node ids (PyG edge_index) or as graph-LOCAL
+// int32 ids (what a TU file stores, and what the compact feeder ships): same kernels, two loaders.
+template <typename IdxT> struct EdgeIdx;
+template <> struct EdgeIdx<int64_t> { static __device__ __forceinline__ int local(int64_t v, int64_t n0) { return (int)(v - n0); } };
+template <> struct EdgeIdx<int32_t> { static __device__ __forceinline__ int local(int32_t v, int64_t) { return v; } };
+
 // non-loop edges per graph (+ its node count): the CSR segment length of the graph
+template <typename IdxT>
 __global__ void __launch_bounds__(256)
-k_graph_nnz(const int64_t* __restrict__ row, const int64_t* __restrict__ col, const int64_t* __restrict__ eptr,
+k_graph_nnz(const IdxT* __restrict__ row, const IdxT* __restrict__ col, const int64_t* __restrict__ eptr,
             const int64_t* __restrict__ node_ptr, int G, int* __restrict__ seg_len) {
   __shared__ int sm[33];
   const int g = blockIdx.x;
   const int64_t e0 = eptr[g], e1 = eptr[g + 1];
   int c = 0;
-  for (int64_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) c += (row[e] != col[e]);
+  for (int64_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) c += (row[e] != col[e]);   // equal ids <=> self loop in either index space
   int tot;
   block_excl_scan(c, sm, &tot);
   if (threadIdx.x == 0) seg_len[g] = tot + (int)(node_ptr[g + 1] - node_ptr[g]);
@@ -52,21 +60,26 @@ struct SegLen {
   __device__ int operator()(int64_t i) const { return v[i]; }
 };
 
+// Shared memory is sized per LAUNCH, so one 5,748-node graph in a DD batch used to pin every CTA at 161 KB = one
+// CTA per SM for 3,504 graphs of ~277 nodes.  The host launches the kernel twice when the largest graph is big:
+// graphs with n in (n_lo, max_nodes] are this launch's, the rest exit at once.
+template <typename IdxT>
 __global__ void __launch_bounds__(256)
-k_csr_graph(const int64_t* __restrict__ row, const int64_t* __restrict__ col, const int64_t* __restrict__ eptr,
+k_csr_graph(const IdxT* __restrict__ row, const IdxT* __restrict__ col, const int64_t* __restrict__ eptr,
             const int64_t* __restrict__ node_ptr, const int* __restrict__ seg_off, int G, int64_t E_cap,
             int* __restrict__ rowptr, int* __restrict__ colidx, float* __restrict__ val, int* __restrict__ eid,
             int* __restrict__ t_rowptr, int* __restrict__ t_colidx, float* __restrict__ t_val, int* __restrict__ t_eid,
-            int* __restrict__ slot_d, int* __restrict__ slot_s, int max_nodes) {
+            int* __restrict__ slot_d, int* __restrict__ slot_s, int max_nodes, int n_lo, int n_hi, int edge_cap) {
   extern __shared__ int sh[];
   __shared__ int scan_sm[33];
   const int g = blockIdx.x;
   const int64_t n0 = node_ptr[g];
   const int n = (int)(node_ptr[g + 1] - n0);
+  if (n > n_hi) __trap();                            // caller broke the size contract: fail loudly
+  if (n <= n_lo || n > max_nodes) return;            // the other launch's graph
   const int64_t e0 = eptr[g];
   const int m = (int)(eptr[g + 1] - e0);
   const int base = seg_off[g];
-  if (n > max_nodes) __trap();                       // caller broke the size contract: fail loudly
   int* cnt_d = sh;                       // [max_nodes]  in-degree (non-loop)
   int* cnt_s = cnt_d + max_nodes;        // [max_nodes]  out-degree
   int* rp_d = cnt_s + max_nodes;         // [max_nodes+1] local rowptr, dst-major
@@ -74,15 +87,20 @@ k_csr_graph(const int64_t* __restrict__ row, const int64_t* __restrict__ col, co
   int* fil_d = rp_s + max_nodes + 1;     // [max_nodes]  fill cursors
   int* fil_s = fil_d + max_nodes;        // [max_nodes]
   float* dis = reinterpret_cast<float*>(fil_s + max_nodes);   // [max_nodes]
-  // slot -> local edge id tables (arbitrary order inside a row): this graph's slice of a global
-  // scratch array; written and re-read by this CTA only, so it stays in L1/L2
-  int* tmp_d = slot_d + e0;
-  int* tmp_s = slot_s + e0;
+  // Per-edge state.  A graph with at most edge_cap edges keeps it in shared memory: its endpoints packed as
+  // (r << 16 | c) after the one global read, and the two slot -> local edge id tables (arbitrary order inside a row).
+  // The rank loops below read those tables deg times per edge: from L2 (round 1) they were 70 % of the kernel's
+  // stall samples.  Bigger graphs use their slice of a global scratch array and re-read the edge list from L2.
+  int* sh_edge = reinterpret_cast<int*>(dis + max_nodes);
+  const bool es = m <= edge_cap && max_nodes <= 65536;
+  int* tmp_d = es ? sh_edge + edge_cap : slot_d + e0;
+  int* tmp_s = es ? sh_edge + 2 * edge_cap : slot_s + e0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) { cnt_d[i] = 0; cnt_s[i] = 0; fil_d[i] = 0; fil_s[i] = 0; }
   __syncthreads();
   for (int e = threadIdx.x; e < m; e += blockDim.x) {
-    const int r = (int)(row[e0 + e] - n0), c = (int)(col[e0 + e] - n0);
+    const int r = EdgeIdx<IdxT>::local(row[e0 + e], n0), c = EdgeIdx<IdxT>::local(col[e0 + e], n0);
     if ((unsigned)r >= (unsigned)n || (unsigned)c >= (unsigned)n) __trap();   // edge leaves its graph: not a packed batch
+    if (es) sh_edge[e] = (int)(((unsigned)r << 16) | (unsigned)c);
     if (r != c) { atomicAdd(&cnt_d[c], 1); atomicAdd(&cnt_s[r], 1); }
   }
   __syncthreads();
@@ -110,9 +128,14 @@ k_csr_graph(const int64_t* __restrict__ row, const int64_t* __restrict__ col, co
       if (t_rowptr) t_rowptr[n0 + i] = base + rp_s[i];
     }
   }
+  auto endpoints = [&](int e, int& r, int& c) {
+    if (es) { const unsigned p = (unsigned)sh_edge[e]; r = (int)(p >> 16); c = (int)(p & 0xffffu); }
+    else { r = EdgeIdx<IdxT>::local(row[e0 + e], n0); c = EdgeIdx<IdxT>::local(col[e0 + e], n0); }
+  };
   // slot claim (arbitrary order) ...
   for (int e = threadIdx.x; e < m; e += blockDim.x) {
-    const int r = (int)(row[e0 + e] - n0), c = (int)(col[e0 + e] - n0);
+    int r, c;
+    endpoints(e, r, c);
     if (r == c) continue;
     tmp_d[rp_d[c] - c + atomicAdd(&fil_d[c], 1)] = e;        // rp - index = offset without the loops
     tmp_s[rp_s[r] - r + atomicAdd(&fil_s[r], 1)] = e;
@@ -120,7 +143,8 @@ k_csr_graph(const int64_t* __restrict__ row, const int64_t* __restrict__ col, co
   __syncthreads();
   // ... then the rank among the row's edge ids gives the stable (COO-order) position
   for (int e = threadIdx.x; e < m; e += blockDim.x) {
-    const int r = (int)(row[e0 + e] - n0), c = (int)(col[e0 + e] - n0);
+    int r, c;
+    endpoints(e, r, c);
     if (r == c) continue;
     const float v = __fmul_rn(__fmul_rn(dis[r], 1.0f), dis[c]);
     {
@@ -153,8 +177,8 @@ k_csr_graph(const int64_t* __restrict__ row, const int64_t* __restrict__ col, co
   }
 }
 
-static size_t graph_smem_bytes(int64_t max_nodes) {
-  return (size_t)(6 * max_nodes + 2) * 4 + (size_t)max_nodes * 4 + 64;
+static size_t graph_smem_bytes(int64_t max_nodes, int64_t edge_cap = 0) {
+  return (size_t)(6 * max_nodes + 2) * 4 + (size_t)max_nodes * 4 + (size_t)edge_cap * 12 + 64;
 }
 
 }  // namespace tsg
@@ -174,20 +198,29 @@ extern "C" size_t tsg_csr_build_graphs_workspace_bytes(int64_t num_graphs, int64
          2 * ws_bytes((size_t)num_edges_cap + 1, 4) + 512;
 }
 
-/* returns TSG_EINVAL with a message if a graph does not fit the shared-memory budget (caller falls back) */
-extern "C" int tsg_csr_build_graphs(const int64_t* row, const int64_t* col, const int64_t* edge_ptr,
-                                    const int64_t* node_ptr, int64_t num_graphs, int64_t num_nodes,
-                                    int64_t num_edges_cap, int64_t max_graph_nodes,
-                                    int32_t* rowptr, int32_t* colidx, float* val, int32_t* eid,
-                                    int32_t* t_rowptr, int32_t* t_colidx, float* t_val, int32_t* t_eid,
-                                    void* workspace, size_t workspace_bytes, void* stream) {
+namespace tsg {
+constexpr int CSRG_SMALL_NODES = 1024;     // 28.7 KB of node arrays per CTA
+constexpr int CSRG_SMALL_EDGES = 3072;     // + 36 KB of per-edge state: 3 CTAs per SM, no global round trips
+
+static int edge_cap_env() {           // TSG_CSRG_EDGE_CAP=0 restores the global slot tables (A/B measurements)
+  static const int v = [] { const char* e = getenv("TSG_CSRG_EDGE_CAP"); int x = e ? atoi(e) : CSRG_SMALL_EDGES; return x < 0 ? 0 : (x > 8192 ? 8192 : x); }();
+  return v;
+}
+
+template <typename IdxT>
+static int csr_build_graphs_impl(const IdxT* row, const IdxT* col, const int64_t* edge_ptr,
+                                 const int64_t* node_ptr, int64_t num_graphs, int64_t num_nodes,
+                                 int64_t num_edges_cap, int64_t max_graph_nodes,
+                                 int32_t* rowptr, int32_t* colidx, float* val, int32_t* eid,
+                                 int32_t* t_rowptr, int32_t* t_colidx, float* t_val, int32_t* t_eid,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
   TSG_REQUIRE(num_graphs > 0 && num_nodes > 0, "csr_build_graphs: empty batch");
   TSG_REQUIRE(num_nodes + num_edges_cap < (int64_t)0x7fffffff, "csr_build_graphs: sum n + sum E must stay below 2^31");
   TSG_REQUIRE((num_edges_cap == 0 || (row && col)) && edge_ptr && node_ptr && rowptr && colidx && val, "csr_build_graphs: null pointer");
   TSG_REQUIRE(!t_rowptr || (t_colidx && t_val), "csr_build_graphs: null transposed output");
-  size_t smem = graph_smem_bytes(max_graph_nodes);
-  TSG_REQUIRE(smem <= 200 * 1024, "csr_build_graphs: a graph with %lld nodes needs %zu B of shared memory",
-              (long long)max_graph_nodes, smem);
+  const size_t smem_max = graph_smem_bytes(max_graph_nodes);
+  TSG_REQUIRE(smem_max <= 200 * 1024, "csr_build_graphs: a graph with %lld nodes needs %zu B of shared memory",
+              (long long)max_graph_nodes, smem_max);
   if (workspace_bytes < tsg_csr_build_graphs_workspace_bytes(num_graphs, num_edges_cap)) { set_error("csr_build_graphs: workspace too small"); return TSG_EWORKSPACE; }
   cudaStream_t st = (cudaStream_t)stream;
   Workspace ws(workspace, workspace_bytes);
@@ -196,12 +229,44 @@ extern "C" int tsg_csr_build_graphs(const int64_t* row, const int64_t* col, cons
   int* scan_ws = ws.take<int>(scan_ws_ints(num_graphs));
   int* slot_d = ws.take<int>(num_edges_cap + 1);
   int* slot_s = ws.take<int>(num_edges_cap + 1);
-  k_graph_nnz<<<(int)num_graphs, 256, 0, st>>>(row, col, edge_ptr, node_ptr, (int)num_graphs, seg_len);
+  k_graph_nnz<IdxT><<<(int)num_graphs, 256, 0, st>>>(row, col, edge_ptr, node_ptr, (int)num_graphs, seg_len);
   int rc = exclusive_scan(SegLen{seg_len}, num_graphs, seg_off, scan_ws, st);
   if (rc) return rc;
-  if (smem > 48 * 1024) cudaFuncSetAttribute(k_csr_graph, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  k_csr_graph<<<(int)num_graphs, 256, smem, st>>>(row, col, edge_ptr, node_ptr, seg_off, (int)num_graphs, num_edges_cap,
-                                                  rowptr, colidx, val, eid, t_rowptr, t_colidx, t_val, t_eid,
-                                                  slot_d, slot_s, (int)max_graph_nodes);
+  const int hi = (int)max_graph_nodes;
+  const int split = hi > CSRG_SMALL_NODES ? CSRG_SMALL_NODES : hi;
+  size_t smem_attr = graph_smem_bytes(split, edge_cap_env());
+  if (smem_max > smem_attr) smem_attr = smem_max;
+  if (smem_attr > 48 * 1024) cudaFuncSetAttribute(k_csr_graph<IdxT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_attr);
+  // size classes [0, split] and (split, hi]
+  for (int cls = 0; cls < (hi > split ? 2 : 1); ++cls) {
+    const int lo = cls == 0 ? -1 : split, cap = cls == 0 ? split : hi;
+    const int ecap = cls == 0 ? edge_cap_env() : 0;      // big graphs: all shared memory goes to the node arrays
+    k_csr_graph<IdxT><<<(int)num_graphs, 256, graph_smem_bytes(cap, ecap), st>>>(
+        row, col, edge_ptr, node_ptr, seg_off, (int)num_graphs, num_edges_cap, rowptr, colidx, val, eid,
+        t_rowptr, t_colidx, t_val, t_eid, slot_d, slot_s, cap, lo, hi, ecap);
+  }
   return check_launch("csr_build_graphs");
+}
+}  // namespace tsg
+
+/* returns TSG_EINVAL with a message if a graph does not fit the shared-memory budget (caller falls back) */
+extern "C" int tsg_csr_build_graphs(const int64_t* row, const int64_t* col, const int64_t* edge_ptr,
+                                    const int64_t* node_ptr, int64_t num_graphs, int64_t num_nodes,
+                                    int64_t num_edges_cap, int64_t max_graph_nodes,
+                                    int32_t* rowptr, int32_t* colidx, float* val, int32_t* eid,
+                                    int32_t* t_rowptr, int32_t* t_colidx, float* t_val, int32_t* t_eid,
+                                    void* workspace, size_t workspace_bytes, void* stream) {
+  return csr_build_graphs_impl<int64_t>(row, col, edge_ptr, node_ptr, num_graphs, num_nodes, num_edges_cap, max_graph_nodes,
+                                        rowptr, colidx, val, eid, t_rowptr, t_colidx, t_val, t_eid, workspace, workspace_bytes, stream);
+}
+
+/* same, for graph-LOCAL int32 endpoints (row[e], col[e] in [0, n_g)) with the per-graph edge offsets given */
+extern "C" int tsg_csr_build_graphs_local(const int32_t* row, const int32_t* col, const int64_t* edge_ptr,
+                                          const int64_t* node_ptr, int64_t num_graphs, int64_t num_nodes,
+                                          int64_t num_edges_cap, int64_t max_graph_nodes,
+                                          int32_t* rowptr, int32_t* colidx, float* val, int32_t* eid,
+                                          int32_t* t_rowptr, int32_t* t_colidx, float* t_val, int32_t* t_eid,
+                                          void* workspace, size_t workspace_bytes, void* stream) {
+  return csr_build_graphs_impl<int32_t>(row, col, edge_ptr, node_ptr, num_graphs, num_nodes, num_edges_cap, max_graph_nodes,
+                                        rowptr, colidx, val, eid, t_rowptr, t_colidx, t_val, t_eid, workspace, workspace_bytes, stream);
 }

@@ -144,10 +144,47 @@ class _SagEncoderFn(torch.autograd.Function):
         return (None, None, None, None, None, *grads)
 
 
+class _SagEncoderCompactFn(torch.autograd.Function):
+    """K10 on the compact level-0 input (ops.CompactBatch): labels instead of the one-hot x, local int32 endpoints
+    instead of the int64 edge_index.  Same arena, same kernels below level 0."""
+
+    @staticmethod
+    def forward(ctx, cb, ptrs, shape, *params):
+        from . import _lib
+        dev = cb.label.device
+        params = [p.contiguous() for p in params]
+        arena_bytes = _lib.lib.tsg_sag_arena_bytes(ctypes.byref(shape))
+        if arena_bytes == 0:
+            raise RuntimeError("tsg: bad SAG encoder shape")
+        arena = torch.empty(arena_bytes, dtype=torch.uint8, device=dev)
+        z = torch.empty(shape.num_graphs, 2 * shape.hidden, dtype=torch.float32, device=dev)
+        parr = (ctypes.c_void_p * 12)(*[p.data_ptr() for p in params])
+        _lib.call("tsg_sag_encoder_fwd_compact", ctypes.byref(shape), _lib.ptr(cb.label), _lib.ptr(cb.row), _lib.ptr(cb.col),
+                  _lib.ptr(cb.edge_ptr), _lib.ptr(ptrs), parr, _lib.ptr(z), _lib.ptr(arena), arena_bytes, _lib.stream_ptr())
+        ctx.shape, ctx.arena, ctx.arena_bytes, ctx.label = shape, arena, arena_bytes, cb.label
+        ctx.save_for_backward(ptrs, *params)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        from . import _lib
+        ptrs, *params = ctx.saved_tensors
+        dz = dz.contiguous()
+        grads = [torch.empty_like(p) for p in params]
+        parr = (ctypes.c_void_p * 12)(*[p.data_ptr() for p in params])
+        garr = (ctypes.c_void_p * 12)(*[g.data_ptr() for g in grads])
+        _lib.call("tsg_sag_encoder_bwd_compact", ctypes.byref(ctx.shape), _lib.ptr(ctx.label), _lib.ptr(ptrs), parr,
+                  _lib.ptr(dz), garr, _lib.ptr(ctx.arena), ctx.arena_bytes, _lib.stream_ptr())
+        ctx.arena = None
+        return (None, None, None, *grads)
+
+
 class PackedSAGNet(torch.nn.Module):
     """Code/sag/network.py `Net` over a packed batch.  Three levels of
     GCNConv -> ReLU -> SAGPool(score GCNConv, top-k, gate, filter_adj) -> [gmp || gap],
     summed, then lin1/ReLU/dropout/lin2/ReLU/lin3/log_softmax."""
+
+    accepts_compact = True       # forward(x=ops.CompactBatch, edge_index=None, node_ptr_host)
 
     def __init__(self, num_features: int, nhid: int, num_classes: int, pooling_ratio: float,
                  dropout_ratio: float):
@@ -166,23 +203,23 @@ class PackedSAGNet(torch.nn.Module):
         """x [sum n, F] f32, edge_index int64 [2, sum E] (or an EdgeList), node_ptr_host int64 [G+1]
         on the HOST (graph sizes are known where the batch was packed, so every level's sizes are
         computed without a device round trip)."""
-        dev = x.device
-        edges = edge_index if isinstance(edge_index, EdgeList) else EdgeList.from_edge_index(edge_index)
+        compact = x if isinstance(x, ops.CompactBatch) else None
+        dev = compact.label.device if compact is not None else x.device
         plan, ptrs = self._level_plan(node_ptr_host, dev)
+        if compact is not None:
+            # labels + local endpoints straight into the executor; anything it does not cover expands first (K0)
+            z = self._encode_compact(compact, plan, ptrs) if (USE_EXECUTOR and not return_aux) else None
+            if z is not None:
+                return self.head(z)
+            x, edge_index = compact.expand()
+        edges = edge_index if isinstance(edge_index, EdgeList) else EdgeList.from_edge_index(edge_index)
         # K2 shared-memory tiles: runs of whole graphs per pooling level (block-diagonal => self-contained)
         tiles = ([torch.from_numpy(ops.make_tiles(plan[l])).pin_memory().to(dev, non_blocking=True)
                   for l in range(3)] if ops.USE_TILED_SPMM else [None] * 3)
         if USE_EXECUTOR and not return_aux and edges.count is None and x.dim() == 2:
-            from . import _lib
-            shape = _lib.SagShape(plan.shape[1] - 1, x.size(1), self.nhid, edges.cap)
-            for l in range(4):
-                shape.n[l] = int(plan[l, -1])
-            for l in range(3):
-                shape.max_graph_nodes[l] = max(int(np.diff(plan[l]).max()), 1)
-            if min(shape.n) > 0 and max(shape.max_graph_nodes) <= ops.GRAPH_CSR_MAX_NODES:
-                params = []
-                for conv, pool in ((self.conv1, self.pool1), (self.conv2, self.pool2), (self.conv3, self.pool3)):
-                    params += [conv.weight, conv.bias, pool.score_layer.weight, pool.score_layer.bias]
+            shape = self._sag_shape(plan, x.size(1), edges.cap)
+            if shape is not None:
+                params = self._encoder_params()
                 z = _SagEncoderFn.apply(x, edges.row, edges.col, ptrs, shape, *params)
                 return self.head(z)
         aux = {"perm": [], "edges": [], "score": []}
@@ -205,6 +242,33 @@ class PackedSAGNet(torch.nn.Module):
                 aux["perm"].append(perm); aux["edges"].append(edges); aux["score"].append(score)
         z = self.head(outs[0] + outs[1] + outs[2])                        # network.py:46
         return (z, aux) if return_aux else z
+
+    def _sag_shape(self, plan, in_feat, num_edges):
+        from . import _lib
+        shape = _lib.SagShape(plan.shape[1] - 1, in_feat, self.nhid, num_edges)
+        for l in range(4):
+            shape.n[l] = int(plan[l, -1])
+        for l in range(3):
+            shape.max_graph_nodes[l] = max(int(np.diff(plan[l]).max()), 1)
+        ok = min(shape.n) > 0 and max(shape.max_graph_nodes) <= ops.GRAPH_CSR_MAX_NODES
+        return shape if ok else None
+
+    def _encoder_params(self):
+        params = []
+        for conv, pool in ((self.conv1, self.pool1), (self.conv2, self.pool2), (self.conv3, self.pool3)):
+            params += [conv.weight, conv.bias, pool.score_layer.weight, pool.score_layer.bias]
+        return params
+
+    def _encode_compact(self, cb, plan, ptrs):
+        from . import _lib
+        if cb.num_labels != self.num_features:
+            raise ValueError(f"tsg: batch has {cb.num_labels} node labels, conv1 expects {self.num_features} input columns")
+        if _lib.lib.tsg_embed_bwd_weight_workspace_bytes(cb.num_labels, self.nhid) == 0:
+            return None
+        shape = self._sag_shape(plan, cb.num_labels, int(cb.row.shape[0]))
+        if shape is None:
+            return None
+        return _SagEncoderCompactFn.apply(cb, ptrs, shape, *self._encoder_params())
 
     def _level_plan(self, node_ptr_host, dev):
         """(host plan int64 [4, G+1], the same on the device).  Batches that come round again (an epoch over a fixed

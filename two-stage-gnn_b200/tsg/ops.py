@@ -52,6 +52,32 @@ class EdgeList:
 
 
 @dataclass
+class CompactBatch:
+    """A packed batch as the dataset stores it (SURVEY 8f n1 feeder): one categorical label per node -- the
+    reference's one-hot `data.x` (Code/sag/train.py:34; load_data.py:74-87) is onehot(label) -- and graph-LOCAL
+    int32 edge endpoints.  All tensors live on the device; `node_ptr` / `edge_ptr` are int64 [G+1] offsets.
+    PackedSAGNet consumes it directly (K10 compact entries: no fp32 one-hot matrix, no int64 edge_index);
+    `expand()` materialises the PyG wire format with K0 for every other consumer."""
+    label: torch.Tensor
+    row: torch.Tensor
+    col: torch.Tensor
+    node_ptr: torch.Tensor
+    edge_ptr: torch.Tensor
+    num_labels: int
+
+    def expand(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(x [N, num_labels] fp32 one-hot, edge_index [2, E] int64 with batch-global ids) via tsg_pack_batch."""
+        dev = self.label.device
+        G, N, E = self.node_ptr.shape[0] - 1, int(self.label.shape[0]), int(self.row.shape[0])
+        ids = torch.arange(G, dtype=torch.int64, device=dev)
+        x = torch.empty(N, self.num_labels, dtype=torch.float32, device=dev)
+        ei = torch.empty(2, E, dtype=torch.int64, device=dev)
+        call("tsg_pack_batch", ptr(ids), ptr(self.node_ptr), ptr(self.edge_ptr), G, ptr(self.node_ptr), ptr(self.edge_ptr),
+             ptr(self.row), ptr(self.col), ptr(self.label), None, self.num_labels, ptr(x), ptr(ei[0]), ptr(ei[1]), stream_ptr())
+        return x, ei
+
+
+@dataclass
 class CSR:
     rowptr: torch.Tensor
     colidx: torch.Tensor
@@ -131,6 +157,52 @@ def build_csr_graphs(edges: EdgeList, node_ptr: torch.Tensor, num_nodes: int, ma
     csr.tile_ptr = node_ptr            # graph boundaries = self-contained tiles (K1b traps on a leaving edge)
     csr.tma_ok = True                  # arrays carry the 16-byte slack tsg_spmm_tma needs
     return csr
+
+
+def build_csr_graphs_local(cb: "CompactBatch", num_nodes: int, max_graph_nodes: int) -> CSR:
+    """K1b on a CompactBatch: graph-local int32 endpoints + per-graph edge offsets; same CSR (both orientations,
+    GCN normalisation) as build_csr_graphs on the expanded batch."""
+    if max_graph_nodes > GRAPH_CSR_MAX_NODES:
+        raise RuntimeError(f"tsg: a graph of {max_graph_nodes} nodes exceeds the per-graph CSR builder "
+                           f"({GRAPH_CSR_MAX_NODES}); expand() the batch and use build_csr")
+    dev = cb.label.device
+    E, N, G = int(cb.row.shape[0]), int(num_nodes), cb.node_ptr.numel() - 1
+    cap = E + N
+    i32 = dict(dtype=torch.int32, device=dev)
+    arrs = [torch.empty(N + 1 + 4, **i32)[:N + 1], torch.empty(cap + 4, **i32)[:cap],
+            torch.empty(cap + 4, dtype=torch.float32, device=dev)[:cap]]
+    arrs += [torch.empty(N + 1 + 4, **i32)[:N + 1], torch.empty(cap + 4, **i32)[:cap],
+             torch.empty(cap + 4, dtype=torch.float32, device=dev)[:cap]]
+    wsb = lib.tsg_csr_build_graphs_workspace_bytes(G, E)
+    ws = workspace(wsb, dev)
+    call("tsg_csr_build_graphs_local", ptr(cb.row), ptr(cb.col), ptr(cb.edge_ptr), ptr(cb.node_ptr), G, N, E,
+         int(max_graph_nodes), ptr(arrs[0]), ptr(arrs[1]), ptr(arrs[2]), None, ptr(arrs[3]), ptr(arrs[4]),
+         ptr(arrs[5]), None, ptr(ws), wsb, stream_ptr())
+    csr = CSR(arrs[0], arrs[1], arrs[2], None, arrs[3], arrs[4], arrs[5], None, N)
+    csr.tile_ptr = cb.node_ptr
+    csr.tma_ok = True
+    return csr
+
+
+def embed_fwd(weight: torch.Tensor, label: torch.Tensor) -> torch.Tensor:
+    """K3c: onehot(label) @ weight without the one-hot matrix.  weight [K, M] f32, label int32 [N]."""
+    weight = weight.contiguous()
+    out = torch.empty(label.numel(), weight.size(1), dtype=torch.float32, device=weight.device)
+    call("tsg_embed_fwd", ptr(weight), ptr(label), ptr(out), label.numel(), weight.size(0), weight.size(1), stream_ptr())
+    return out
+
+
+def embed_bwd_weight(label: torch.Tensor, dy: torch.Tensor, num_labels: int) -> torch.Tensor:
+    """K3c: onehot(label)^T @ dy as a fixed-order segment sum.  dy [N, M] f32 -> [num_labels, M]."""
+    dy = dy.contiguous()
+    m = dy.size(1)
+    wsb = lib.tsg_embed_bwd_weight_workspace_bytes(num_labels, m)
+    if wsb == 0:
+        raise RuntimeError(f"tsg: a {num_labels} x {m} label table does not fit shared memory")
+    ws = workspace(wsb, dy.device)
+    dw = torch.empty(num_labels, m, dtype=torch.float32, device=dy.device)
+    call("tsg_embed_bwd_weight", ptr(label), ptr(dy), ptr(dw), label.numel(), num_labels, m, ptr(ws), wsb, stream_ptr())
+    return dw
 
 
 def spmm_raw(rowptr, colidx, val, H: torch.Tensor, bias=None, relu: bool = False,

@@ -144,13 +144,16 @@ class TripletTrainer:
         cur.synchronize()
         return [float(h) for h in host_losses]
 
-    def run_from_host_compact(self, host_batches, device, num_node_labels: int) -> list:
+    def run_from_host_compact(self, host_batches, device, num_node_labels: int, expand: bool = False) -> list:
         """Pipelined end-to-end loop over COMPACT host batches: what a TU dataset actually stores for a graph --
         node labels and the edge list -- instead of the fp32 one-hot matrix and int64 edge_index the PyG surface
         materialises.  Each batch: dict(label int32 [N], row / col int32 [E] LOCAL node ids, node_ptr / edge_ptr
         int64 numpy [G+1], triplets int64 [T,3]), tensors pinned.  Per step the H2D is 4N + 8E + 16G bytes
-        (43 MB instead of 423 MB for the bench batch); `tsg_pack_batch` (K0) expands it on the GPU into the same
-        x [N, L] fp32 / edge_index [2, E] int64 the fp32-wire path uploads, then the step is identical."""
+        (43 MB instead of 423 MB for the bench batch).  The batch goes to the model as an `ops.CompactBatch`:
+        PackedSAGNet's executor consumes labels and local endpoints directly (K3c gather / segment sum for conv1,
+        K1b on int32 local ids), so neither the fp32 one-hot x nor the int64 edge_index is ever written.
+        `expand=True` restores the earlier behaviour: `tsg_pack_batch` (K0) materialises both on the GPU first
+        (models without a compact path do that themselves through `CompactBatch.expand`)."""
         from ._lib import call, ptr, stream_ptr
         cur = torch.cuda.current_stream(device)
         copy = getattr(self, "_copy_stream", None)
@@ -160,7 +163,9 @@ class TripletTrainer:
         def upload(b):
             copy.wait_stream(cur)
             G = b["node_ptr"].shape[0] - 1
-            meta = torch.from_numpy(np.concatenate([np.arange(G, dtype=np.int64), b["node_ptr"], b["edge_ptr"]])).pin_memory()
+            meta = b.get("_meta")
+            if meta is None:          # pinned once per host batch, reused when the batch comes round again
+                meta = b["_meta"] = torch.from_numpy(np.concatenate([b["node_ptr"], b["edge_ptr"]])).pin_memory()
             with torch.cuda.stream(copy):
                 t = {k: b[k].to(device, non_blocking=True) for k in ("label", "row", "col", "triplets")}
                 t["meta"] = meta.to(device, non_blocking=True)
@@ -184,11 +189,12 @@ class TripletTrainer:
             for v in t.values():
                 v.record_stream(cur)
             G, N, E = nptr.shape[0] - 1, int(nptr[-1]), int(eptr[-1])
-            ids, d_nptr, d_eptr = t["meta"][:G], t["meta"][G:2 * G + 1], t["meta"][2 * G + 1:]
-            x = torch.empty(N, num_node_labels, dtype=torch.float32, device=device)
-            ei = torch.empty(2, E, dtype=torch.int64, device=device)
-            call("tsg_pack_batch", ptr(ids), ptr(d_nptr), ptr(d_eptr), G, ptr(d_nptr), ptr(d_eptr), ptr(t["row"]), ptr(t["col"]),
-                 ptr(t["label"]), None, num_node_labels, ptr(x), ptr(ei[0]), ptr(ei[1]), stream_ptr())
+            d_nptr, d_eptr = t["meta"][:G + 1], t["meta"][G + 1:]
+            cb = ops.CompactBatch(t["label"], t["row"], t["col"], d_nptr, d_eptr, num_node_labels)
+            if expand or not getattr(self.model, "accepts_compact", False):
+                x, ei = cb.expand()
+            else:
+                x, ei = cb, None
             loss = self.step(x, ei, nptr, t["triplets"])
             h = torch.empty((), dtype=torch.float32, pin_memory=True)
             h.copy_(loss, non_blocking=True)
@@ -199,6 +205,9 @@ class TripletTrainer:
     def step_from_ids(self, corpus, graph_ids_host: np.ndarray, triplets_host: torch.Tensor) -> float:
         """End-to-end call against an HBM-resident corpus (tsg.feeder.DeviceCorpus): the host sends the
         step's graph ids + triplet index list, the batch is assembled on the GPU, the loss is read back."""
-        x, ei, nptr = corpus.pack(graph_ids_host)
+        if corpus.label is not None and getattr(self.model, "accepts_compact", False):
+            (x, nptr), ei = corpus.pack_compact(graph_ids_host), None
+        else:
+            x, ei, nptr = corpus.pack(graph_ids_host)
         tr = triplets_host.to(corpus.device, non_blocking=True)
         return float(self.step(x, ei, nptr, tr).item())
