@@ -448,6 +448,15 @@ int tsg_sag_encoder_bwd(const tsg_sag_shape* shape, const float* x, const int64_
                         const float* const* params, const float* dz, float* const* grads,
                         void* arena, size_t arena_bytes, void* stream);
 
+/* One level's conv-output backward, fused (used by tsg_sag_encoder_bwd when hidden % 4 == 0): with
+ * dh = inv >= 0 ? dxo[inv] * tanh(score) : 0 (gate backward of Code/sag/layers.py:21, never materialised),
+ * dhm = ReLU'(h) * (dh + dsw ws^T), dbias = colsum(dhm), dws = h^T dsw (score_layer.weight gradient).
+ * dhm / dbias bit-identical to tsg_gate_gather_bwd + tsg_relu_bwd_colsum_rank1; dws to fp32 summation order of
+ * tsg_linear_bwd_weight.  workspace >= 2 * tsg_colsum_workspace_bytes(N, F). */
+int tsg_sag_conv_bwd_fused(const float* dxo, const int32_t* inv, const float* score, const float* h,
+                           const float* dsw, const float* ws_vec, float* dhm, float* dbias, float* dws,
+                           int64_t N, int64_t F, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Compact level-0 input (SURVEY 8f n1 feeder): the batch as the dataset stores it -- one categorical label per node
  * (the one-hot x of Code/sag/train.py:34 / load_data.py:74-87 is onehot(label), in_feat = number of labels) and
  * graph-local int32 edge endpoints with per-graph offsets edge_ptr [G+1] (device).  conv1's x @ W becomes a row gather

@@ -63,18 +63,23 @@ def test_embed_bwd_weight_rejects_oversize_table(cuda):
 
 
 def _big_graph_corpus():
-    """a few DD graphs + one 1,500-node graph (second launch size class) + an edge-free and a one-node graph"""
+    """a few DD graphs + one 1,500-node graph (second launch size class) + a star with a 300-edge hub row (rows longer
+    than the per-thread sort limit) + an edge-free and a one-node graph"""
     base = synth.make_corpus("DD", 6, seed=11)
     rng = np.random.default_rng(0)
     n_big, m_big = 1500, 4000
     r = rng.integers(0, n_big, m_big); c = rng.integers(0, n_big, m_big)      # includes a few self loops
-    rows = [base.row, np.concatenate([r, c]), np.zeros(0, np.int64), np.zeros(0, np.int64)]
-    cols = [base.col, np.concatenate([c, r]), np.zeros(0, np.int64), np.zeros(0, np.int64)]
-    sizes = [n_big, 5, 1]
+    leaves = rng.permutation(np.arange(1, 301)); hub = np.zeros(300, np.int64)
+    star_r = np.concatenate([hub, leaves, [7, 7]]); star_c = np.concatenate([leaves, hub, [7, 9]])   # + a loop, + a duplicate-free extra
+    z = np.zeros(0, np.int64)
+    rows = [base.row, np.concatenate([r, c]), star_r, z, z]
+    cols = [base.col, np.concatenate([c, r]), star_c, z, z]
+    sizes = [n_big, 301, 5, 1]
+    edges = [2 * m_big, star_r.shape[0], 0, 0]
     node_ptr = np.concatenate([base.node_ptr, base.node_ptr[-1] + np.cumsum(sizes)]).astype(np.int64)
-    edge_ptr = np.concatenate([base.edge_ptr, base.edge_ptr[-1] + np.array([2 * m_big, 2 * m_big, 2 * m_big])]).astype(np.int64)
+    edge_ptr = np.concatenate([base.edge_ptr, base.edge_ptr[-1] + np.cumsum(edges)]).astype(np.int64)
     labels = np.concatenate([base.node_label, rng.integers(0, base.num_node_labels, sum(sizes)).astype(np.int32)])
-    y = np.concatenate([base.y, [0, 1, 0]])
+    y = np.concatenate([base.y, [0, 1, 0, 1]])
     return synth.Corpus("DD", node_ptr, edge_ptr, np.concatenate(rows), np.concatenate(cols), labels, y, base.num_node_labels)
 
 

@@ -1,6 +1,7 @@
 // api.cu -- ABI version, thread-local error string, device check.
 #include "common.cuh"
 #include <string.h>
+#include <mutex>
 
 namespace tsg {
 static thread_local char g_err[512] = "";
@@ -9,6 +10,29 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+}  // namespace tsg
+
+namespace tsg {
+// Ticket pool for the fused reduction tails (common.cuh partial_sum_tail): 4,096 zeroed counters per device, handed
+// out round robin.  A counter returns to zero when its kernel ends, so a slot is clean again long before the 4,096
+// calls that bring it round; kernels running concurrently on different streams get different slots.
+static constexpr int TICKETS = 4096;
+static unsigned* g_ticket_pool[64];
+static unsigned g_ticket_cursor[64];
+static std::mutex g_ticket_mu;
+
+unsigned* ticket_next() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lock(g_ticket_mu);
+  if (!g_ticket_pool[dev]) {
+    unsigned* p = nullptr;
+    if (cudaMalloc(&p, TICKETS * sizeof(unsigned)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (cudaMemset(p, 0, TICKETS * sizeof(unsigned)) != cudaSuccess) { cudaGetLastError(); cudaFree(p); return nullptr; }
+    g_ticket_pool[dev] = p;
+  }
+  return g_ticket_pool[dev] + (g_ticket_cursor[dev]++ % TICKETS);
 }
 }  // namespace tsg
 

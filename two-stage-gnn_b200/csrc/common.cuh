@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include "../../include/tsg.h"
 
 #ifndef TSG_NUM_SMS
@@ -211,6 +212,57 @@ k_partial_sum_final(const float* __restrict__ part, float* __restrict__ out0, in
     else if (out1) out1[i - n0] = t;
   }
 }
+
+// Same second stage fused into the producing kernel: every CTA calls this (all threads, no early exits) after it
+// wrote its partial row; the CTA that draws the last ticket folds the rows in EXACTLY k_partial_sum_final's order, so
+// the result does not depend on which CTA that is.  Saves one ~5 us launch per reduction (21 per training step
+// before); worth it only while one CTA can read nb * total floats quickly (fused_tail_ok).  The ticket is a
+// zero-initialised counter from ticket_next(); atomicInc wraps it back to zero for its next user.
+__device__ __forceinline__ void partial_sum_tail(const float* part, float* out0, int n0, float* out1, int nb,
+                                                 int total, unsigned* ticket) {
+  __shared__ float t_sm[32][33];
+  __shared__ int t_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) t_last = atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1;
+  __syncthreads();
+  if (!t_last) return;
+  __threadfence();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int cb = 0; cb < total; cb += 32) {
+    const int i = cb + lane;
+    for (int y = w; y < 32; y += nw) {
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      if (i < total) {
+        int b = y;
+        for (; b + 96 < nb; b += 128) {
+          s0 += __ldcg(part + (size_t)b * total + i);
+          s1 += __ldcg(part + (size_t)(b + 32) * total + i);
+          s2 += __ldcg(part + (size_t)(b + 64) * total + i);
+          s3 += __ldcg(part + (size_t)(b + 96) * total + i);
+        }
+        for (; b < nb; b += 32) s0 += __ldcg(part + (size_t)b * total + i);
+      }
+      t_sm[y][lane] = (s0 + s1) + (s2 + s3);
+    }
+    __syncthreads();
+    if (w == 0 && i < total) {
+      float t = t_sm[0][lane];
+#pragma unroll
+      for (int k = 1; k < 32; ++k) t += t_sm[k][lane];
+      if (i < n0) { if (out0) out0[i] = t; }
+      else if (out1) out1[i - n0] = t;
+    }
+    __syncthreads();
+  }
+}
+
+static inline bool fused_tail_ok(int64_t nb, int64_t total) {
+  static const bool off = getenv("TSG_NO_FUSED_TAIL") != nullptr;
+  return !off && nb * total <= 64 * 1024;
+}
+
+unsigned* ticket_next();      // api.cu: a zeroed device counter from a per-device pool (nullptr if the pool cannot be made)
 
 static inline void launch_partial_sum_final(const float* part, float* out0, int n0, float* out1, int nb,
                                             int total, cudaStream_t st) {

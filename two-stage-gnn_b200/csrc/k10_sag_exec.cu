@@ -46,7 +46,7 @@ static size_t scratch_need(const tsg_sag_shape* sh) {
     up(tsg_csr_build_graphs_workspace_bytes(sh->num_graphs, sh->num_edges));
     up(tsg_topk_workspace_bytes(sh->n[l], sh->num_graphs));
     up(tsg_csr_filter_workspace_bytes(sh->n[l + 1]));
-    up(tsg_colsum_workspace_bytes(sh->n[l], sh->hidden));
+    up(2 * tsg_colsum_workspace_bytes(sh->n[l], sh->hidden));
     up(tsg_linear_bwd_weight_workspace_bytes(l == 0 ? sh->in_feat : sh->hidden, sh->hidden));
     up(tsg_linear_bwd_weight_workspace_bytes(sh->hidden, 1));
   }
@@ -103,6 +103,11 @@ struct SagInput {
   const int32_t *lrow, *lcol;
   const int64_t* edge_ptr;
 };
+
+static bool sag_unfused_env() {        // TSG_SAG_UNFUSED=1: the kernel-per-op backward (A/B measurements, parity tests)
+  static const bool v = getenv("TSG_SAG_UNFUSED") != nullptr;
+  return v;
+}
 
 static bool shape_ok(const tsg_sag_shape* sh) {
   if (!sh || sh->num_graphs <= 0 || sh->in_feat <= 0 || sh->hidden <= 0 || sh->num_edges < 0) return false;
@@ -212,13 +217,20 @@ static int sag_bwd(const tsg_sag_shape* sh, const SagInput& in, const int64_t* l
     //   (the next level's linear backward already wrote its dX into a.dxg: accumulate in place)
     TSG_TRY(tsg_readout_bwd(dz, 2 * H, b.argmax, ptr_n, G, k, H,
                             TSG_READOUT_MAX | TSG_READOUT_MEAN | (l < 2 ? TSG_READOUT_ACCUM : 0), a.dxg, stream));
-    TSG_TRY(tsg_gate_gather_bwd(a.dxg, b.h, b.score, b.inv, a.dh, a.dscore, n, H, stream));
+    // fused level backward (k_sag_conv_bwd_v4): dh is never materialised and h is read once for mask, dbias and dws
+    const bool fused = H % 4 == 0 && H <= 512 && (((uintptr_t)ws) & 15) == 0 && !sag_unfused_env();
+    TSG_TRY(tsg_gate_gather_bwd(a.dxg, b.h, b.score, b.inv, fused ? nullptr : a.dh, a.dscore, n, H, stream));
     // score layer: score = A_hat (h ws) + bs
     TSG_TRY(tsg_relu_bwd_colsum(a.dscore, nullptr, nullptr, dbs, n, 1, a.scratch, a.scratch_bytes, stream));
     TSG_TRY(tsg_spmm(b.t_rowptr, b.t_colidx, b.t_val, a.dscore, nullptr, a.dsw, n, 1, 0, stream));
-    TSG_TRY(tsg_linear_bwd_weight(b.h, a.dsw, dws, nullptr, n, H, 1, a.scratch, a.scratch_bytes, stream));
     // conv layer: h = ReLU(A_hat (x W) + b); its incoming gradient is dh + dsw ws^T, added on the fly
-    TSG_TRY(tsg_relu_bwd_colsum_rank1(a.dh, b.h, a.dsw, ws, a.dhm, dbias, n, H, a.scratch, a.scratch_bytes, stream));
+    if (fused) {
+      TSG_TRY(tsg_sag_conv_bwd_fused(a.dxg, b.inv, b.score, b.h, a.dsw, ws, a.dhm, dbias, dws, n, H, a.scratch,
+                                     a.scratch_bytes, stream));
+    } else {
+      TSG_TRY(tsg_linear_bwd_weight(b.h, a.dsw, dws, nullptr, n, H, 1, a.scratch, a.scratch_bytes, stream));
+      TSG_TRY(tsg_relu_bwd_colsum_rank1(a.dh, b.h, a.dsw, ws, a.dhm, dbias, n, H, a.scratch, a.scratch_bytes, stream));
+    }
     TSG_TRY(tsg_spmm(b.t_rowptr, b.t_colidx, b.t_val, a.dhm, nullptr, a.dxw, n, H, 0, stream));
     if (l > 0) TSG_TRY(tsg_linear_fwd(a.dxw, W, nullptr, a.dxg, n, H, fin, 1, 0, stream));   // d(x_l), k_{l-1} = n rows
     if (l == 0 && in.label) TSG_TRY(tsg_embed_bwd_weight(in.label, a.dxw, dW, n, fin, H, a.scratch, a.scratch_bytes, stream));

@@ -36,6 +36,10 @@ __global__ void k_edge_ptr(const int64_t* __restrict__ row, int64_t E_cap, const
 
 // Edge endpoints come either as the batch's global int64 node ids (PyG edge_index) or as graph-LOCAL
 // int32 ids (what a TU file stores, and what the compact feeder ships): same kernels, two loaders.
+constexpr int CSRG_SMALL_NODES = 1024;     // 28.7 KB of node arrays per CTA
+constexpr int CSRG_SMALL_EDGES = 3072;     // + 36 KB of per-edge state: 3 CTAs per SM, no global round trips
+
+
 template <typename IdxT> struct EdgeIdx;
 template <> struct EdgeIdx<int64_t> { static __device__ __forceinline__ int local(int64_t v, int64_t n0) { return (int)(v - n0); } };
 template <> struct EdgeIdx<int32_t> { static __device__ __forceinline__ int local(int32_t v, int64_t) { return v; } };
@@ -89,8 +93,11 @@ k_csr_graph(const IdxT* __restrict__ row, const IdxT* __restrict__ col, const in
   float* dis = reinterpret_cast<float*>(fil_s + max_nodes);   // [max_nodes]
   // Per-edge state.  A graph with at most edge_cap edges keeps it in shared memory: its endpoints packed as
   // (r << 16 | c) after the one global read, and the two slot -> local edge id tables (arbitrary order inside a row).
-  // The rank loops below read those tables deg times per edge: from L2 (round 1) they were 70 % of the kernel's
-  // stall samples.  Bigger graphs use their slice of a global scratch array and re-read the edge list from L2.
+  // The rank loops below read those tables deg times per edge: from L2 they were 57 % of the kernel's stall samples
+  // (profiles/r01c_k1b_notes.md).  Bigger graphs use their slice of a global scratch array and re-read the edge
+  // list from L2.  Measured and dropped (profiles/r01c_k1b_notes.md): sorting every row's segment by one thread +
+  // one thread per output slot (coalesced stores): 214 us instead of 193; a table-free stable counting sort with
+  // per-warp 16-bit histograms and match.any ranks (6x fewer instructions): 253 us -- match.any is the bottleneck.
   int* sh_edge = reinterpret_cast<int*>(dis + max_nodes);
   const bool es = m <= edge_cap && max_nodes <= 65536;
   int* tmp_d = es ? sh_edge + edge_cap : slot_d + e0;
@@ -141,27 +148,29 @@ k_csr_graph(const IdxT* __restrict__ row, const IdxT* __restrict__ col, const in
     tmp_s[rp_s[r] - r + atomicAdd(&fil_s[r], 1)] = e;
   }
   __syncthreads();
-  // ... then the rank among the row's edge ids gives the stable (COO-order) position
-  for (int e = threadIdx.x; e < m; e += blockDim.x) {
-    int r, c;
-    endpoints(e, r, c);
-    if (r == c) continue;
-    const float v = __fmul_rn(__fmul_rn(dis[r], 1.0f), dis[c]);
-    {
-      const int s = rp_d[c] - c, len = cnt_d[c];
-      int rank = 0;
-      for (int q = 0; q < len; ++q) rank += (tmp_d[s + q] < e);
-      const int p = base + rp_d[c] + rank;
-      colidx[p] = (int)n0 + r; val[p] = v;
-      if (eid) eid[p] = (int)(e0 + e);
-    }
-    if (t_rowptr) {
-      const int s = rp_s[r] - r, len = cnt_s[r];
-      int rank = 0;
-      for (int q = 0; q < len; ++q) rank += (tmp_s[s + q] < e);
-      const int p = base + rp_s[r] + rank;
-      t_colidx[p] = (int)n0 + c; t_val[p] = v;
-      if (t_eid) t_eid[p] = (int)(e0 + e);
+  {
+    // ... then the rank among the row's edge ids gives the stable (COO-order) position
+    for (int e = threadIdx.x; e < m; e += blockDim.x) {
+      int r, c;
+      endpoints(e, r, c);
+      if (r == c) continue;
+      const float v = __fmul_rn(__fmul_rn(dis[r], 1.0f), dis[c]);
+      {
+        const int s = rp_d[c] - c, len = cnt_d[c];
+        int rank = 0;
+        for (int q = 0; q < len; ++q) rank += (tmp_d[s + q] < e);
+        const int p = base + rp_d[c] + rank;
+        colidx[p] = (int)n0 + r; val[p] = v;
+        if (eid) eid[p] = (int)(e0 + e);
+      }
+      if (t_rowptr) {
+        const int s = rp_s[r] - r, len = cnt_s[r];
+        int rank = 0;
+        for (int q = 0; q < len; ++q) rank += (tmp_s[s + q] < e);
+        const int p = base + rp_s[r] + rank;
+        t_colidx[p] = (int)n0 + c; t_val[p] = v;
+        if (t_eid) t_eid[p] = (int)(e0 + e);
+      }
     }
   }
   for (int i = threadIdx.x; i < n; i += blockDim.x) {        // appended self loops: last slot of the row
@@ -176,6 +185,7 @@ k_csr_graph(const IdxT* __restrict__ row, const IdxT* __restrict__ col, const in
     }
   }
 }
+
 
 static size_t graph_smem_bytes(int64_t max_nodes, int64_t edge_cap = 0) {
   return (size_t)(6 * max_nodes + 2) * 4 + (size_t)max_nodes * 4 + (size_t)edge_cap * 12 + 64;
@@ -199,9 +209,6 @@ extern "C" size_t tsg_csr_build_graphs_workspace_bytes(int64_t num_graphs, int64
 }
 
 namespace tsg {
-constexpr int CSRG_SMALL_NODES = 1024;     // 28.7 KB of node arrays per CTA
-constexpr int CSRG_SMALL_EDGES = 3072;     // + 36 KB of per-edge state: 3 CTAs per SM, no global round trips
-
 static int edge_cap_env() {           // TSG_CSRG_EDGE_CAP=0 restores the global slot tables (A/B measurements)
   static const int v = [] { const char* e = getenv("TSG_CSRG_EDGE_CAP"); int x = e ? atoi(e) : CSRG_SMALL_EDGES; return x < 0 ? 0 : (x > 8192 ? 8192 : x); }();
   return v;

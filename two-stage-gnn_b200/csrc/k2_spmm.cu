@@ -596,7 +596,8 @@ constexpr int CS_MAX_BLOCKS = TSG_NUM_SMS * 8;
 __global__ void __launch_bounds__(CS_THREADS)
 k_relu_bwd_colsum(const float* __restrict__ dY, const float* __restrict__ Y, float* __restrict__ dYm,
                   float* __restrict__ part, int64_t N, int F, int64_t rows_per_block,
-                  const float* __restrict__ row_scale, const float* __restrict__ col_vec) {
+                  const float* __restrict__ row_scale, const float* __restrict__ col_vec,
+                  float* __restrict__ dbias, unsigned* ticket) {
   // thread layout: column f = threadIdx.x % Fp, row lane = threadIdx.x / Fp  (Fp = cols per pass)
   extern __shared__ float sm[];
   int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
@@ -626,6 +627,7 @@ k_relu_bwd_colsum(const float* __restrict__ dY, const float* __restrict__ Y, flo
     }
     __syncthreads();
   }
+  if (ticket) partial_sum_tail(part, dbias, F, nullptr, gridDim.x, F, ticket);
 }
 
 // float4 variant for F % 4 == 0 (the scalar kernel above ran at 2.8 TB/s): thread = (row lane, group of 4
@@ -634,7 +636,8 @@ k_relu_bwd_colsum(const float* __restrict__ dY, const float* __restrict__ Y, flo
 __global__ void __launch_bounds__(CS_THREADS)
 k_relu_bwd_colsum_v4(const float4* __restrict__ dY, const float4* __restrict__ Y, float4* __restrict__ dYm,
                      float* __restrict__ part, int64_t N, int F4, int64_t rows_per_block,
-                     const float* __restrict__ row_scale, const float4* __restrict__ col_vec) {
+                     const float* __restrict__ row_scale, const float4* __restrict__ col_vec,
+                     float* __restrict__ dbias, unsigned* ticket) {
   extern __shared__ float4 sm4[];
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
   int64_t r1 = r0 + rows_per_block; if (r1 > N) r1 = N;
@@ -676,6 +679,71 @@ k_relu_bwd_colsum_v4(const float4* __restrict__ dY, const float4* __restrict__ Y
     }
     __syncthreads();
   }
+  if (ticket) partial_sum_tail(part, dbias, F4 * 4, nullptr, gridDim.x, F4 * 4, ticket);
+}
+
+// Backward of one SAGPool level's conv output h, fused (K10 executor, F % 4 == 0):
+//   dh[r]   = inv[r] >= 0 ? dxo[inv[r]] * tanh(score[r]) : 0        (gate backward, layers.py:21 -- never written)
+//   g       = dh + dsw[r] * ws                                      (score layer's x-gradient, rank 1)
+//   dhm     = g where h > 0 else 0                                  (ReLU backward; the only big write)
+//   dbias   = column sum of dhm                                     (conv bias gradient)
+//   dws     = column sum of h * dsw[r]                              (score layer's weight gradient h^T dsw)
+// Same per-element arithmetic as k_gate_gather_bwd_v4 followed by k_relu_bwd_colsum_v4 (dhm and dbias are
+// bit-identical to that sequence); dws replaces a separate pass over h (k_linear_bwd_weight_small) and is summed in
+// this kernel's fixed row order.  Saves, per level, one write + one read of dh and one read of h.
+__global__ void __launch_bounds__(CS_THREADS)
+k_sag_conv_bwd_v4(const float4* __restrict__ dxo, const int* __restrict__ inv, const float* __restrict__ score,
+                  const float4* __restrict__ Y, const float* __restrict__ dsw, const float4* __restrict__ ws4,
+                  float4* __restrict__ dYm, float* __restrict__ part, int64_t N, int F4, int64_t rows_per_block,
+                  float* __restrict__ dbias, float* __restrict__ dws, unsigned* ticket) {
+  extern __shared__ float4 sm4[];                       // [2][CS_THREADS]
+  int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  int64_t r1 = r0 + rows_per_block; if (r1 > N) r1 = N;
+  const int cols = F4 < CS_THREADS ? F4 : CS_THREADS;
+  const int rl = CS_THREADS / cols;
+  const int F = F4 * 4;
+  for (int fb = 0; fb < F4; fb += cols) {
+    const int f = fb + threadIdx.x % cols;
+    const int lane_r = threadIdx.x / cols;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), acw = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane_r < rl && f < F4) {
+      const float4 cv = ws4[f];
+      auto one = [&](int64_t r) {
+        const int m = __ldg(inv + r);
+        const float rs = __ldg(dsw + r);
+        const float4 y = Y[r * F4 + f];
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m >= 0) {
+          const float t = tanhf(__ldg(score + r));
+          const float4 go = __ldg(dxo + (int64_t)m * F4 + f);
+          g = make_float4(go.x * t, go.y * t, go.z * t, go.w * t);
+        }
+        g.x = __fadd_rn(g.x, __fmul_rn(rs, cv.x)); g.y = __fadd_rn(g.y, __fmul_rn(rs, cv.y));
+        g.z = __fadd_rn(g.z, __fmul_rn(rs, cv.z)); g.w = __fadd_rn(g.w, __fmul_rn(rs, cv.w));
+        if (!(y.x > 0.f)) g.x = 0.f;
+        if (!(y.y > 0.f)) g.y = 0.f;
+        if (!(y.z > 0.f)) g.z = 0.f;
+        if (!(y.w > 0.f)) g.w = 0.f;
+        dYm[r * F4 + f] = g;
+        acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
+        acw.x = fmaf(y.x, rs, acw.x); acw.y = fmaf(y.y, rs, acw.y); acw.z = fmaf(y.z, rs, acw.z); acw.w = fmaf(y.w, rs, acw.w);
+      };
+      int64_t r = r0 + lane_r;
+      for (; r + rl < r1; r += 2 * rl) { one(r); one(r + rl); }
+      if (r < r1) one(r);
+    }
+    sm4[threadIdx.x] = acc;
+    sm4[CS_THREADS + threadIdx.x] = acw;
+    __syncthreads();
+    if (threadIdx.x < 2 * cols && fb + threadIdx.x % cols < F4) {
+      const int which = threadIdx.x / cols, c = threadIdx.x % cols;       // 0: dbias partial, 1: dws partial
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = 0; k < rl; ++k) { const float4 v = sm4[which * CS_THREADS + k * cols + c]; t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w; }
+      reinterpret_cast<float4*>(part + (int64_t)blockIdx.x * 2 * F + (int64_t)which * F)[fb + c] = t;
+    }
+    __syncthreads();
+  }
+  if (ticket) partial_sum_tail(part, dbias, F, dws, gridDim.x, 2 * F, ticket);
 }
 
 }  // namespace tsg
@@ -794,11 +862,36 @@ extern "C" int tsg_relu_bwd_colsum_rank1(const float* dY, const float* Y, const 
   int nb = colsum_blocks(N);
   int64_t rpb = (N + nb - 1) / nb; if (rpb < 1) rpb = 1;
   const bool v4 = (F % 4 == 0) && ((((uintptr_t)dY) | ((uintptr_t)Y) | ((uintptr_t)dYm) | ((uintptr_t)col_vec) | ((uintptr_t)part)) & 15) == 0;
+  unsigned* ticket = fused_tail_ok(nb, F) ? ticket_next() : nullptr;      // second stage inside the kernel when small
   if (v4)
     k_relu_bwd_colsum_v4<<<nb, CS_THREADS, CS_THREADS * sizeof(float4), st>>>((const float4*)dY, (const float4*)Y, (float4*)dYm, part,
-                                                                            N, (int)(F / 4), rpb, row_scale, (const float4*)col_vec);
+                                                                            N, (int)(F / 4), rpb, row_scale, (const float4*)col_vec,
+                                                                            dbias, ticket);
   else
-    k_relu_bwd_colsum<<<nb, CS_THREADS, CS_THREADS * sizeof(float), st>>>(dY, Y, dYm, part, N, (int)F, rpb, row_scale, col_vec);
-  launch_partial_sum_final(part, dbias, (int)F, nullptr, nb, (int)F, st);
+    k_relu_bwd_colsum<<<nb, CS_THREADS, CS_THREADS * sizeof(float), st>>>(dY, Y, dYm, part, N, (int)F, rpb, row_scale, col_vec,
+                                                                        dbias, ticket);
+  if (!ticket) launch_partial_sum_final(part, dbias, (int)F, nullptr, nb, (int)F, st);
   return check_launch("relu_bwd_colsum");
+}
+
+/* K10's fused level backward (see k_sag_conv_bwd_v4).  Requires F % 4 == 0 and 16-byte aligned matrices; the caller
+ * (k10_sag_exec.cu) uses the unfused sequence otherwise.  Workspace: 2 * tsg_colsum_workspace_bytes(N, F). */
+extern "C" int tsg_sag_conv_bwd_fused(const float* dxo, const int32_t* inv, const float* score, const float* h,
+                                      const float* dsw, const float* ws_vec, float* dhm, float* dbias, float* dws,
+                                      int64_t N, int64_t F, void* workspace, size_t workspace_bytes, void* stream) {
+  TSG_REQUIRE(N > 0 && F > 0 && F % 4 == 0 && 2 * (F / 4) <= CS_THREADS, "sag_conv_bwd_fused: bad shape");
+  TSG_REQUIRE(dxo && inv && score && h && dsw && ws_vec && dhm && dbias && dws, "sag_conv_bwd_fused: null pointer");
+  TSG_REQUIRE(((((uintptr_t)dxo) | ((uintptr_t)h) | ((uintptr_t)dhm) | ((uintptr_t)ws_vec) | ((uintptr_t)workspace)) & 15) == 0,
+              "sag_conv_bwd_fused: operands must be 16-byte aligned");
+  if (workspace_bytes < 2 * tsg_colsum_workspace_bytes(N, F)) { set_error("sag_conv_bwd_fused: workspace too small"); return TSG_EWORKSPACE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  float* part = (float*)workspace;
+  const int nb = colsum_blocks(N);
+  int64_t rpb = (N + nb - 1) / nb; if (rpb < 1) rpb = 1;
+  unsigned* ticket = fused_tail_ok(nb, 2 * F) ? ticket_next() : nullptr;
+  k_sag_conv_bwd_v4<<<nb, CS_THREADS, 2 * CS_THREADS * sizeof(float4), st>>>(
+      (const float4*)dxo, inv, score, (const float4*)h, dsw, (const float4*)ws_vec, (float4*)dhm, part, N, (int)(F / 4), rpb,
+      dbias, dws, ticket);
+  if (!ticket) launch_partial_sum_final(part, dbias, (int)F, dws, nb, (int)(2 * F), st);
+  return check_launch("sag_conv_bwd_fused");
 }

@@ -619,7 +619,7 @@ k_linear_fwd_small(const float* __restrict__ X, const float* __restrict__ W, con
 template <int LPR>
 __global__ void __launch_bounds__(256)
 k_linear_bwd_weight_small(const float* __restrict__ X, const float* __restrict__ dY, float* __restrict__ part,
-                          int N, int K, int M) {
+                          int N, int K, int M, float* __restrict__ dW, unsigned* ticket) {
   extern __shared__ __align__(16) float smem[];            // [groups][K*M] for the in-CTA combine
   const int l = threadIdx.x % LPR, grp = threadIdx.x / LPR;
   const int groups = 256 / LPR;
@@ -661,6 +661,7 @@ k_linear_bwd_weight_small(const float* __restrict__ X, const float* __restrict__
     for (int g = 1; g < groups; ++g) sacc += smem[(size_t)g * K * M + i];
     mypart[i] = sacc;
   }
+  if (ticket) partial_sum_tail(part, dW, K * M, nullptr, gridDim.x, K * M, ticket);
 }
 
 // lanes per row: enough for M columns (4 per lane) and few enough rows per tile that the X tile
@@ -805,15 +806,16 @@ extern "C" int tsg_linear_bwd_weight(const float* X, const float* dY, float* dW,
     size_t smem_s = (size_t)groups * K * M * sizeof(float);
     if (smem_s <= 200 * 1024) {
       int grid = LBW_GRID;
+      unsigned* ticket = fused_tail_ok(grid, K * M) ? ticket_next() : nullptr;
 #define TSG_GOS(L)                                                                                          \
       { int rc = set_smem(k_linear_bwd_weight_small<L>, smem_s, "linear_bwd_weight(small)"); if (rc) return rc; \
-        k_linear_bwd_weight_small<L><<<grid, 256, smem_s, st>>>(X, dY, part, (int)N, (int)K, (int)M); }
+        k_linear_bwd_weight_small<L><<<grid, 256, smem_s, st>>>(X, dY, part, (int)N, (int)K, (int)M, dW, ticket); }
       switch (lpr) {
         case 1: TSG_GOS(1) break; case 2: TSG_GOS(2) break; case 4: TSG_GOS(4) break;
         case 8: TSG_GOS(8) break; case 16: TSG_GOS(16) break; default: TSG_GOS(32) break;
       }
 #undef TSG_GOS
-      launch_partial_sum_final(part, dW, (int)(K * M), nullptr, grid, (int)(K * M), st);
+      if (!ticket) launch_partial_sum_final(part, dW, (int)(K * M), nullptr, grid, (int)(K * M), st);
       return check_launch("linear_bwd_weight(small)");
     }
   }

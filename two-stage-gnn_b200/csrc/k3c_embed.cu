@@ -171,10 +171,9 @@ extern "C" int tsg_embed_bwd_weight(const int32_t* label, const float* dY, float
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     kern<<<EMB_BWD_GRID, nw * 32, smem, st>>>(label, dY, part, N, (int)K, (int)M, rows_per_cta);
   };
-  if (variant == 1) launch(k_embed_bwd_weight<8, true>);
-  else if (variant == 2) launch(k_embed_bwd_weight<8, false>);
-  else if (variant == 3) launch(k_embed_bwd_weight<16, true>);
-  else launch(k_embed_bwd_weight<16, false>);
+  if (variant == 1) launch(k_embed_bwd_weight<8, true>);          // A/B variants (TSG_EMB_VARIANT), measured in
+  else if (variant == 2) launch(k_embed_bwd_weight<16, false>);   // profiles/r01c_compact_input.md
+  else launch(k_embed_bwd_weight<16, true>);
   launch_partial_sum_final(part, dW, (int)(K * M), nullptr, EMB_BWD_GRID, (int)(K * M), st);
   return check_launch("embed_bwd_weight");
 }

@@ -226,7 +226,7 @@ k_gate_gather_bwd_v4(const float4* __restrict__ dxo, const float4* __restrict__ 
         dot += go.x * xv.x + go.y * xv.y + go.z * xv.z + go.w * xv.w;
         g = make_float4(go.x * t, go.y * t, go.z * t, go.w * t);
       }
-      if (ok) dx[j * F4 + f] = g;
+      if (ok && dx) dx[j * F4 + f] = g;
     }
 #pragma unroll
     for (int d = LPR / 2; d > 0; d >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, d, LPR);
@@ -258,7 +258,7 @@ k_gate_gather_bwd(const float* __restrict__ dxo, const float* __restrict__ x,
         dot += go * x[j * F + f];
         g = go * t;
       }
-      dx[j * F + f] = g;
+      if (dx) dx[j * F + f] = g;
     }
 #pragma unroll
     for (int d = LPR / 2; d > 0; d >>= 1) dot += __shfl_xor_sync(gmask, dot, d);
@@ -353,7 +353,7 @@ extern "C" int tsg_gate_gather_bwd(const float* dxo, const float* x, const float
                                    int64_t N, int64_t F, void* stream) {
   TSG_REQUIRE(N >= 0 && F > 0, "gate_gather_bwd: bad shape");
   if (N == 0) return TSG_OK;
-  TSG_REQUIRE(dxo && x && score && inv && dx && dscore, "gate_gather_bwd: null pointer");
+  TSG_REQUIRE(dxo && x && score && inv && dscore, "gate_gather_bwd: null pointer");     // dx nullable: dscore only
   cudaStream_t st = (cudaStream_t)stream;
   if (F % 4 == 0 && ((((uintptr_t)dxo) | ((uintptr_t)x) | ((uintptr_t)dx)) & 15) == 0) {
     int F4 = (int)(F / 4);
