@@ -448,6 +448,13 @@ int tsg_sag_encoder_bwd(const tsg_sag_shape* shape, const float* x, const int64_
                         const float* const* params, const float* dz, float* const* grads,
                         void* arena, size_t arena_bytes, void* stream);
 
+/* tsg_spmm plus dot_out[r] = Y[r, :] . dot_vec from K2's epilogue (conv + the score layer's h @ ws of
+ * Code/sag/layers.py:18 in one pass); bit-identical to tsg_spmm followed by tsg_linear_fwd(Y, dot_vec, out_feat = 1),
+ * which is what runs for shapes the epilogue does not cover (feat > 128 or not a multiple of 4). */
+int tsg_spmm_dot(const int32_t* rowptr, const int32_t* colidx, const float* val /*nullable*/, const float* H,
+                 const float* bias /*nullable*/, float* Y, const float* dot_vec, float* dot_out,
+                 int64_t num_rows, int64_t feat, int flags, void* stream);
+
 /* One level's conv-output backward, fused (used by tsg_sag_encoder_bwd when hidden % 4 == 0): with
  * dh = inv >= 0 ? dxo[inv] * tanh(score) : 0 (gate backward of Code/sag/layers.py:21, never materialised),
  * dhm = ReLU'(h) * (dh + dsw ws^T), dbias = colsum(dhm), dws = h^T dsw (score_layer.weight gradient).

@@ -182,3 +182,26 @@ def test_spmm_tma_equals_spmm(cuda, exact, shape, G, F):
         ref = ops.spmm_raw(rp, ci, v, h, bias, relu=True, exact=exact)
         got = ops.spmm_raw(rp, ci, v, h, bias, relu=True, exact=exact, tile_ptr=gptr, tma=True)
         assert torch.equal(got, ref)
+
+
+@pytest.mark.parametrize("F", [32, 16, 128, 24, 6, 256])
+def test_spmm_dot_epilogue_is_the_k3_product(cuda, F):
+    """tsg_spmm_dot: Y bit-identical to tsg_spmm, dot_out bit-identical to tsg_linear_fwd(Y, w, out_feat=1) -- from K2's
+    epilogue when F % 4 == 0 and F <= 128, from the K3 call behind it otherwise (F = 6, 256)."""
+    from tsg import ops, synth
+    from tsg._lib import call, ptr, stream_ptr
+    c = synth.make_corpus("DD", 700, seed=21)          # enough rows for the 1024-thread configuration
+    b = synth.pack(c)
+    n = int(c.node_ptr[-1])
+    csr = ops.build_csr(ops.EdgeList.from_edge_index(torch.from_numpy(b["edge_index"]).to(cuda)), n)
+    g = torch.Generator().manual_seed(F)
+    H = torch.randn(n, F, generator=g).to(cuda); bias = torch.randn(F, generator=g).to(cuda)
+    w = torch.randn(F, 1, generator=g).to(cuda)
+    for rows in (n, 300):                                # big (1024-thread) and small (256-thread) launch shapes
+        Y0 = ops.spmm_raw(csr.rowptr[:rows + 1], csr.colidx, csr.val, H, bias, relu=True)
+        d0 = ops.linear_raw(Y0, w, None, False)
+        Y1 = torch.empty(rows, F, device=cuda); d1 = torch.empty(rows, device=cuda)
+        call("tsg_spmm_dot", ptr(csr.rowptr), ptr(csr.colidx), ptr(csr.val), ptr(H), ptr(bias), ptr(Y1), ptr(w), ptr(d1),
+             rows, F, ops.SPMM_RELU, stream_ptr())
+        assert torch.equal(Y0, Y1)
+        assert torch.equal(d0.view(-1), d1)

@@ -162,8 +162,8 @@ static int sag_fwd(const tsg_sag_shape* sh, const SagInput& in, const int64_t* l
     }
     if (l == 0 && in.label) TSG_TRY(tsg_embed_fwd(W, in.label, b.xw, n, fin, H, stream));     // onehot(label) @ W
     else TSG_TRY(tsg_linear_fwd(xin, W, nullptr, b.xw, n, fin, H, 0, 0, stream));
-    TSG_TRY(tsg_spmm(b.rowptr, b.colidx, b.val, b.xw, bias, b.h, n, H, TSG_SPMM_RELU, stream));
-    TSG_TRY(tsg_linear_fwd(b.h, ws, nullptr, b.sw, n, H, 1, 0, 0, stream));
+    // h = ReLU(A_hat xw + b) and, from the same registers, sw = h ws (the score layer's product)
+    TSG_TRY(tsg_spmm_dot(b.rowptr, b.colidx, b.val, b.xw, bias, b.h, ws, b.sw, n, H, TSG_SPMM_RELU, stream));
     TSG_TRY(tsg_spmm(b.rowptr, b.colidx, b.val, b.sw, bs, b.score, n, 1, 0, stream));
     TSG_TRY(tsg_topk(b.score, ptr_l, ptr_n, G, n, b.perm, a.scratch, a.scratch_bytes, stream));
     TSG_TRY(tsg_inv_perm(b.perm, k, n, b.inv, stream));            // filter_adj's relabelling table (layers.py:23)

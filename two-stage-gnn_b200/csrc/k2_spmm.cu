@@ -274,7 +274,8 @@ __global__ void __launch_bounds__(THREADS, 2048 / THREADS)
 k_spmm_g(const int* __restrict__ rowptr, const int* __restrict__ colidx,
          const float* __restrict__ val, const float4* __restrict__ H,
          const float4* __restrict__ bias, float4* __restrict__ Y,
-         int num_rows, int F4, int relu, int hdist) {
+         int num_rows, int F4, int relu, int hdist,
+         const float4* __restrict__ dot_vec, float* __restrict__ dot_out) {
   constexpr int RPI = THREADS / LPR;              // rows per CTA iteration
   const int l = threadIdx.x % LPR;
   const int rpc = (num_rows + gridDim.x - 1) / gridDim.x;
@@ -309,6 +310,7 @@ k_spmm_g(const int* __restrict__ rowptr, const int* __restrict__ colidx,
         if (HAS_VAL) bulk_prefetch_l2(val + q, n);
       }
     }
+    float dot = 0.f;                     // fused y[r, :] . dot_vec (host guarantees F4 <= LPR: one f per lane)
     for (int f = l; f < F4; f += LPR) {
       const char* Hl = reinterpret_cast<const char*>(H + f);
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -354,6 +356,18 @@ k_spmm_g(const int* __restrict__ rowptr, const int* __restrict__ colidx,
         acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f);
       }
       Y[(size_t)r * F4 + f] = acc;
+      if (dot_vec != nullptr) {          // same per-lane FMA chain and butterfly as k_linear_fwd_small: bit-identical
+        const float4 w = __ldg(dot_vec + f);
+        dot = fmaf(acc.x, w.x, dot); dot = fmaf(acc.y, w.y, dot);
+        dot = fmaf(acc.z, w.z, dot); dot = fmaf(acc.w, w.w, dot);
+      }
+    }
+    if (dot_vec != nullptr) {
+      // the LPR lanes of a row leave the row loop together, so the group is converged here
+      const unsigned gmask = LPR == 32 ? 0xffffffffu : (((1u << LPR) - 1u) << (((threadIdx.x & 31) / LPR) * LPR));
+#pragma unroll
+      for (int d = LPR / 2; d > 0; d >>= 1) dot += __shfl_xor_sync(gmask, dot, d, LPR);
+      if (l == 0) dot_out[r] = dot;
     }
   }
 }
@@ -533,7 +547,9 @@ static int env_int(const char* name, int dflt) {
 
 template <bool HAS_VAL>
 static int launch_spmm(const int* rowptr, const int* colidx, const float* val, const float* H,
-                       const float* bias, float* Y, int64_t N, int64_t F, int relu, bool exact, cudaStream_t st) {
+                       const float* bias, float* Y, int64_t N, int64_t F, int relu, bool exact, cudaStream_t st,
+                       const float* dot_vec = nullptr, float* dot_out = nullptr, bool* dot_done = nullptr) {
+  if (dot_done) *dot_done = false;
   bool vec = (F % 4 == 0) && (((uintptr_t)H & 15) == 0) && (((uintptr_t)Y & 15) == 0) &&
              (bias == nullptr || ((uintptr_t)bias & 15) == 0);
   if (vec) {
@@ -560,7 +576,12 @@ static int launch_spmm(const int* rowptr, const int* colidx, const float* val, c
       int g = (int)((N + rpi - 1) / rpi);
       const int cap = big ? TSG_NUM_SMS * ctas_per_sm_1024 : TSG_NUM_SMS * 32;
       if (g > cap) g = cap;
-#define TSG_G(L, FM, T) k_spmm_g<L, HAS_VAL, FM, T><<<g, T, 0, st>>>(rowptr, colidx, val, (const float4*)H, (const float4*)bias, (float4*)Y, (int)N, F4, relu, big ? hdist : 0)
+      // y . dot_vec in the epilogue when one lane owns one float4 of the row (F <= 128) -- the shape k_linear_fwd_small
+      // would take; otherwise the caller runs K3 afterwards
+      const bool fuse_dot = dot_vec && dot_out && F4 <= lpr && (((uintptr_t)dot_vec) & 15) == 0;
+      const float4* dv = fuse_dot ? (const float4*)dot_vec : nullptr;
+      if (dot_done) *dot_done = fuse_dot;
+#define TSG_G(L, FM, T) k_spmm_g<L, HAS_VAL, FM, T><<<g, T, 0, st>>>(rowptr, colidx, val, (const float4*)H, (const float4*)bias, (float4*)Y, (int)N, F4, relu, big ? hdist : 0, dv, dot_out)
 #define TSG_GT(L, FM) if (big) TSG_G(L, FM, 1024); else TSG_G(L, FM, 256);
 #define TSG_GV(L) if (exact) { TSG_GT(L, false) } else { TSG_GT(L, true) }
       switch (lpr) {
@@ -894,4 +915,27 @@ extern "C" int tsg_sag_conv_bwd_fused(const float* dxo, const int32_t* inv, cons
       dbias, dws, ticket);
   if (!ticket) launch_partial_sum_final(part, dbias, (int)F, dws, nb, (int)(2 * F), st);
   return check_launch("sag_conv_bwd_fused");
+}
+
+/* tsg_spmm + the row-wise product Y @ dot_vec (the score layer's h @ ws of Code/sag/layers.py:18 right behind
+ * conv's ReLU(A_hat (xW) + b)): computed in K2's epilogue while the row is in registers -- bit-identical to
+ * tsg_linear_fwd(Y, dot_vec, M = 1) -- or, for shapes the epilogue does not cover, by that call. */
+extern "C" int tsg_linear_fwd(const float* X, const float* W, const float* bias, float* Y, int64_t N, int64_t K, int64_t M,
+                              int w_transposed, int flags, void* stream);
+extern "C" int tsg_spmm_dot(const int32_t* rowptr, const int32_t* colidx, const float* val, const float* H,
+                            const float* bias, float* Y, const float* dot_vec, float* dot_out,
+                            int64_t num_rows, int64_t feat, int flags, void* stream) {
+  TSG_REQUIRE(num_rows >= 0 && feat > 0, "spmm_dot: bad shape rows=%lld feat=%lld", (long long)num_rows, (long long)feat);
+  TSG_REQUIRE(num_rows < (int64_t)0x7fffffff, "spmm_dot: too many rows");
+  if (num_rows == 0) return TSG_OK;
+  TSG_REQUIRE(rowptr && colidx && H && Y && dot_vec && dot_out, "spmm_dot: null pointer");
+  const int relu = (flags & TSG_SPMM_RELU) ? 1 : 0;
+  const bool exact = (flags & TSG_SPMM_EXACT) != 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  static const bool off = getenv("TSG_NO_SPMM_DOT") != nullptr;
+  bool done = false;
+  int rc = val ? launch_spmm<true>(rowptr, colidx, val, H, bias, Y, num_rows, feat, relu, exact, st, off ? nullptr : dot_vec, dot_out, &done)
+               : launch_spmm<false>(rowptr, colidx, val, H, bias, Y, num_rows, feat, relu, exact, st, off ? nullptr : dot_vec, dot_out, &done);
+  if (rc != TSG_OK || done) return rc;
+  return tsg_linear_fwd(Y, dot_vec, nullptr, dot_out, num_rows, feat, 1, 0, 0, stream);
 }
