@@ -455,6 +455,14 @@ int tsg_spmm_dot(const int32_t* rowptr, const int32_t* colidx, const float* val 
                  const float* bias /*nullable*/, float* Y, const float* dot_vec, float* dot_out,
                  int64_t num_rows, int64_t feat, int flags, void* stream);
 
+/* Score-side gate backward driven by perm (the other half of tsg_sag_conv_bwd_fused): dscore[perm[i]] =
+ * (dxo[i] . x[perm[i]]) * (1 - tanh(score)^2), zero for dropped nodes, and dbias_score = sum(dscore) (the score
+ * GCNConv's bias gradient).  dscore bit-identical to tsg_gate_gather_bwd; feat % 4 == 0. */
+size_t tsg_gate_score_bwd_workspace_bytes(void);
+int tsg_gate_score_bwd(const float* dxo, const float* x, const float* score, const int64_t* perm,
+                       int64_t num_perm, int64_t num_nodes, int64_t feat, float* dscore, float* dbias_score,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
 /* One level's conv-output backward, fused (used by tsg_sag_encoder_bwd when hidden % 4 == 0): with
  * dh = inv >= 0 ? dxo[inv] * tanh(score) : 0 (gate backward of Code/sag/layers.py:21, never materialised),
  * dhm = ReLU'(h) * (dh + dsw ws^T), dbias = colsum(dhm), dws = h^T dsw (score_layer.weight gradient).

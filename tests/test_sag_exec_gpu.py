@@ -29,8 +29,9 @@ def test_executor_matches_op_by_op(cuda, shape, G, nhid):
     tnn.USE_EXECUTOR = True
     assert torch.equal(res[True][0], res[False][0])
     for k in res[False][1]:
-        if k.endswith("score_layer.weight") and nhid % 4 == 0:
-            # the executor's fused level backward sums h^T dsw in its own fixed order (k_sag_conv_bwd_v4)
+        if (k.endswith("score_layer.weight") or k.endswith("score_layer.bias")) and nhid % 4 == 0:
+            # the executor's fused level backward sums h^T dsw (k_sag_conv_bwd_v4) and sum(dscore)
+            # (k_gate_score_bwd) in its own fixed order
             scale = float(res[False][1][k].abs().max()) + 1e-12
             assert float((res[True][1][k] - res[False][1][k]).abs().max()) <= 2e-5 * scale, k
         else:
@@ -113,6 +114,15 @@ def test_fused_level_backward_matches_the_kernel_sequence(cuda, N, F):
     dscore2 = torch.empty(N, device=cuda)
     call("tsg_gate_gather_bwd", ptr(dxo), ptr(h), ptr(score), ptr(inv), None, ptr(dscore2), N, F, stream_ptr())
     assert torch.equal(dscore, dscore2)                                  # dscore-only mode
+    # perm-driven score half: same dscore, plus its sum
+    wsg = torch.empty(lib.tsg_gate_score_bwd_workspace_bytes(), dtype=torch.uint8, device=cuda)
+    perm_d = perm.to(cuda)
+    for _ in range(2):
+        dscore3 = torch.full((N,), 7.0, device=cuda); dbs = torch.empty(1, device=cuda)
+        call("tsg_gate_score_bwd", ptr(dxo), ptr(h), ptr(score), ptr(perm_d), k, N, F, ptr(dscore3), ptr(dbs), ptr(wsg),
+             wsg.numel(), stream_ptr())
+        assert torch.equal(dscore, dscore3)
+        np.testing.assert_allclose(float(dbs), float(dscore.double().sum()), rtol=1e-5, atol=1e-4)
     dhm = torch.empty(N, F, device=cuda); db = torch.empty(F, device=cuda)
     call("tsg_relu_bwd_colsum_rank1", ptr(dh), ptr(h), ptr(dsw), ptr(wsv), ptr(dhm), ptr(db), N, F, ptr(ws), wsb, stream_ptr())
     outs = []

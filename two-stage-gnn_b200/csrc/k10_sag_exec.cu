@@ -51,6 +51,7 @@ static size_t scratch_need(const tsg_sag_shape* sh) {
     up(tsg_linear_bwd_weight_workspace_bytes(sh->hidden, 1));
   }
   up(tsg_embed_bwd_weight_workspace_bytes(sh->in_feat, sh->hidden));
+  up(tsg_gate_score_bwd_workspace_bytes());
   return align_up(m, 256) + 256;
 }
 
@@ -219,9 +220,13 @@ static int sag_bwd(const tsg_sag_shape* sh, const SagInput& in, const int64_t* l
                             TSG_READOUT_MAX | TSG_READOUT_MEAN | (l < 2 ? TSG_READOUT_ACCUM : 0), a.dxg, stream));
     // fused level backward (k_sag_conv_bwd_v4): dh is never materialised and h is read once for mask, dbias and dws
     const bool fused = H % 4 == 0 && H <= 512 && (((uintptr_t)ws) & 15) == 0 && !sag_unfused_env();
-    TSG_TRY(tsg_gate_gather_bwd(a.dxg, b.h, b.score, b.inv, fused ? nullptr : a.dh, a.dscore, n, H, stream));
-    // score layer: score = A_hat (h ws) + bs
-    TSG_TRY(tsg_relu_bwd_colsum(a.dscore, nullptr, nullptr, dbs, n, 1, a.scratch, a.scratch_bytes, stream));
+    // score layer: score = A_hat (h ws) + bs; dscore from the gate, its sum = dbs
+    if (fused) {
+      TSG_TRY(tsg_gate_score_bwd(a.dxg, b.h, b.score, b.perm, k, n, H, a.dscore, dbs, a.scratch, a.scratch_bytes, stream));
+    } else {
+      TSG_TRY(tsg_gate_gather_bwd(a.dxg, b.h, b.score, b.inv, a.dh, a.dscore, n, H, stream));
+      TSG_TRY(tsg_relu_bwd_colsum(a.dscore, nullptr, nullptr, dbs, n, 1, a.scratch, a.scratch_bytes, stream));
+    }
     TSG_TRY(tsg_spmm(b.t_rowptr, b.t_colidx, b.t_val, a.dscore, nullptr, a.dsw, n, 1, 0, stream));
     // conv layer: h = ReLU(A_hat (x W) + b); its incoming gradient is dh + dsw ws^T, added on the fly
     if (fused) {

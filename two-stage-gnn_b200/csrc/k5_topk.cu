@@ -266,6 +266,62 @@ k_gate_gather_bwd(const float* __restrict__ dxo, const float* __restrict__ x,
   }
 }
 
+// Score-side half of the gate backward, driven by perm instead of inv (K10 fused backward; the x-side half lives in
+// k_sag_conv_bwd_v4): for the i-th kept node j = perm[i]
+//     dscore[j] = (dxo[i, :] . x[j, :]) * (1 - tanh(score[j])^2)            layers.py:21 backward w.r.t. score
+// (dropped nodes keep the zero the caller memset), and the kernel also returns sum_j dscore[j] = the score layer's
+// bias gradient.  Same per-lane products and butterfly as k_gate_gather_bwd_v4, so dscore is bit-identical to it; every
+// lane group works on a kept row (the inv-driven kernel idled on the dropped half) and dxo is read sequentially.
+constexpr int GSB_THREADS = 256;
+constexpr int GSB_GRID = TSG_NUM_SMS * 4;
+
+template <int LPR>
+__global__ void __launch_bounds__(GSB_THREADS)
+k_gate_score_bwd(const float4* __restrict__ dxo, const float4* __restrict__ x, const float* __restrict__ score,
+                 const int64_t* __restrict__ perm, float* __restrict__ dscore, float* __restrict__ part,
+                 int64_t K, int F4, float* __restrict__ dbs, unsigned* ticket) {
+  constexpr int GROUPS = GSB_THREADS / LPR;
+  __shared__ float s_sum[GSB_THREADS / 32];
+  const int l = threadIdx.x % LPR, grp = threadIdx.x / LPR;
+  const int64_t per_cta = (K + gridDim.x - 1) / gridDim.x;
+  const int64_t i0 = (int64_t)blockIdx.x * per_cta;
+  const int64_t i1 = i0 + per_cta < K ? i0 + per_cta : K;
+  const int64_t iters = (per_cta + GROUPS - 1) / GROUPS;               // uniform trip count (shuffles below)
+  float local = 0.f;                                                    // this group's dscore sum (lane 0 holds it)
+  for (int64_t it = 0; it < iters; ++it) {
+    const int64_t i = i0 + it * GROUPS + grp;
+    const bool ok = i < i1;
+    const int64_t j = ok ? __ldg(perm + i) : 0;
+    float t = 0.f, dot = 0.f;
+    if (ok) t = tanhf(__ldg(score + j));
+    for (int f = l; f < F4; f += LPR) {
+      if (ok) {
+        const float4 go = __ldg(dxo + i * F4 + f);
+        const float4 xv = __ldg(x + j * F4 + f);
+        dot += go.x * xv.x + go.y * xv.y + go.z * xv.z + go.w * xv.w;
+      }
+    }
+#pragma unroll
+    for (int d = LPR / 2; d > 0; d >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, d, LPR);
+    if (ok && l == 0) {
+      const float ds = dot * (1.f - t * t);
+      dscore[j] = ds;
+      local += ds;
+    }
+  }
+  // block sum in a fixed order: lanes (butterfly over the warp; non-leader lanes hold 0), then warps in index order
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) local += __shfl_xor_sync(0xffffffffu, local, d);
+  if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tsum = s_sum[0];
+    for (int w = 1; w < GSB_THREADS / 32; ++w) tsum += s_sum[w];
+    part[blockIdx.x] = tsum;
+  }
+  partial_sum_tail(part, dbs, 1, nullptr, gridDim.x, 1, ticket);
+}
+
 }  // namespace tsg
 
 using namespace tsg;
@@ -376,4 +432,32 @@ extern "C" int tsg_gate_gather_bwd(const float* dxo, const float* x, const float
   }
 #undef TSG_GO
   return check_launch("gate_gather_bwd");
+}
+
+/* workspace: GSB_GRID floats */
+extern "C" size_t tsg_gate_score_bwd_workspace_bytes(void) { return ws_bytes((size_t)GSB_GRID, 4) + 256; }
+
+extern "C" int tsg_gate_score_bwd(const float* dxo, const float* x, const float* score, const int64_t* perm,
+                                  int64_t num_perm, int64_t num_nodes, int64_t F, float* dscore, float* dbias_score,
+                                  void* workspace, size_t workspace_bytes, void* stream) {
+  TSG_REQUIRE(num_perm > 0 && num_nodes > 0 && F > 0 && F % 4 == 0, "gate_score_bwd: bad shape");
+  TSG_REQUIRE(dxo && x && score && perm && dscore && dbias_score && workspace, "gate_score_bwd: null pointer");
+  TSG_REQUIRE(((((uintptr_t)dxo) | ((uintptr_t)x)) & 15) == 0, "gate_score_bwd: operands must be 16-byte aligned");
+  if (workspace_bytes < tsg_gate_score_bwd_workspace_bytes()) { set_error("gate_score_bwd: workspace too small"); return TSG_EWORKSPACE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned* ticket = ticket_next();
+  TSG_REQUIRE(ticket != nullptr, "gate_score_bwd: no ticket pool on this device");
+  cudaMemsetAsync(dscore, 0, (size_t)num_nodes * sizeof(float), st);      // dropped nodes
+  const int F4 = (int)(F / 4);
+  int lp = 1; while (lp < F4 && lp < 32) lp <<= 1;
+  int grid = (int)((num_perm + (GSB_THREADS / lp) - 1) / (GSB_THREADS / lp));
+  if (grid > GSB_GRID) grid = GSB_GRID;
+#define TSG_GS(L) k_gate_score_bwd<L><<<grid, GSB_THREADS, 0, st>>>((const float4*)dxo, (const float4*)x, score, perm, dscore, \
+                                                                    (float*)workspace, num_perm, F4, dbias_score, ticket)
+  switch (lp) {
+    case 1: TSG_GS(1); break; case 2: TSG_GS(2); break; case 4: TSG_GS(4); break;
+    case 8: TSG_GS(8); break; case 16: TSG_GS(16); break; default: TSG_GS(32); break;
+  }
+#undef TSG_GS
+  return check_launch("gate_score_bwd");
 }

@@ -79,6 +79,8 @@ _PROTOTYPES = {
     "tsg_sag_encoder_bwd": (I, [P, P, P, P, P, P, P, SZ, P]),
     "tsg_sag_encoder_fwd_compact": (I, [P, P, P, P, P, P, P, P, P, SZ, P]),
     "tsg_sag_encoder_bwd_compact": (I, [P, P, P, P, P, P, P, SZ, P]),
+    "tsg_gate_score_bwd_workspace_bytes": (SZ, []),
+    "tsg_gate_score_bwd": (I, [P, P, P, P, I64, I64, I64, P, P, P, SZ, P]),
     "tsg_spmm_dot": (I, [P, P, P, P, P, P, P, P, I64, I64, I, P]),
     "tsg_sag_conv_bwd_fused": (I, [P, P, P, P, P, P, P, P, P, I64, I64, P, SZ, P]),
     "tsg_embed_fwd": (I, [P, P, P, I64, I64, I64, P]),
