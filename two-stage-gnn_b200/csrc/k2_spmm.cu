@@ -712,6 +712,7 @@ k_relu_bwd_colsum_v4(const float4* __restrict__ dY, const float4* __restrict__ Y
 // Same per-element arithmetic as k_gate_gather_bwd_v4 followed by k_relu_bwd_colsum_v4 (dhm and dbias are
 // bit-identical to that sequence); dws replaces a separate pass over h (k_linear_bwd_weight_small) and is summed in
 // this kernel's fixed row order.  Saves, per level, one write + one read of dh and one read of h.
+template <int CB_ROWS>
 __global__ void __launch_bounds__(CS_THREADS)
 k_sag_conv_bwd_v4(const float4* __restrict__ dxo, const int* __restrict__ inv, const float* __restrict__ score,
                   const float4* __restrict__ Y, const float* __restrict__ dsw, const float4* __restrict__ ws4,
@@ -729,29 +730,45 @@ k_sag_conv_bwd_v4(const float4* __restrict__ dxo, const int* __restrict__ inv, c
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), acw = make_float4(0.f, 0.f, 0.f, 0.f);
     if (lane_r < rl && f < F4) {
       const float4 cv = ws4[f];
-      auto one = [&](int64_t r) {
-        const int m = __ldg(inv + r);
-        const float rs = __ldg(dsw + r);
-        const float4 y = Y[r * F4 + f];
-        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (m >= 0) {
-          const float t = tanhf(__ldg(score + r));
-          const float4 go = __ldg(dxo + (int64_t)m * F4 + f);
-          g = make_float4(go.x * t, go.y * t, go.z * t, go.w * t);
+      // CB_ROWS rows per thread in flight: all index / scale / h loads first, then the dependent score -> tanh and
+      // inv -> dxo gathers, then the arithmetic (rows are still accumulated in increasing order)
+      for (int64_t rb = r0 + lane_r; rb < r1; rb += (int64_t)CB_ROWS * rl) {
+        int m[CB_ROWS]; float rs[CB_ROWS], t[CB_ROWS]; float4 y[CB_ROWS], go[CB_ROWS];
+#pragma unroll
+        for (int u = 0; u < CB_ROWS; ++u) {
+          const int64_t r = rb + (int64_t)u * rl;
+          const bool ok = r < r1;
+          m[u] = ok ? __ldg(inv + r) : -2;
+          rs[u] = ok ? __ldg(dsw + r) : 0.f;
+          y[u] = ok ? Y[r * F4 + f] : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        g.x = __fadd_rn(g.x, __fmul_rn(rs, cv.x)); g.y = __fadd_rn(g.y, __fmul_rn(rs, cv.y));
-        g.z = __fadd_rn(g.z, __fmul_rn(rs, cv.z)); g.w = __fadd_rn(g.w, __fmul_rn(rs, cv.w));
-        if (!(y.x > 0.f)) g.x = 0.f;
-        if (!(y.y > 0.f)) g.y = 0.f;
-        if (!(y.z > 0.f)) g.z = 0.f;
-        if (!(y.w > 0.f)) g.w = 0.f;
-        dYm[r * F4 + f] = g;
-        acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
-        acw.x = fmaf(y.x, rs, acw.x); acw.y = fmaf(y.y, rs, acw.y); acw.z = fmaf(y.z, rs, acw.z); acw.w = fmaf(y.w, rs, acw.w);
-      };
-      int64_t r = r0 + lane_r;
-      for (; r + rl < r1; r += 2 * rl) { one(r); one(r + rl); }
-      if (r < r1) one(r);
+#pragma unroll
+        for (int u = 0; u < CB_ROWS; ++u) {
+          const int64_t r = rb + (int64_t)u * rl;
+          t[u] = 0.f; go[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (m[u] >= 0) { t[u] = __ldg(score + r); go[u] = __ldg(dxo + (int64_t)m[u] * F4 + f); }
+        }
+#pragma unroll
+        for (int u = 0; u < CB_ROWS; ++u) {
+          if (m[u] == -2) continue;
+          const int64_t r = rb + (int64_t)u * rl;
+          float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (m[u] >= 0) {
+            const float th = tanhf(t[u]);
+            g = make_float4(go[u].x * th, go[u].y * th, go[u].z * th, go[u].w * th);
+          }
+          g.x = __fadd_rn(g.x, __fmul_rn(rs[u], cv.x)); g.y = __fadd_rn(g.y, __fmul_rn(rs[u], cv.y));
+          g.z = __fadd_rn(g.z, __fmul_rn(rs[u], cv.z)); g.w = __fadd_rn(g.w, __fmul_rn(rs[u], cv.w));
+          if (!(y[u].x > 0.f)) g.x = 0.f;
+          if (!(y[u].y > 0.f)) g.y = 0.f;
+          if (!(y[u].z > 0.f)) g.z = 0.f;
+          if (!(y[u].w > 0.f)) g.w = 0.f;
+          __stcs(dYm + r * F4 + f, g);
+          acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
+          acw.x = fmaf(y[u].x, rs[u], acw.x); acw.y = fmaf(y[u].y, rs[u], acw.y);
+          acw.z = fmaf(y[u].z, rs[u], acw.z); acw.w = fmaf(y[u].w, rs[u], acw.w);
+        }
+      }
     }
     sm4[threadIdx.x] = acc;
     sm4[CS_THREADS + threadIdx.x] = acw;
@@ -910,9 +927,12 @@ extern "C" int tsg_sag_conv_bwd_fused(const float* dxo, const int32_t* inv, cons
   const int nb = colsum_blocks(N);
   int64_t rpb = (N + nb - 1) / nb; if (rpb < 1) rpb = 1;
   unsigned* ticket = fused_tail_ok(nb, 2 * F) ? ticket_next() : nullptr;
-  k_sag_conv_bwd_v4<<<nb, CS_THREADS, 2 * CS_THREADS * sizeof(float4), st>>>(
-      (const float4*)dxo, inv, score, (const float4*)h, dsw, (const float4*)ws_vec, (float4*)dhm, part, N, (int)(F / 4), rpb,
-      dbias, dws, ticket);
+  static const int cbr = env_int("TSG_CONV_BWD_ROWS", 2);      // measured at the level-0 shape: 1: 99 us, 2: 79, 4: 83, 8: 99
+#define TSG_CB(R) k_sag_conv_bwd_v4<R><<<nb, CS_THREADS, 2 * CS_THREADS * sizeof(float4), st>>>(                         \
+      (const float4*)dxo, inv, score, (const float4*)h, dsw, (const float4*)ws_vec, (float4*)dhm, part, N, (int)(F / 4), rpb, \
+      dbias, dws, ticket)
+  if (cbr == 1) TSG_CB(1); else if (cbr == 4) TSG_CB(4); else if (cbr == 8) TSG_CB(8); else TSG_CB(2);
+#undef TSG_CB
   if (!ticket) launch_partial_sum_final(part, dbias, (int)F, dws, nb, (int)(2 * F), st);
   return check_launch("sag_conv_bwd_fused");
 }

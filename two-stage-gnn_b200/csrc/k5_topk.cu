@@ -66,6 +66,9 @@ k_topk_rank(const float* __restrict__ score, const int64_t* __restrict__ gptr,
   }
 }
 
+// (Measured and dropped, profiles/r01c_step_kernels.md: one WARP per graph with the keys in registers -- shuffles for
+// strides < 32, register exchanges above, no barriers: 95 us instead of 69 for the 0.97 M-node level; 24 serial
+// warps per SM lose to 8-warp CTAs at the same compare-exchange count.)
 // Sorting variant for graphs that fit shared memory (n <= TOPK_SMEM_KEYS): bitonic sort of the composite keys in
 // DESCENDING order -- n log^2 n compare-exchanges instead of n^2 compares (10x fewer at n = 512; the rank kernel
 // took 135 us on the 0.97 M-node level).  Keys are distinct, so the network's output is THE total order the rank
@@ -274,6 +277,7 @@ k_gate_gather_bwd(const float* __restrict__ dxo, const float* __restrict__ x,
 // lane group works on a kept row (the inv-driven kernel idled on the dropped half) and dxo is read sequentially.
 constexpr int GSB_THREADS = 256;
 constexpr int GSB_GRID = TSG_NUM_SMS * 4;
+constexpr int GSB_ROWS = 4;
 
 template <int LPR>
 __global__ void __launch_bounds__(GSB_THREADS)
@@ -286,27 +290,41 @@ k_gate_score_bwd(const float4* __restrict__ dxo, const float4* __restrict__ x, c
   const int64_t per_cta = (K + gridDim.x - 1) / gridDim.x;
   const int64_t i0 = (int64_t)blockIdx.x * per_cta;
   const int64_t i1 = i0 + per_cta < K ? i0 + per_cta : K;
-  const int64_t iters = (per_cta + GROUPS - 1) / GROUPS;               // uniform trip count (shuffles below)
+  const int64_t iters = (per_cta + GROUPS * GSB_ROWS - 1) / (GROUPS * GSB_ROWS);      // uniform trip count (shuffles below)
   float local = 0.f;                                                    // this group's dscore sum (lane 0 holds it)
   for (int64_t it = 0; it < iters; ++it) {
-    const int64_t i = i0 + it * GROUPS + grp;
-    const bool ok = i < i1;
-    const int64_t j = ok ? __ldg(perm + i) : 0;
-    float t = 0.f, dot = 0.f;
-    if (ok) t = tanhf(__ldg(score + j));
-    for (int f = l; f < F4; f += LPR) {
-      if (ok) {
-        const float4 go = __ldg(dxo + i * F4 + f);
-        const float4 xv = __ldg(x + j * F4 + f);
-        dot += go.x * xv.x + go.y * xv.y + go.z * xv.z + go.w * xv.w;
+    // GSB_ROWS kept rows per lane group in flight: perm first, then the dependent score / x gathers
+    int64_t i[GSB_ROWS], j[GSB_ROWS];
+    bool ok[GSB_ROWS];
+    float t[GSB_ROWS], dot[GSB_ROWS];
+#pragma unroll
+    for (int u = 0; u < GSB_ROWS; ++u) {
+      i[u] = i0 + (it * GSB_ROWS + u) * GROUPS + grp;
+      ok[u] = i[u] < i1;
+      j[u] = ok[u] ? __ldg(perm + i[u]) : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < GSB_ROWS; ++u) {
+      t[u] = ok[u] ? __ldg(score + j[u]) : 0.f;
+      dot[u] = 0.f;
+      for (int f = l; f < F4; f += LPR) {
+        if (ok[u]) {
+          const float4 go = __ldg(dxo + i[u] * F4 + f);
+          const float4 xv = __ldg(x + j[u] * F4 + f);
+          dot[u] += go.x * xv.x + go.y * xv.y + go.z * xv.z + go.w * xv.w;
+        }
       }
     }
 #pragma unroll
-    for (int d = LPR / 2; d > 0; d >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, d, LPR);
-    if (ok && l == 0) {
-      const float ds = dot * (1.f - t * t);
-      dscore[j] = ds;
-      local += ds;
+    for (int u = 0; u < GSB_ROWS; ++u) {
+#pragma unroll
+      for (int d = LPR / 2; d > 0; d >>= 1) dot[u] += __shfl_xor_sync(0xffffffffu, dot[u], d, LPR);
+      if (ok[u] && l == 0) {
+        const float th = tanhf(t[u]);
+        const float ds = dot[u] * (1.f - th * th);
+        dscore[j[u]] = ds;
+        local += ds;
+      }
     }
   }
   // block sum in a fixed order: lanes (butterfly over the warp; non-leader lanes hold 0), then warps in index order
