@@ -274,13 +274,19 @@ def main():
         t = lambda v: (torch.from_numpy(v) if isinstance(v, np.ndarray) else v).to(dev)
         cbs = [ops.CompactBatch(t(c["label"]), t(c["row"]), t(c["col"]), t(c["node_ptr"]), t(c["edge_ptr"]),
                                 corpus.num_node_labels) for c in compact]
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
         for i in range(a.warmup + a.steps):
+            if i == a.warmup:
+                ev[0].record()
             b = dev_batches[i % 2]
             if a.profile_step == "compact":
                 trainer.step(cbs[i % 2], None, b["node_ptr"], b["triplets"])
             else:
                 trainer.step(b["x"], b["edge_index"], b["node_ptr"], b["triplets"])
+        ev[1].record()
         torch.cuda.synchronize()
+        print(f"[profile-step] {a.profile_step}: {ev[0].elapsed_time(ev[1]) / max(a.steps, 1):.4f} ms/step over {a.steps} steps",
+              file=sys.stderr)
         os.close(json_fd)
         return
 
@@ -449,7 +455,7 @@ def main():
                 "config": {"workload": workload_name(a), "graphs_per_step_per_gpu": graphs_per_step,
                            "nodes_per_step": N, "directed_edges_per_step": E,
                            "l2_policy": "inputs larger than L2 (x alone is %.0f MB), 2 alternating batches" % (N * corpus.num_node_labels * 4 / 1e6),
-                           "parallelism": f"dp{world}: shard by graph, all-gather embeddings, all-reduce grads"},
+                           "parallelism": f"dp{world}: shard by graph; one all-reduce per step carrying [T_r * grads, T_r * loss, T_r]"},
                 "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": ms_e2e / a.steps,
                         "h2d_bytes_per_step": int(h2d_compact), "d2h_bytes_per_step": 4,
                         "api": "TripletTrainer.run_from_host_compact: pinned host node labels[i32 N] + local edge lists"

@@ -455,6 +455,13 @@ int tsg_spmm_dot(const int32_t* rowptr, const int32_t* colidx, const float* val 
                  const float* bias /*nullable*/, float* Y, const float* dot_vec, float* dot_out,
                  int64_t num_rows, int64_t feat, int flags, void* stream);
 
+/* SAGPool gate + readout in one pass (used by tsg_sag_encoder_fwd when hidden % 4 == 0): xo[i] = x[perm[i]] *
+ * tanh(score[perm[i]]) (Code/sag/layers.py:21) and out[g] = [max || mean] over graph g's rows of xo
+ * (network.py:36,40,44), argmax as tsg_readout_fwd.  Bit-identical to tsg_gate_gather_fwd + tsg_readout_fwd. */
+int tsg_gate_readout_fwd(const float* x, const float* score, const int64_t* perm, const int64_t* graph_ptr_out,
+                         int64_t num_graphs, int64_t feat, float* xo, float* out, int64_t out_stride,
+                         int32_t* argmax, void* stream);
+
 /* Score-side gate backward driven by perm (the other half of tsg_sag_conv_bwd_fused): dscore[perm[i]] =
  * (dxo[i] . x[perm[i]]) * (1 - tanh(score)^2), zero for dropped nodes, and dbias_score = sum(dscore) (the score
  * GCNConv's bias gradient).  dscore bit-identical to tsg_gate_gather_bwd; feat % 4 == 0. */

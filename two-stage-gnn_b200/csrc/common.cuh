@@ -259,7 +259,7 @@ __device__ __forceinline__ void partial_sum_tail(const float* part, float* out0,
 
 static inline bool fused_tail_ok(int64_t nb, int64_t total) {
   static const bool off = getenv("TSG_NO_FUSED_TAIL") != nullptr;
-  return !off && nb * total <= 64 * 1024;
+  return !off && nb * total <= 128 * 1024;
 }
 
 unsigned* ticket_next();      // api.cu: a zeroed device counter from a per-device pool (nullptr if the pool cannot be made)

@@ -168,8 +168,13 @@ static int sag_fwd(const tsg_sag_shape* sh, const SagInput& in, const int64_t* l
     TSG_TRY(tsg_spmm(b.rowptr, b.colidx, b.val, b.sw, bs, b.score, n, 1, 0, stream));
     TSG_TRY(tsg_topk(b.score, ptr_l, ptr_n, G, n, b.perm, a.scratch, a.scratch_bytes, stream));
     TSG_TRY(tsg_inv_perm(b.perm, k, n, b.inv, stream));            // filter_adj's relabelling table (layers.py:23)
-    TSG_TRY(tsg_gate_gather_fwd(b.h, b.score, b.perm, nullptr, b.xg, nullptr, k, H, stream));
-    TSG_TRY(tsg_readout_fwd(b.xg, ptr_n, G, H, TSG_READOUT_MAX | TSG_READOUT_MEAN, b.out, 2 * H, b.argmax, stream));
+    static const bool no_gr = getenv("TSG_NO_GATE_READOUT") != nullptr;
+    if (H % 4 == 0 && !sag_unfused_env() && !no_gr) {       // gate + readout in one pass (the gated rows are not read back)
+      TSG_TRY(tsg_gate_readout_fwd(b.h, b.score, b.perm, ptr_n, G, H, b.xg, b.out, 2 * H, b.argmax, stream));
+    } else {
+      TSG_TRY(tsg_gate_gather_fwd(b.h, b.score, b.perm, nullptr, b.xg, nullptr, k, H, stream));
+      TSG_TRY(tsg_readout_fwd(b.xg, ptr_n, G, H, TSG_READOUT_MAX | TSG_READOUT_MEAN, b.out, 2 * H, b.argmax, stream));
+    }
     xin = b.xg;
   }
   const int64_t tot = G * 2 * H;

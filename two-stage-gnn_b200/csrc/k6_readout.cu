@@ -90,6 +90,87 @@ k_readout_fwd(const float* __restrict__ x, const int64_t* __restrict__ gptr, int
   }
 }
 
+// SAGPool gate + readout in one pass (K10 executor, F % 4 == 0): row i of graph g is
+//     xo[lo + i] = x[perm[lo + i]] * tanh(score[perm[lo + i]])                 layers.py:21
+// written once and reduced on the fly into [gmp || gap] (network.py:36,40,44) -- the gated rows are not read back.
+// Same reduction order as k_readout_fwd<4, LPR> (sub-group s takes rows s, s + RPW, ... in order, then the fixed
+// butterfly) and the same products as k_gate_gather_fwd<4>: out, argmax and xo are bit-identical to the two-kernel
+// sequence.  GRO_U row batches per sub-group are loaded before any is reduced (perm -> score / x is a dependent chain).
+constexpr int GRO_U = 4;
+
+template <int LPR>
+__global__ void __launch_bounds__(RO_THREADS)
+k_gate_readout_fwd(const float4* __restrict__ x, const float* __restrict__ score, const int64_t* __restrict__ perm,
+                   const int64_t* __restrict__ gptr, int G, int F4, float4* __restrict__ xo,
+                   float* __restrict__ out, int64_t out_stride, int* __restrict__ argmax) {
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR, l = lane % LPR;
+  const int F = F4 * 4;
+  const int warps_per_block = RO_THREADS / 32;
+  for (int g = blockIdx.x * warps_per_block + (threadIdx.x >> 5); g < G; g += gridDim.x * warps_per_block) {
+    const int64_t lo = gptr[g], hi = gptr[g + 1];
+    const int n = (int)(hi - lo);
+    for (int fb = 0; fb < F4; fb += LPR) {           // warp-uniform trip count
+      const int f = fb + l;
+      const bool fok = f < F4;
+      float mx[4], sm[4]; int am[4];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) { mx[v] = -FLT_MAX; sm[v] = 0.f; am[v] = -1; }
+      if (fok) {
+        for (int ib = sub; ib < n; ib += RPW * GRO_U) {
+          int64_t j[GRO_U]; float t[GRO_U]; float4 xv[GRO_U];
+#pragma unroll
+          for (int u = 0; u < GRO_U; ++u) {
+            const int i = ib + u * RPW;
+            j[u] = i < n ? __ldg(perm + lo + i) : -1;
+          }
+#pragma unroll
+          for (int u = 0; u < GRO_U; ++u) {
+            t[u] = 0.f; xv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j[u] >= 0) { t[u] = __ldg(score + j[u]); xv[u] = __ldg(x + j[u] * F4 + f); }
+          }
+#pragma unroll
+          for (int u = 0; u < GRO_U; ++u) {
+            if (j[u] < 0) continue;
+            const int i = ib + u * RPW;
+            const float th = tanhf(t[u]);
+            float4 w = xv[u];
+            w.x *= th; w.y *= th; w.z *= th; w.w *= th;
+            xo[(lo + i) * F4 + f] = w;
+            const float vals[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              sm[v] += vals[v];
+              if (vals[v] > mx[v] || am[v] < 0) { mx[v] = vals[v]; am[v] = i; }
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int d = LPR; d < 32; d <<= 1) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          float omx = __shfl_xor_sync(0xffffffffu, mx[v], d);
+          int oam = __shfl_xor_sync(0xffffffffu, am[v], d);
+          float osm = __shfl_xor_sync(0xffffffffu, sm[v], d);
+          sm[v] = (sub & (d / LPR)) ? osm + sm[v] : sm[v] + osm;
+          bool take = oam >= 0 && (am[v] < 0 || omx > mx[v] || (omx == mx[v] && oam < am[v]));
+          if (take) { mx[v] = omx; am[v] = oam; }
+        }
+      }
+      if (fok && sub == 0) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          out[(int64_t)g * out_stride + f * 4 + v] = am[v] >= 0 ? mx[v] : 0.f;
+          argmax[(int64_t)g * F + f * 4 + v] = am[v] >= 0 ? (int)(lo + am[v]) : -1;
+          out[(int64_t)g * out_stride + F + f * 4 + v] = sm[v] / (float)(n > 0 ? n : 1);
+        }
+      }
+    }
+  }
+}
+
 template <int VEC, int LPR>
 __global__ void __launch_bounds__(RO_BWD_THREADS)
 k_readout_bwd(const float* __restrict__ dout, int64_t dstride, const int* __restrict__ argmax,
@@ -199,4 +280,24 @@ extern "C" int tsg_readout_bwd(const float* dout, int64_t dout_stride, const int
   bool vec = F % 4 == 0 && (((uintptr_t)dx) & 15) == 0;
   if (vec) return launch_bwd<4>(pick_lpr(F / 4), grid, st, dout, dout_stride, argmax, gptr, (int)G, (int)F, mode, dx);
   return launch_bwd<1>(pick_lpr(F), grid, st, dout, dout_stride, argmax, gptr, (int)G, (int)F, mode, dx);
+}
+
+/* gate (x[perm] * tanh(score[perm])) + [max || mean] readout in one pass; see k_gate_readout_fwd.  feat % 4 == 0. */
+extern "C" int tsg_gate_readout_fwd(const float* x, const float* score, const int64_t* perm, const int64_t* gptr,
+                                    int64_t G, int64_t F, float* xo, float* out, int64_t out_stride, int32_t* argmax,
+                                    void* stream) {
+  TSG_REQUIRE(G >= 0 && F > 0 && F % 4 == 0 && G < (int64_t)0x7fffffff, "gate_readout_fwd: bad shape");
+  if (G == 0) return TSG_OK;
+  TSG_REQUIRE(x && score && perm && gptr && xo && out && argmax, "gate_readout_fwd: null pointer");
+  TSG_REQUIRE(((((uintptr_t)x) | ((uintptr_t)xo)) & 15) == 0, "gate_readout_fwd: operands must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = grid_for(G, RO_THREADS / 32);
+  const int F4 = (int)(F / 4);
+#define TSG_GR(L) k_gate_readout_fwd<L><<<grid, RO_THREADS, 0, st>>>((const float4*)x, score, perm, gptr, (int)G, F4, (float4*)xo, out, out_stride, argmax)
+  switch (pick_lpr(F4)) {
+    case 1: TSG_GR(1); break; case 2: TSG_GR(2); break; case 4: TSG_GR(4); break;
+    case 8: TSG_GR(8); break; case 16: TSG_GR(16); break; default: TSG_GR(32); break;
+  }
+#undef TSG_GR
+  return check_launch("gate_readout_fwd");
 }

@@ -3,9 +3,10 @@
 Mirrors the loop of Code/sag/train_triplet.py:198-214 (TNet forward -> MarginRankingLoss ->
 backward -> Adam step) with two differences that are the point of this framework: the step runs
 ONE packed forward over all 3T graphs of T triplets instead of 3 single-graph forwards per
-triplet, and it is data-parallel: every rank embeds its own graphs, embeddings are all-gathered
-(NCCL) so the triplet loss sees the global batch, parameter gradients are all-reduced in one flat
-bucket.  Graphs are independent, so there is no other exchange step.
+triplet, and it is data-parallel: every rank embeds its own graphs and evaluates its own triplets; ONE
+all-reduce (NCCL) per step of the flat bucket [T_r * gradients, T_r * loss, T_r] yields the global-batch mean
+loss and its gradient on every rank.  Graphs are independent, so there is no other exchange step
+(`all_gather_rows` stays for triplets that reference graphs of other ranks).
 """
 from __future__ import annotations
 
@@ -58,6 +59,27 @@ def all_reduce_grads(params, group=None) -> None:
     torch._foreach_copy_(grads, views)          # one multi-tensor kernel instead of one copy per parameter
 
 
+def all_reduce_grads_and_loss(params, loss_local: torch.Tensor, num_local: int, group=None) -> torch.Tensor:
+    """The step's ONE collective when every rank's triplets index its own graphs.  `loss_local` is the MEAN hinge over
+    this rank's `num_local` triplets and the parameters hold its gradient; the global batch's mean loss is
+    sum_r(T_r * loss_r) / sum_r(T_r) and its gradient the same combination of the per-rank gradients, so one
+    all-reduce(SUM) of [T_r * grads..., T_r * loss_r, T_r] carries everything -- no embedding all-gather, no triplet
+    all-gather, nothing to wait for before the backward pass.  Returns the global mean loss (on the device)."""
+    grads = [p.grad for p in params if p.grad is not None]
+    tail = torch.stack([loss_local.detach().reshape(()), torch.ones((), dtype=loss_local.dtype, device=loss_local.device)])
+    flat = torch.cat([g.reshape(-1) for g in grads] + [tail])
+    flat.mul_(float(num_local))
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    flat.div_(flat[-1].clone())
+    views, off = [], 0
+    for g in grads:
+        n = g.numel()
+        views.append(flat[off:off + n].view_as(g)); off += n
+    if grads:
+        torch._foreach_copy_(grads, views)
+    return flat[-2]
+
+
 class TripletTrainer:
     """model: tsg.nn.PackedSAGNet (or any module with the same forward signature)."""
 
@@ -73,24 +95,19 @@ class TripletTrainer:
 
     def step(self, x: torch.Tensor, edge_index: torch.Tensor, node_ptr_host: np.ndarray,
              triplets: torch.Tensor) -> torch.Tensor:
-        """x/edge_index/triplets on the device.  `triplets` [T,3] index rows of THIS rank's
-        embedding matrix; with world > 1 they are offset into the gathered matrix and every rank's
-        triplets are gathered too, so the loss is the mean over the global batch."""
+        """x/edge_index/triplets on the device.  `triplets` [T,3] index rows of THIS rank's embedding matrix; with
+        world > 1 the returned loss is the mean over the GLOBAL batch and the parameters receive its gradient."""
         self.model.train()
         emb = self.model(x, edge_index, node_ptr_host)
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
-        if world > 1:
-            rank = dist.get_rank(self.group)
-            emb_all = all_gather_rows(emb, self.group)
-            trip_local = (triplets + rank * emb.size(0)).contiguous()
-            trip_all = torch.empty(world * triplets.size(0), 3, dtype=triplets.dtype, device=triplets.device)
-            dist.all_gather_into_tensor(trip_all, trip_local, group=self.group)
-        else:
-            emb_all, trip_all = emb, triplets
-        loss, _, _ = ops.triplet_loss(emb_all, trip_all, self.margin)
+        loss, _, _ = ops.triplet_loss(emb, triplets, self.margin)         # mean over THIS rank's triplets
         self.opt.zero_grad(set_to_none=True)
         loss.backward()
-        all_reduce_grads(list(self.model.parameters()), self.group)
+        if world > 1:
+            # triplets are rank-local by contract, so the global-batch loss and gradient are the T_r-weighted means of
+            # the per-rank ones: one all-reduce per step (the all-gather formulation, kept as all_gather_rows for
+            # triplets that cross ranks, cost two more collectives and a synchronisation before the backward pass)
+            loss = all_reduce_grads_and_loss(list(self.model.parameters()), loss, int(triplets.size(0)), self.group)
         self.opt.step()
         return loss.detach()
 
