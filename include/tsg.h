@@ -470,6 +470,14 @@ int tsg_gate_score_bwd(const float* dxo, const float* x, const float* score, con
                        int64_t num_perm, int64_t num_nodes, int64_t feat, float* dscore, float* dbias_score,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* conv1 on one-hot node-label features: Y = act(A_hat * W[label] + bias) with the table gathered inside K2 (x W is
+ * never materialised), plus the optional Y @ dot_vec epilogue of tsg_spmm_dot.  Bit-identical to tsg_embed_fwd followed
+ * by tsg_spmm_dot.  feat % 4 == 0 (<= 128 with dot_vec), 16-byte aligned W / bias / Y; TSG_EINVAL otherwise. */
+int tsg_spmm_label_dot(const int32_t* rowptr, const int32_t* colidx, const float* val /*nullable*/, const float* W,
+                       const int32_t* label, int64_t num_labels, const float* bias /*nullable*/, float* Y,
+                       const float* dot_vec /*nullable*/, float* dot_out /*nullable*/, int64_t num_rows, int64_t feat,
+                       int flags, void* stream);
+
 /* One level's conv-output backward, fused (used by tsg_sag_encoder_bwd when hidden % 4 == 0): with
  * dh = inv >= 0 ? dxo[inv] * tanh(score) : 0 (gate backward of Code/sag/layers.py:21, never materialised),
  * dhm = ReLU'(h) * (dh + dsw ws^T), dbias = colsum(dhm), dws = h^T dsw (score_layer.weight gradient).

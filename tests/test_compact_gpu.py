@@ -168,3 +168,32 @@ def test_resident_corpus_compact_gather(cuda):
     dense = DeviceCorpus(c, cuda, dense_x=np.random.default_rng(0).random((int(c.node_ptr[-1]), 5), dtype=np.float32))
     with pytest.raises(RuntimeError):
         dense.pack_compact(ids)
+
+
+@pytest.mark.parametrize("F,with_dot", [(32, True), (16, True), (128, True), (64, False)])
+def test_label_table_spmm_is_embed_then_spmm(cuda, F, with_dot):
+    """tsg_spmm_label_dot (W[label] gathered inside K2) == tsg_embed_fwd -> tsg_spmm_dot, bit for bit, in both launch
+    shapes; labels outside the table contribute the zero row."""
+    from tsg import ops
+    from tsg._lib import call, ptr, stream_ptr
+    c = synth.make_corpus("DD", 700, seed=4)
+    b = synth.pack(c)
+    n = int(c.node_ptr[-1]); K = c.num_node_labels
+    csr = ops.build_csr(ops.EdgeList.from_edge_index(torch.from_numpy(b["edge_index"]).to(cuda)), n)
+    g = torch.Generator().manual_seed(F)
+    label = torch.from_numpy(c.node_label.astype(np.int32)).clone()
+    label[5], label[77], label[n - 1] = -1, K, K + 9
+    label = label.to(cuda)
+    W = torch.randn(K, F, generator=g).to(cuda); bias = torch.randn(F, generator=g).to(cuda)
+    w = torch.randn(F, 1, generator=g).to(cuda)
+    xw = ops.embed_fwd(W, label)
+    for rows in (n, 300):
+        Y0 = torch.empty(rows, F, device=cuda); d0 = torch.empty(rows, device=cuda)
+        call("tsg_spmm_dot", ptr(csr.rowptr), ptr(csr.colidx), ptr(csr.val), ptr(xw), ptr(bias), ptr(Y0), ptr(w), ptr(d0),
+             rows, F, ops.SPMM_RELU, stream_ptr())
+        Y1 = torch.empty(rows, F, device=cuda); d1 = torch.empty(rows, device=cuda)
+        call("tsg_spmm_label_dot", ptr(csr.rowptr), ptr(csr.colidx), ptr(csr.val), ptr(W), ptr(label), K, ptr(bias), ptr(Y1),
+             ptr(w) if with_dot else None, ptr(d1) if with_dot else None, rows, F, ops.SPMM_RELU, stream_ptr())
+        assert torch.equal(Y0, Y1)
+        if with_dot:
+            assert torch.equal(d0, d1)

@@ -161,10 +161,18 @@ static int sag_fwd(const tsg_sag_shape* sh, const SagInput& in, const int64_t* l
       TSG_TRY(tsg_csr_filter(pb.rowptr, pb.colidx, pb.t_rowptr, pb.t_colidx, pb.perm, pb.inv, n, b.rowptr, b.colidx, b.val,
                              b.t_rowptr, b.t_colidx, b.t_val, a.scratch, a.scratch_bytes, stream));
     }
-    if (l == 0 && in.label) TSG_TRY(tsg_embed_fwd(W, in.label, b.xw, n, fin, H, stream));     // onehot(label) @ W
-    else TSG_TRY(tsg_linear_fwd(xin, W, nullptr, b.xw, n, fin, H, 0, 0, stream));
-    // h = ReLU(A_hat xw + b) and, from the same registers, sw = h ws (the score layer's product)
-    TSG_TRY(tsg_spmm_dot(b.rowptr, b.colidx, b.val, b.xw, bias, b.h, ws, b.sw, n, H, TSG_SPMM_RELU, stream));
+    static const bool no_label_spmm = getenv("TSG_NO_LABEL_SPMM") != nullptr;
+    const bool label_spmm = l == 0 && in.label && H % 4 == 0 && H <= 128 && !no_label_spmm &&
+                            ((((uintptr_t)W) | ((uintptr_t)bias) | ((uintptr_t)ws)) & 15) == 0;
+    if (label_spmm) {
+      // conv1 on one-hot labels: x W = W[label] is gathered from the 11 KB table inside K2, never written
+      TSG_TRY(tsg_spmm_label_dot(b.rowptr, b.colidx, b.val, W, in.label, fin, bias, b.h, ws, b.sw, n, H, TSG_SPMM_RELU, stream));
+    } else {
+      if (l == 0 && in.label) TSG_TRY(tsg_embed_fwd(W, in.label, b.xw, n, fin, H, stream));     // onehot(label) @ W
+      else TSG_TRY(tsg_linear_fwd(xin, W, nullptr, b.xw, n, fin, H, 0, 0, stream));
+      // h = ReLU(A_hat xw + b) and, from the same registers, sw = h ws (the score layer's product)
+      TSG_TRY(tsg_spmm_dot(b.rowptr, b.colidx, b.val, b.xw, bias, b.h, ws, b.sw, n, H, TSG_SPMM_RELU, stream));
+    }
     TSG_TRY(tsg_spmm(b.rowptr, b.colidx, b.val, b.sw, bs, b.score, n, 1, 0, stream));
     TSG_TRY(tsg_topk(b.score, ptr_l, ptr_n, G, n, b.perm, a.scratch, a.scratch_bytes, stream));
     TSG_TRY(tsg_inv_perm(b.perm, k, n, b.inv, stream));            // filter_adj's relabelling table (layers.py:23)

@@ -275,7 +275,10 @@ k_spmm_g(const int* __restrict__ rowptr, const int* __restrict__ colidx,
          const float* __restrict__ val, const float4* __restrict__ H,
          const float4* __restrict__ bias, float4* __restrict__ Y,
          int num_rows, int F4, int relu, int hdist,
-         const float4* __restrict__ dot_vec, float* __restrict__ dot_out) {
+         const float4* __restrict__ dot_vec, float* __restrict__ dot_out,
+         const int* __restrict__ row_label = nullptr, int num_labels = 0) {
+  // row_label != nullptr: H is a [num_labels, F] TABLE and neighbour c contributes H[row_label[c]] -- conv1 on one-hot
+  // node-label features (x W = W[label]) without ever materialising x W: the gathers hit an L1-resident table.
   constexpr int RPI = THREADS / LPR;              // rows per CTA iteration
   const int l = threadIdx.x % LPR;
   const int rpc = (num_rows + gridDim.x - 1) / gridDim.x;
@@ -289,8 +292,9 @@ k_spmm_g(const int* __restrict__ rowptr, const int* __restrict__ colidx,
     const int epi = (int)(((long long)(p_e - p_b) * RPI) / (r_end - r_begin)) + 1;
     s_pf[0] = epi; s_pf[1] = nnz_end;
     // head of this CTA's H window and CSR slice
-    bulk_prefetch_l2(reinterpret_cast<const char*>(H) + (size_t)r_begin * row_bytes,
-                     (size_t)min(hdist, num_rows - r_begin) * row_bytes);
+    if (row_label == nullptr)
+      bulk_prefetch_l2(reinterpret_cast<const char*>(H) + (size_t)r_begin * row_bytes,
+                       (size_t)min(hdist, num_rows - r_begin) * row_bytes);
     const size_t n0 = (size_t)min(2 * epi, nnz_end - p_b) * 4;
     bulk_prefetch_l2(colidx + p_b, n0);
     if (HAS_VAL) bulk_prefetch_l2(val + p_b, n0);
@@ -299,7 +303,7 @@ k_spmm_g(const int* __restrict__ rowptr, const int* __restrict__ colidx,
     const int s = __ldg(rowptr + r), t = __ldg(rowptr + r + 1);
     if (hdist > 0 && threadIdx.x == 0) {
       const int hr = r + hdist;                                       // H rows [hr, hr + RPI)
-      if (hr < num_rows)
+      if (hr < num_rows && row_label == nullptr)
         bulk_prefetch_l2(reinterpret_cast<const char*>(H) + (size_t)hr * row_bytes,
                          (size_t)min(RPI, num_rows - hr) * row_bytes);
       const int epi = s_pf[0], nnz_end = s_pf[1];
@@ -322,10 +326,18 @@ k_spmm_g(const int* __restrict__ rowptr, const int* __restrict__ colidx,
              acc.z = __fadd_rn(acc.z, __fmul_rn(v, h.z)); acc.w = __fadd_rn(acc.w, __fmul_rn(v, h.w)); }
       int p = s;
       for (; p + 4 <= t; p += 4) {
-        const int c0 = __ldg(colidx + p), c1 = __ldg(colidx + p + 1);
-        const int c2 = __ldg(colidx + p + 2), c3 = __ldg(colidx + p + 3);
+        int c0 = __ldg(colidx + p), c1 = __ldg(colidx + p + 1);
+        int c2 = __ldg(colidx + p + 2), c3 = __ldg(colidx + p + 3);
         float v0 = 1.f, v1 = 1.f, v2 = 1.f, v3 = 1.f;
         if (HAS_VAL) { v0 = __ldg(val + p); v1 = __ldg(val + p + 1); v2 = __ldg(val + p + 2); v3 = __ldg(val + p + 3); }
+        if (row_label != nullptr) {
+          c0 = __ldg(row_label + c0); c1 = __ldg(row_label + c1); c2 = __ldg(row_label + c2); c3 = __ldg(row_label + c3);
+          // a label outside the table is the all-zero one-hot row: contributes nothing
+          if ((unsigned)c0 >= (unsigned)num_labels) { c0 = 0; v0 = 0.f; }
+          if ((unsigned)c1 >= (unsigned)num_labels) { c1 = 0; v1 = 0.f; }
+          if ((unsigned)c2 >= (unsigned)num_labels) { c2 = 0; v2 = 0.f; }
+          if ((unsigned)c3 >= (unsigned)num_labels) { c3 = 0; v3 = 0.f; }
+        }
         const float4 h0 = TSG_LD(c0), h1 = TSG_LD(c1), h2 = TSG_LD(c2), h3 = TSG_LD(c3);
         TSG_ACC(h0, v0) TSG_ACC(h1, v1) TSG_ACC(h2, v2) TSG_ACC(h3, v3)
       }
@@ -336,6 +348,12 @@ k_spmm_g(const int* __restrict__ rowptr, const int* __restrict__ colidx,
         if (HAS_VAL) v0 = __ldg(val + p);
         if (rem > 1) { c1 = __ldg(colidx + p + 1); if (HAS_VAL) v1 = __ldg(val + p + 1); }
         if (rem > 2) { c2 = __ldg(colidx + p + 2); if (HAS_VAL) v2 = __ldg(val + p + 2); }
+        if (row_label != nullptr) {
+          c0 = __ldg(row_label + c0);
+          if ((unsigned)c0 >= (unsigned)num_labels) { c0 = 0; v0 = 0.f; }
+          if (rem > 1) { c1 = __ldg(row_label + c1); if ((unsigned)c1 >= (unsigned)num_labels) { c1 = 0; v1 = 0.f; } }
+          if (rem > 2) { c2 = __ldg(row_label + c2); if ((unsigned)c2 >= (unsigned)num_labels) { c2 = 0; v2 = 0.f; } }
+        }
         const float4 h0 = TSG_LD(c0);
         float4 h1 = h0, h2 = h0;
         if (rem > 1) h1 = TSG_LD(c1);
@@ -548,7 +566,8 @@ static int env_int(const char* name, int dflt) {
 template <bool HAS_VAL>
 static int launch_spmm(const int* rowptr, const int* colidx, const float* val, const float* H,
                        const float* bias, float* Y, int64_t N, int64_t F, int relu, bool exact, cudaStream_t st,
-                       const float* dot_vec = nullptr, float* dot_out = nullptr, bool* dot_done = nullptr) {
+                       const float* dot_vec = nullptr, float* dot_out = nullptr, bool* dot_done = nullptr,
+                       const int* row_label = nullptr, int num_labels = 0) {
   if (dot_done) *dot_done = false;
   bool vec = (F % 4 == 0) && (((uintptr_t)H & 15) == 0) && (((uintptr_t)Y & 15) == 0) &&
              (bias == nullptr || ((uintptr_t)bias & 15) == 0);
@@ -559,7 +578,7 @@ static int launch_spmm(const int* rowptr, const int* colidx, const float* val, c
     static const bool legacy = env_int("TSG_SPMM_LEGACY", 0) != 0;
     static const int hdist = env_int("TSG_SPMM_HDIST", 128);
     static const int ctas_per_sm_1024 = env_int("TSG_SPMM_CTAS", 2);
-    if (legacy) {
+    if (legacy && row_label == nullptr) {
       int grid = grid_for(N, SPMM_THREADS / lpr, 32);
 #define TSG_GO(L) k_spmm_vec4<L, HAS_VAL><<<grid, SPMM_THREADS, 0, st>>>(rowptr, colidx, val, (const float4*)H, (const float4*)bias, (float4*)Y, (int)N, F4, relu)
       switch (lpr) {
@@ -581,7 +600,7 @@ static int launch_spmm(const int* rowptr, const int* colidx, const float* val, c
       const bool fuse_dot = dot_vec && dot_out && F4 <= lpr && (((uintptr_t)dot_vec) & 15) == 0;
       const float4* dv = fuse_dot ? (const float4*)dot_vec : nullptr;
       if (dot_done) *dot_done = fuse_dot;
-#define TSG_G(L, FM, T) k_spmm_g<L, HAS_VAL, FM, T><<<g, T, 0, st>>>(rowptr, colidx, val, (const float4*)H, (const float4*)bias, (float4*)Y, (int)N, F4, relu, big ? hdist : 0, dv, dot_out)
+#define TSG_G(L, FM, T) k_spmm_g<L, HAS_VAL, FM, T><<<g, T, 0, st>>>(rowptr, colidx, val, (const float4*)H, (const float4*)bias, (float4*)Y, (int)N, F4, relu, big ? hdist : 0, dv, dot_out, row_label, num_labels)
 #define TSG_GT(L, FM) if (big) TSG_G(L, FM, 1024); else TSG_G(L, FM, 256);
 #define TSG_GV(L) if (exact) { TSG_GT(L, false) } else { TSG_GT(L, true) }
       switch (lpr) {
@@ -958,4 +977,28 @@ extern "C" int tsg_spmm_dot(const int32_t* rowptr, const int32_t* colidx, const 
                : launch_spmm<false>(rowptr, colidx, val, H, bias, Y, num_rows, feat, relu, exact, st, off ? nullptr : dot_vec, dot_out, &done);
   if (rc != TSG_OK || done) return rc;
   return tsg_linear_fwd(Y, dot_vec, nullptr, dot_out, num_rows, feat, 1, 0, 0, stream);
+}
+
+/* conv1 on one-hot node-label features without x W: Y = act(A_hat * W[label] + bias), and optionally the score
+ * layer's Y @ dot_vec from the same epilogue (dot_vec / dot_out may both be null).  Bit-identical to tsg_embed_fwd ->
+ * tsg_spmm_dot.  Needs the float4 path (feat % 4 == 0, 16-byte aligned W / Y / bias); returns TSG_EINVAL otherwise and
+ * the caller runs the two-call sequence. */
+extern "C" int tsg_spmm_label_dot(const int32_t* rowptr, const int32_t* colidx, const float* val, const float* W,
+                                  const int32_t* label, int64_t num_labels, const float* bias, float* Y,
+                                  const float* dot_vec, float* dot_out, int64_t num_rows, int64_t feat, int flags,
+                                  void* stream) {
+  TSG_REQUIRE(num_rows > 0 && feat > 0 && num_labels > 0 && num_rows < (int64_t)0x7fffffff && num_labels < (int64_t)0x7fffffff,
+              "spmm_label_dot: bad shape");
+  TSG_REQUIRE(rowptr && colidx && W && label && Y && ((dot_vec == nullptr) == (dot_out == nullptr)), "spmm_label_dot: null pointer");
+  const bool vec = (feat % 4 == 0) && (((uintptr_t)W & 15) == 0) && (((uintptr_t)Y & 15) == 0) &&
+                   (bias == nullptr || ((uintptr_t)bias & 15) == 0) && (dot_vec == nullptr || (((uintptr_t)dot_vec & 15) == 0 && feat <= 128));
+  TSG_REQUIRE(vec, "spmm_label_dot: needs feat %% 4 == 0 (<= 128 with dot_vec) and 16-byte aligned operands");
+  const int relu = (flags & TSG_SPMM_RELU) ? 1 : 0;
+  const bool exact = (flags & TSG_SPMM_EXACT) != 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  bool done = false;
+  int rc = val ? launch_spmm<true>(rowptr, colidx, val, W, bias, Y, num_rows, feat, relu, exact, st, dot_vec, dot_out, &done, label, (int)num_labels)
+               : launch_spmm<false>(rowptr, colidx, val, W, bias, Y, num_rows, feat, relu, exact, st, dot_vec, dot_out, &done, label, (int)num_labels);
+  if (rc == TSG_OK && dot_vec && !done) { set_error("spmm_label_dot: dot epilogue not taken"); return TSG_EINVAL; }
+  return rc;
 }
