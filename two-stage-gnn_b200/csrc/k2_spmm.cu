@@ -269,7 +269,9 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void* p, size_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(a), "r"((unsigned)(e - a)) : "memory");
 }
 
-template <int LPR, bool HAS_VAL, bool FMA, int THREADS>
+// MODE bit 0: y . dot_vec epilogue; bit 1: H is a table indexed by row_label (compile-time: the plain kernel runs at its
+// 32-register budget and the extra operands cost it 10 % when they were run-time branches)
+template <int LPR, bool HAS_VAL, bool FMA, int THREADS, int MODE>
 __global__ void __launch_bounds__(THREADS, 2048 / THREADS)
 k_spmm_g(const int* __restrict__ rowptr, const int* __restrict__ colidx,
          const float* __restrict__ val, const float4* __restrict__ H,
@@ -277,7 +279,7 @@ k_spmm_g(const int* __restrict__ rowptr, const int* __restrict__ colidx,
          int num_rows, int F4, int relu, int hdist,
          const float4* __restrict__ dot_vec, float* __restrict__ dot_out,
          const int* __restrict__ row_label = nullptr, int num_labels = 0) {
-  // row_label != nullptr: H is a [num_labels, F] TABLE and neighbour c contributes H[row_label[c]] -- conv1 on one-hot
+  // (MODE & 2): H is a [num_labels, F] TABLE and neighbour c contributes H[row_label[c]] -- conv1 on one-hot
   // node-label features (x W = W[label]) without ever materialising x W: the gathers hit an L1-resident table.
   constexpr int RPI = THREADS / LPR;              // rows per CTA iteration
   const int l = threadIdx.x % LPR;
@@ -292,7 +294,7 @@ k_spmm_g(const int* __restrict__ rowptr, const int* __restrict__ colidx,
     const int epi = (int)(((long long)(p_e - p_b) * RPI) / (r_end - r_begin)) + 1;
     s_pf[0] = epi; s_pf[1] = nnz_end;
     // head of this CTA's H window and CSR slice
-    if (row_label == nullptr)
+    if (!(MODE & 2))
       bulk_prefetch_l2(reinterpret_cast<const char*>(H) + (size_t)r_begin * row_bytes,
                        (size_t)min(hdist, num_rows - r_begin) * row_bytes);
     const size_t n0 = (size_t)min(2 * epi, nnz_end - p_b) * 4;
@@ -303,7 +305,7 @@ k_spmm_g(const int* __restrict__ rowptr, const int* __restrict__ colidx,
     const int s = __ldg(rowptr + r), t = __ldg(rowptr + r + 1);
     if (hdist > 0 && threadIdx.x == 0) {
       const int hr = r + hdist;                                       // H rows [hr, hr + RPI)
-      if (hr < num_rows && row_label == nullptr)
+      if (hr < num_rows && !(MODE & 2))
         bulk_prefetch_l2(reinterpret_cast<const char*>(H) + (size_t)hr * row_bytes,
                          (size_t)min(RPI, num_rows - hr) * row_bytes);
       const int epi = s_pf[0], nnz_end = s_pf[1];
@@ -330,7 +332,7 @@ k_spmm_g(const int* __restrict__ rowptr, const int* __restrict__ colidx,
         int c2 = __ldg(colidx + p + 2), c3 = __ldg(colidx + p + 3);
         float v0 = 1.f, v1 = 1.f, v2 = 1.f, v3 = 1.f;
         if (HAS_VAL) { v0 = __ldg(val + p); v1 = __ldg(val + p + 1); v2 = __ldg(val + p + 2); v3 = __ldg(val + p + 3); }
-        if (row_label != nullptr) {
+        if ((MODE & 2)) {
           c0 = __ldg(row_label + c0); c1 = __ldg(row_label + c1); c2 = __ldg(row_label + c2); c3 = __ldg(row_label + c3);
           // a label outside the table is the all-zero one-hot row: contributes nothing
           if ((unsigned)c0 >= (unsigned)num_labels) { c0 = 0; v0 = 0.f; }
@@ -348,7 +350,7 @@ k_spmm_g(const int* __restrict__ rowptr, const int* __restrict__ colidx,
         if (HAS_VAL) v0 = __ldg(val + p);
         if (rem > 1) { c1 = __ldg(colidx + p + 1); if (HAS_VAL) v1 = __ldg(val + p + 1); }
         if (rem > 2) { c2 = __ldg(colidx + p + 2); if (HAS_VAL) v2 = __ldg(val + p + 2); }
-        if (row_label != nullptr) {
+        if ((MODE & 2)) {
           c0 = __ldg(row_label + c0);
           if ((unsigned)c0 >= (unsigned)num_labels) { c0 = 0; v0 = 0.f; }
           if (rem > 1) { c1 = __ldg(row_label + c1); if ((unsigned)c1 >= (unsigned)num_labels) { c1 = 0; v1 = 0.f; } }
@@ -374,13 +376,13 @@ k_spmm_g(const int* __restrict__ rowptr, const int* __restrict__ colidx,
         acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f);
       }
       Y[(size_t)r * F4 + f] = acc;
-      if (dot_vec != nullptr) {          // same per-lane FMA chain and butterfly as k_linear_fwd_small: bit-identical
+      if ((MODE & 1)) {          // same per-lane FMA chain and butterfly as k_linear_fwd_small: bit-identical
         const float4 w = __ldg(dot_vec + f);
         dot = fmaf(acc.x, w.x, dot); dot = fmaf(acc.y, w.y, dot);
         dot = fmaf(acc.z, w.z, dot); dot = fmaf(acc.w, w.w, dot);
       }
     }
-    if (dot_vec != nullptr) {
+    if ((MODE & 1)) {
       // the LPR lanes of a row leave the row loop together, so the group is converged here
       const unsigned gmask = LPR == 32 ? 0xffffffffu : (((1u << LPR) - 1u) << (((threadIdx.x & 31) / LPR) * LPR));
 #pragma unroll
@@ -600,8 +602,10 @@ static int launch_spmm(const int* rowptr, const int* colidx, const float* val, c
       const bool fuse_dot = dot_vec && dot_out && F4 <= lpr && (((uintptr_t)dot_vec) & 15) == 0;
       const float4* dv = fuse_dot ? (const float4*)dot_vec : nullptr;
       if (dot_done) *dot_done = fuse_dot;
-#define TSG_G(L, FM, T) k_spmm_g<L, HAS_VAL, FM, T><<<g, T, 0, st>>>(rowptr, colidx, val, (const float4*)H, (const float4*)bias, (float4*)Y, (int)N, F4, relu, big ? hdist : 0, dv, dot_out, row_label, num_labels)
-#define TSG_GT(L, FM) if (big) TSG_G(L, FM, 1024); else TSG_G(L, FM, 256);
+      const int mode = (dv ? 1 : 0) | (row_label ? 2 : 0);
+#define TSG_GM(L, FM, T, M) k_spmm_g<L, HAS_VAL, FM, T, M><<<g, T, 0, st>>>(rowptr, colidx, val, (const float4*)H, (const float4*)bias, (float4*)Y, (int)N, F4, relu, big ? hdist : 0, dv, dot_out, row_label, num_labels)
+#define TSG_G(L, FM, T) { if (mode == 0) TSG_GM(L, FM, T, 0); else if (mode == 1) TSG_GM(L, FM, T, 1); else if (mode == 2) TSG_GM(L, FM, T, 2); else TSG_GM(L, FM, T, 3); }
+#define TSG_GT(L, FM) if (big) TSG_G(L, FM, 1024) else TSG_G(L, FM, 256)
 #define TSG_GV(L) if (exact) { TSG_GT(L, false) } else { TSG_GT(L, true) }
       switch (lpr) {
         case 1: TSG_GV(1) break; case 2: TSG_GV(2) break; case 4: TSG_GV(4) break;
@@ -610,6 +614,7 @@ static int launch_spmm(const int* rowptr, const int* colidx, const float* val, c
 #undef TSG_GV
 #undef TSG_GT
 #undef TSG_G
+#undef TSG_GM
     }
   } else {
     int lpr = 1; while (lpr < F && lpr < 32) lpr <<= 1;
