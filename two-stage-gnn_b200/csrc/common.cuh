@@ -215,8 +215,9 @@ k_partial_sum_final(const float* __restrict__ part, float* __restrict__ out0, in
 
 // Same second stage fused into the producing kernel: every CTA calls this (all threads, no early exits) after it
 // wrote its partial row; the CTA that draws the last ticket folds the rows in EXACTLY k_partial_sum_final's order, so
-// the result does not depend on which CTA that is.  Saves one ~5 us launch per reduction (21 per training step
-// before); worth it only while one CTA can read nb * total floats quickly (fused_tail_ok).  The ticket is a
+// the result does not depend on which CTA that is.  Saves one launch per reduction, but ONE CTA folding the partials
+// is latency bound: measured 40 us for 1,184 x 64 partials (the stand-alone kernel: 5 us), so fused_tail_ok only
+// admits reductions of at most 2,048 partial values (column sums of narrow matrices, scalar sums).  The ticket is a
 // zero-initialised counter from ticket_next(); atomicInc wraps it back to zero for its next user.
 __device__ __forceinline__ void partial_sum_tail(const float* part, float* out0, int n0, float* out1, int nb,
                                                  int total, unsigned* ticket) {
@@ -235,6 +236,7 @@ __device__ __forceinline__ void partial_sum_tail(const float* part, float* out0,
       float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
       if (i < total) {
         int b = y;
+#pragma unroll 4
         for (; b + 96 < nb; b += 128) {
           s0 += __ldcg(part + (size_t)b * total + i);
           s1 += __ldcg(part + (size_t)(b + 32) * total + i);
@@ -259,7 +261,7 @@ __device__ __forceinline__ void partial_sum_tail(const float* part, float* out0,
 
 static inline bool fused_tail_ok(int64_t nb, int64_t total) {
   static const bool off = getenv("TSG_NO_FUSED_TAIL") != nullptr;
-  return !off && nb * total <= 128 * 1024;
+  return !off && nb * total <= 2048;
 }
 
 unsigned* ticket_next();      // api.cu: a zeroed device counter from a per-device pool (nullptr if the pool cannot be made)
