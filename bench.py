@@ -6,14 +6,14 @@ Workload (BASELINE.json configs[1]): Code/sag `Net(89, nhid=32, final_dim=32, ra
 the anchor of one triplet, so one step = 1,168 triplets = 3,504 graph forward+backward passes packed
 into ONE block-diagonal batch (~0.94 M nodes, ~4.7 M directed edges), then MarginRankingLoss(1.5),
 backward, Adam step.  Per rank (weak scaling): each rank owns its own corpus shard and step batch;
-embeddings are all-gathered for the loss and gradients all-reduced (NCCL).
+one all-reduce per step carries the weighted gradients and the loss (NCCL).
 
   python bench.py [--gpus N] [--steps K] [--warmup W]          our arm
   python bench.py --impl reference ...                         reference CPU arm (oracle port, B=1)
 
 One JSON line on stdout (rank 0).  `value` = graphs/s with inputs resident in HBM; `e2e` = same step
 through TripletTrainer.run_from_host_compact with pinned HOST buffers holding what the dataset stores per
-graph (node labels, local edge lists), expanded on the GPU by K0, H2D + loss read-back inside the timed
+graph (node labels, local edge lists), consumed as they are by the executor's compact entries, H2D + loss read-back inside the timed
 region; `e2e_fp32_wire` = the same with the fp32 one-hot x / int64 edge_index tensors PyG's Batch.to(device)
 moves (PCIe bound); `e2e_blocking` = one blocking call per step; `roofline` = the level-1 GCN aggregation (K2 SpMM)
 timed alone with CUDA events, algorithmic bytes / measured HBM peak; `cpu_baseline` = the oracle
