@@ -465,6 +465,7 @@ int tsg_gate_readout_fwd(const float* x, const float* score, const int64_t* perm
 /* Score-side gate backward driven by perm (the other half of tsg_sag_conv_bwd_fused): dscore[perm[i]] =
  * (dxo[i] . x[perm[i]]) * (1 - tanh(score)^2), zero for dropped nodes, and dbias_score = sum(dscore) (the score
  * GCNConv's bias gradient).  dscore bit-identical to tsg_gate_gather_bwd; feat % 4 == 0. */
+/* (draws a counter from a per-device pool that is cudaMalloc'ed on first use: make the first call outside a stream capture) */
 size_t tsg_gate_score_bwd_workspace_bytes(void);
 int tsg_gate_score_bwd(const float* dxo, const float* x, const float* score, const int64_t* perm,
                        int64_t num_perm, int64_t num_nodes, int64_t feat, float* dscore, float* dbias_score,

@@ -113,13 +113,14 @@ if lib.tsg_abi_version() != 1:
     raise ImportError(f"libtsg ABI version {lib.tsg_abi_version()} != 1")
 
 # kernels each entry point enqueues (memsets not counted); bench.py reports the sum as gpu_launches
-# kernels one call enqueues at the bench shape (counted from profiles/r01c_launches_compact_step.csv)
+# kernels one call enqueues at the bench shape (counted from profiles/r01c_launches_{dense,compact}_step.csv:
+# 90 / 88 of ours per step = 26 outside the executor + 38 / 36 forward + 26 backward)
 KERNELS_PER_CALL = {
     "tsg_pack_batch": 1, "tsg_csr_build": 12, "tsg_edge_ptr": 1, "tsg_csr_build_graphs": 5, "tsg_csr_build_graphs_local": 5, "tsg_embed_fwd": 1, "tsg_embed_bwd_weight": 2, "tsg_spmm": 1, "tsg_spmm_tiled": 1, "tsg_relu_bwd_colsum": 1, "tsg_topk_sizes": 3, "tsg_topk": 2,
     "tsg_batch_to_ptr": 1, "tsg_filter_adj": 7, "tsg_gate_gather_fwd": 1, "tsg_gate_gather_bwd": 1,
     "tsg_readout_fwd": 1, "tsg_readout_bwd": 1, "tsg_triplet_fwd": 2, "tsg_triplet_bwd": 9,
     "tsg_pairdist_matrix": 1, "tsg_linear_fwd": 1, "tsg_dense_epilogue_bwd": 1, "tsg_linear_bwd_weight": 2,
-    "tsg_eigpool_build": 1, "tsg_coarsen_edges": 6, "tsg_inv_perm": 1, "tsg_csr_filter": 5, "tsg_sag_encoder_fwd": 38, "tsg_sag_encoder_bwd": 25, "tsg_sag_encoder_fwd_compact": 36, "tsg_spmm_label_dot": 1, "tsg_gate_readout_fwd": 1, "tsg_sag_encoder_bwd_compact": 25, "tsg_relu_bwd_colsum_rank1": 1, "tsg_sag_conv_bwd_fused": 1, "tsg_gate_score_bwd": 1, "tsg_spmm_dot": 1, "tsg_pack_batch_compact": 1, "tsg_seg_contract": 1, "tsg_seg_linear": 1, "tsg_gat_fwd": 2, "tsg_gat_bwd": 2, "tsg_dense_to_coo": 6, "tsg_nodebn_fwd": 1, "tsg_nodebn_bwd": 1,
+    "tsg_eigpool_build": 1, "tsg_coarsen_edges": 6, "tsg_inv_perm": 1, "tsg_csr_filter": 5, "tsg_sag_encoder_fwd": 38, "tsg_sag_encoder_bwd": 26, "tsg_sag_encoder_fwd_compact": 36, "tsg_spmm_label_dot": 1, "tsg_gate_readout_fwd": 1, "tsg_sag_encoder_bwd_compact": 26, "tsg_relu_bwd_colsum_rank1": 1, "tsg_sag_conv_bwd_fused": 1, "tsg_gate_score_bwd": 1, "tsg_spmm_dot": 1, "tsg_pack_batch_compact": 1, "tsg_seg_contract": 1, "tsg_seg_linear": 1, "tsg_gat_fwd": 2, "tsg_gat_bwd": 2, "tsg_dense_to_coo": 6, "tsg_nodebn_fwd": 1, "tsg_nodebn_bwd": 1,
 }
 launch_calls = 0        # libtsg entry points called since import
 kernel_launches = 0     # kernels enqueued by them
