@@ -73,7 +73,8 @@ k_csr_graph(const IdxT* __restrict__ row, const IdxT* __restrict__ col, const in
             const int64_t* __restrict__ node_ptr, const int* __restrict__ seg_off, int G, int64_t E_cap,
             int* __restrict__ rowptr, int* __restrict__ colidx, float* __restrict__ val, int* __restrict__ eid,
             int* __restrict__ t_rowptr, int* __restrict__ t_colidx, float* __restrict__ t_val, int* __restrict__ t_eid,
-            int* __restrict__ slot_d, int* __restrict__ slot_s, int max_nodes, int n_lo, int n_hi, int edge_cap) {
+            int* __restrict__ slot_d, int* __restrict__ slot_s, int max_nodes, int n_lo, int n_hi, int edge_cap,
+            int sorted_fast_path) {
   extern __shared__ int sh[];
   __shared__ int scan_sm[33];
   const int g = blockIdx.x;
@@ -139,6 +140,48 @@ k_csr_graph(const IdxT* __restrict__ row, const IdxT* __restrict__ col, const in
     if (es) { const unsigned p = (unsigned)sh_edge[e]; r = (int)(p >> 16); c = (int)(p & 0xffffu); }
     else { r = EdgeIdx<IdxT>::local(row[e0 + e], n0); c = EdgeIdx<IdxT>::local(col[e0 + e], n0); }
   };
+  // Coalesced edge lists -- sorted by (row, col), no duplicates, no self loops, every edge with its reverse: what
+  // PyG's TUDataset, the TU loader and tsg_dense_to_coo produce -- need no sorting at all: the
+  // src-major row r is the run of row r in the list, and by symmetry the dst-major row r holds the same neighbours
+  // in the same order (its k-th entry is the edge c_k -> r, found as the reverse of the k-th edge of the run), so both
+  // orientations are the list itself with one loop appended per row, written with consecutive threads on consecutive
+  // slots.  The three properties are VERIFIED per graph (packed keys strictly increasing; reverse edge found by
+  // binary search in its row's run); a graph that fails any of them takes the general path below.
+  int general = 1;
+  if (es && sorted_fast_path) {
+    int bad = 0;
+    for (int e = threadIdx.x; e < m; e += blockDim.x) {
+      const unsigned p = (unsigned)sh_edge[e];
+      const int r = (int)(p >> 16), c = (int)(p & 0xffffu);
+      if (r == c || (e > 0 && (unsigned)sh_edge[e - 1] >= p)) { bad = 1; continue; }
+      int lo = rp_s[c] - c;                              // run of row c (valid when the list is sorted and loop free)
+      const int run_end = rp_s[c + 1] - (c + 1);
+      int hi = run_end;
+      const unsigned key = ((unsigned)c << 16) | (unsigned)r;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if ((unsigned)sh_edge[mid] < key) lo = mid + 1; else hi = mid;
+      }
+      if (lo < run_end && (unsigned)sh_edge[lo] == key) tmp_d[e] = lo;       // id of the reverse edge
+      else bad = 1;
+    }
+    general = __syncthreads_or(bad);
+    if (!general) {
+      for (int e = threadIdx.x; e < m; e += blockDim.x) {
+        const unsigned p = (unsigned)sh_edge[e];
+        const int r = (int)(p >> 16), c = (int)(p & 0xffffu);
+        const float v = __fmul_rn(__fmul_rn(dis[r], 1.0f), dis[c]);      // == (dis[c] * 1) * dis[r]: commutative
+        const int pos = base + e + r;                     // rp[r] + (e - first edge of row r), r loops before it
+        colidx[pos] = (int)n0 + c; val[pos] = v;
+        if (eid) eid[pos] = (int)(e0 + tmp_d[e]);         // dst-major entry (r <- c) is the edge c -> r
+        if (t_rowptr) {
+          t_colidx[pos] = (int)n0 + c; t_val[pos] = v;
+          if (t_eid) t_eid[pos] = (int)(e0 + e);
+        }
+      }
+    }
+  }
+  if (general) {
   // slot claim (arbitrary order) ...
   for (int e = threadIdx.x; e < m; e += blockDim.x) {
     int r, c;
@@ -173,6 +216,7 @@ k_csr_graph(const IdxT* __restrict__ row, const IdxT* __restrict__ col, const in
       }
     }
   }
+  }   // general path
   for (int i = threadIdx.x; i < n; i += blockDim.x) {        // appended self loops: last slot of the row
     const float v = __fmul_rn(__fmul_rn(dis[i], 1.0f), dis[i]);
     const int p = base + rp_d[i + 1] - 1;
@@ -209,6 +253,11 @@ extern "C" size_t tsg_csr_build_graphs_workspace_bytes(int64_t num_graphs, int64
 }
 
 namespace tsg {
+static int sorted_env() {             // TSG_CSRG_SORTED=0: every graph takes the general (slot claim + rank) path
+  static const int v = [] { const char* e = getenv("TSG_CSRG_SORTED"); return e ? atoi(e) : 1; }();
+  return v;
+}
+
 static int edge_cap_env() {           // TSG_CSRG_EDGE_CAP=0 restores the global slot tables (A/B measurements)
   static const int v = [] { const char* e = getenv("TSG_CSRG_EDGE_CAP"); int x = e ? atoi(e) : CSRG_SMALL_EDGES; return x < 0 ? 0 : (x > 8192 ? 8192 : x); }();
   return v;
@@ -250,7 +299,7 @@ static int csr_build_graphs_impl(const IdxT* row, const IdxT* col, const int64_t
     const int ecap = cls == 0 ? edge_cap_env() : 0;      // big graphs: all shared memory goes to the node arrays
     k_csr_graph<IdxT><<<(int)num_graphs, 256, graph_smem_bytes(cap, ecap), st>>>(
         row, col, edge_ptr, node_ptr, seg_off, (int)num_graphs, num_edges_cap, rowptr, colidx, val, eid,
-        t_rowptr, t_colidx, t_val, t_eid, slot_d, slot_s, cap, lo, hi, ecap);
+        t_rowptr, t_colidx, t_val, t_eid, slot_d, slot_s, cap, lo, hi, ecap, sorted_env());
   }
   return check_launch("csr_build_graphs");
 }
