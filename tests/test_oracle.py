@@ -102,3 +102,46 @@ def test_sag_net_oracle_runs_and_backprops():
     assert out.shape == (5, 8)
     out.sum().backward()
     assert all(v.grad is not None for v in p.values())
+
+
+def test_onehot_features_make_conv1_a_table_gather():
+    """K3c / tsg_spmm_label_dot rest on: x = onehot(label)  =>  x @ W == W[label] bit for bit (every other term of the
+    dot product is +-0 * w) and x^T @ dY == the segment sum of dY rows by label.  Checked on the oracle's own GCNConv."""
+    x, ei, batch, _ = _small_batch("DD", 4, seed=9)
+    label = x.argmax(1)
+    assert torch.equal(x, torch.nn.functional.one_hot(label, x.size(1)).float())
+    g = torch.Generator().manual_seed(0)
+    W = torch.randn(x.size(1), 32, generator=g); b = torch.randn(32, generator=g)
+    assert torch.equal(x @ W, W[label])
+    n = x.size(0)
+    ei2, norm = R.gcn_norm(ei, None, n)
+    ref = R.gcn_conv(x, ei, W, b)
+    via_table = R.spmm_coo_edge_order(ei2, norm, W[label], n) + b
+    assert torch.equal(ref, via_table)
+    dy = torch.randn(n, 32, generator=g)
+    seg = torch.zeros(x.size(1), 32, dtype=torch.float64).index_add_(0, label, dy.double())
+    np.testing.assert_allclose((x.double().t() @ dy.double()).numpy(), seg.numpy(), rtol=0, atol=1e-12)
+
+
+def test_coalesced_edge_list_is_its_own_csr_in_both_orientations():
+    """K1b's fast path rests on: for a list sorted by (row, col), loop free, without duplicates and symmetric, the
+    dst-major and the src-major CSR of the self-loop-augmented operator are the SAME arrays -- the list itself with
+    one loop closing every row -- and the edge id of the k-th dst-major entry of row r is the id of the reverse of
+    the k-th edge of run r.  Checked against the oracle's stable counting sort (the K1 contract)."""
+    c = synth.make_corpus("DD", 3, seed=5)
+    for gidx in range(3):
+        n = c.num_nodes(gidx)
+        sl = slice(int(c.edge_ptr[gidx]), int(c.edge_ptr[gidx + 1]))
+        ei = torch.from_numpy(np.stack([c.row[sl], c.col[sl]]).astype(np.int64))
+        rp_d, ci_d, v_d, eid_d = R.gcn_csr(ei, n, by="dst")
+        rp_s, ci_s, v_s, eid_s = R.gcn_csr(ei, n, by="src")
+        assert torch.equal(rp_d, rp_s) and torch.equal(ci_d, ci_s) and torch.equal(v_d, v_s)
+        m = ei.size(1)
+        # the list itself: entry of edge e = (r, c) sits at e + r, the loop of row r at rp[r + 1] - 1
+        pos = torch.arange(m) + ei[0]
+        assert torch.equal(ci_s[pos].long(), ei[1]) and torch.equal(eid_s[pos].long(), torch.arange(m))
+        code = (ei[0] * n + ei[1]).tolist()
+        rev = torch.tensor([code.index(int(cc) * n + int(rr)) for rr, cc in zip(ei[0], ei[1])])
+        assert torch.equal(eid_d[pos].long(), rev)
+        loops = rp_s[1:].long() - 1
+        assert torch.equal(ci_s[loops].long(), torch.arange(n))
