@@ -69,3 +69,28 @@ def test_missing_files_raise():
     from tsg import tu
     with pytest.raises(RuntimeError):
         tu.load(os.path.join(HERE, "golden", "tu", "NOPE", "NOPE"))
+
+
+def test_loaded_corpus_feeds_the_compact_step_format():
+    """H1 -> feeder: a corpus parsed from TU files becomes the compact host batch of run_from_host_compact; its edge
+    lists are coalesced (sorted, loop free, symmetric), i.e. the form K1b's verified fast path takes."""
+    import numpy as np
+    from tsg import tu
+    from tsg.feeder import compact_host_batch
+    c, _, _ = tu.load(os.path.join(os.path.dirname(__file__), "golden", "tu", "TOY", "TOY"), "pyg")
+    ids = np.array([3, 0, 3, 5], dtype=np.int64)
+    b = compact_host_batch(c, ids, np.array([[0, 1, 3], [2, 3, 1]]), pin=False)
+    n = np.diff(c.node_ptr)[ids]; e = np.diff(c.edge_ptr)[ids]
+    assert np.array_equal(np.diff(b["node_ptr"]), n) and np.array_equal(np.diff(b["edge_ptr"]), e)
+    assert b["label"].dtype.is_floating_point is False and b["label"].numel() == n.sum()
+    assert b["row"].numel() == e.sum() and b["triplets"].shape == (2, 3)
+    for k, g in enumerate(ids):
+        sl = slice(int(b["edge_ptr"][k]), int(b["edge_ptr"][k + 1]))
+        src = slice(int(c.edge_ptr[g]), int(c.edge_ptr[g + 1]))
+        assert np.array_equal(b["row"][sl].numpy(), c.row[src]) and np.array_equal(b["col"][sl].numpy(), c.col[src])
+        r, cc, nn = b["row"][sl].numpy().astype(np.int64), b["col"][sl].numpy().astype(np.int64), max(int(n[k]), 1)
+        code = r * nn + cc
+        assert np.all(np.diff(code) > 0) and np.all(r != cc)
+        assert set((cc * nn + r).tolist()) == set(code.tolist())
+    with pytest.raises(ValueError):
+        compact_host_batch(c, ids, np.array([[0, 1, 4]]), pin=False)
