@@ -455,7 +455,10 @@ def main():
                 "config": {"workload": workload_name(a), "graphs_per_step_per_gpu": graphs_per_step,
                            "nodes_per_step": N, "directed_edges_per_step": E,
                            "l2_policy": "inputs larger than L2 (x alone is %.0f MB), 2 alternating batches" % (N * corpus.num_node_labels * 4 / 1e6),
-                           "parallelism": f"dp{world}: shard by graph; one all-reduce per step carrying [T_r * grads, T_r * loss, T_r]"},
+                           "parallelism": f"dp{world}: shard by graph; one all-reduce per step carrying [T_r * grads, T_r * loss, T_r]",
+                           "input_form": "value: PyG wire format (fp32 one-hot x, int64 edge_index) resident in HBM; e2e and "
+                                         "value_compact_input: node labels + graph-local int32 endpoints (what the dataset stores), "
+                                         "identical forward results; e2e_fp32_wire is the end-to-end counterpart of value"},
                 "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": ms_e2e / a.steps,
                         "h2d_bytes_per_step": int(h2d_compact), "d2h_bytes_per_step": 4,
                         "api": "TripletTrainer.run_from_host_compact: pinned host node labels[i32 N] + local edge lists"
