@@ -9,8 +9,10 @@
  *
  * Conventions
  *   - all pointers are DEVICE pointers unless the name ends in _host; caller allocates everything
- *     (inputs, outputs, workspace); the library never allocates, never retains pointers past
- *     return, never synchronises the stream, and is CUDA-graph-capture safe;
+ *     (inputs, outputs, workspace); the compute entry points never allocate, never retain pointers
+ *     past return, never synchronise the stream, and are CUDA-graph-capture safe.  The ONE exception
+ *     is tsg_init_device(): call it once per device before the first compute call and outside any
+ *     stream capture (it cudaMalloc's 16 KB of zeroed counters the fused reduction tails draw from);
  *   - all work is enqueued on `stream` (a cudaStream_t passed as void*);
  *   - return value: 0 on success, negative TSG_E* on failure; tsg_last_error() gives the message
  *     (thread local).  No exceptions cross the ABI.  There is no CPU fallback.
@@ -44,6 +46,11 @@ int tsg_abi_version(void);
 const char* tsg_last_error(void);
 /* 0 if the current device can run this library (compute capability 10.x), else TSG_EARCH. */
 int tsg_check_device(void);
+/* One-time, per-device set-up (the only entry point that allocates / synchronises): creates the 4,096-counter pool
+ * used by kernels that finish their second-stage reduction in the last CTA.  Idempotent, thread safe.  Entry points
+ * that have a separate-launch second stage fall back to it when the pool is missing; tsg_gate_score_bwd and the
+ * executor entries return TSG_EINVAL. */
+int tsg_init_device(void);
 
 /* ------------------------------------------------------------------------------------------
  * K0  device-side batch assembly from an HBM-resident corpus
@@ -465,7 +472,7 @@ int tsg_gate_readout_fwd(const float* x, const float* score, const int64_t* perm
 /* Score-side gate backward driven by perm (the other half of tsg_sag_conv_bwd_fused): dscore[perm[i]] =
  * (dxo[i] . x[perm[i]]) * (1 - tanh(score)^2), zero for dropped nodes, and dbias_score = sum(dscore) (the score
  * GCNConv's bias gradient).  dscore bit-identical to tsg_gate_gather_bwd; feat % 4 == 0. */
-/* (draws a counter from a per-device pool that is cudaMalloc'ed on first use: make the first call outside a stream capture) */
+/* (draws a counter from the per-device pool created by tsg_init_device) */
 size_t tsg_gate_score_bwd_workspace_bytes(void);
 int tsg_gate_score_bwd(const float* dxo, const float* x, const float* score, const int64_t* perm,
                        int64_t num_perm, int64_t num_nodes, int64_t feat, float* dscore, float* dbias_score,

@@ -113,3 +113,55 @@ def test_pool_patch(cuda):
     out = dense_patch.pool_forward(me, xg)
     (out * cot.to(cuda)).sum().backward()
     assert rel_err(out, ref) <= TOL and rel_err(xg.grad, xo.grad) <= TOL
+
+
+@pytest.mark.gpu
+def test_softpool_under_the_patch_trains_the_assignment_tower(cuda):
+    """SoftPoolingGcnEncoder feeds the DIFFERENTIABLE pooled adjacency S^T A S into the same
+    GraphConv.forward (encoders.py:375,378).  The wire-format drop-in must carry d(adj) back to assign_conv_* /
+    assign_pred_*: the forward below is encoders.py:327-406 spelled with the patched methods, checked against the
+    fixture produced by the REAL reference module (readout and every parameter gradient)."""
+    from golden_util import conv_names, load
+    from tsg import dense_patch
+    d = load("dense_diffpool.npz")
+    N, Fi, H, O, L = [int(v) for v in d["dims"]]
+    n = int(d["n"])
+    P = {k[len("param/"):]: v.to(cuda).clone().requires_grad_(True) for k, v in d.items() if k.startswith("param/")}
+
+    def conv(name):
+        return types.SimpleNamespace(weight=P[name + ".weight"], bias=P[name + ".bias"], add_self=False,
+                                     normalize_embedding=True, dropout=0.0)
+
+    def gcn_forward(x, adj, names, mask):
+        outs = []
+        for i, nm in enumerate(names):
+            x = dense_patch.graphconv_forward(conv(nm), x, adj)
+            if i < len(names) - 1:
+                x = dense_patch.apply_bn(None, torch.relu(x))
+            outs.append(x)
+        z = torch.cat(outs, dim=2)
+        return z * mask if mask is not None else z
+
+    x, adj = d["x"].to(cuda), d["adj"].to(cuda)
+    mask = torch.zeros(1, N, 1, device=cuda); mask[0, :n] = 1
+    z = gcn_forward(x, adj, conv_names("conv_first", "conv_block", "conv_last", L), mask)
+    out0 = z.max(dim=1)[0]
+    za = gcn_forward(x, adj, conv_names("assign_conv_first_modules.0", "assign_conv_block_modules.0",
+                                        "assign_conv_last_modules.0", L), mask)
+    s = torch.softmax(za @ P["assign_pred_modules.0.weight"].t() + P["assign_pred_modules.0.bias"], dim=-1) * mask
+    xp = s.transpose(1, 2) @ z
+    ap = s.transpose(1, 2) @ adj @ s
+    assert ap.requires_grad
+    z2 = gcn_forward(xp, ap, conv_names("conv_first_after_pool.0", "conv_block_after_pool.0", "conv_last_after_pool.0", L), None)
+    out = torch.cat([out0, z2.max(dim=1)[0]], dim=1)
+    (out * d["cot"].to(cuda)).sum().backward()
+    assert rel_err(out, d["readout"]) <= TOL
+    checked = 0
+    for k, p in P.items():
+        if "grad/" + k in d:
+            assert p.grad is not None, f"{k}: no gradient reached it through the patched GraphConv"
+            assert rel_err(p.grad, d["grad/" + k]) <= 3e-5, k
+            checked += k.startswith("assign_")
+    assert checked >= 2 * L + 2
+    assert len(dense_patch.CACHE.items) <= dense_patch.CACHE.slots
+    assert not any(m.requires_grad for m, *_ in dense_patch.CACHE.items), "a differentiable adjacency was cached"

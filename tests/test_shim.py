@@ -35,6 +35,7 @@ def test_surface_names_import(shim):
 
 def test_dataset_and_loader(shim):
     os.environ["TSG_SYNTH_GRAPHS"] = "12"
+    os.environ["TSG_ALLOW_SYNTH"] = "1"
     try:
         from torch_geometric.data import DataLoader
         from torch_geometric.datasets import TUDataset
@@ -46,7 +47,21 @@ def test_dataset_and_loader(shim):
         assert int(batch.batch.max()) == 3 and batch.y.numel() == 4
         assert int(batch.edge_index.max()) < batch.x.size(0)
     finally:
-        del os.environ["TSG_SYNTH_GRAPHS"]
+        del os.environ["TSG_SYNTH_GRAPHS"], os.environ["TSG_ALLOW_SYNTH"]
+
+
+def test_dataset_missing_files_raise(shim, tmp_path):
+    """a wrong data path must not silently train on synthetic graphs."""
+    from torch_geometric.datasets import TUDataset
+    os.environ.pop("TSG_ALLOW_SYNTH", None)
+    with pytest.raises(FileNotFoundError):
+        TUDataset(str(tmp_path), name="DD")
+    os.environ["TSG_ALLOW_SYNTH"] = "1"
+    try:
+        with pytest.raises(FileNotFoundError):
+            TUDataset(str(tmp_path), name="NOT_A_DATASET")
+    finally:
+        del os.environ["TSG_ALLOW_SYNTH"]
 
 
 @pytest.mark.skipif(not os.path.isdir(REF_SAG), reason="reference checkout not present on this box")

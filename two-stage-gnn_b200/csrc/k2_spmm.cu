@@ -261,11 +261,13 @@ k_spmm_tiled(const int* __restrict__ rowptr, const int* __restrict__ colidx, con
 // a producer warp issuing per-line L2 prefetches (126 us), L1 evict_first / evict_last hints (+10 %),
 // two float4 per lane with 4 lanes per row (fewer instructions, less memory parallelism: 123-160 us).
 // ------------------------------------------------------------------------------------------
-// TMA bulk prefetch into L2 of [p, p + bytes): address aligned down / size rounded up to 16 bytes
+// TMA bulk prefetch into L2 of [p, p + bytes): start aligned down (stays inside the array: allocations are at least
+// 16-byte aligned), end aligned DOWN too, so the request never reaches past the array's last byte and tsg_spmm needs no
+// slack behind rowptr / colidx / val (a trailing partial 16 bytes is simply not prefetched)
 __device__ __forceinline__ void bulk_prefetch_l2(const void* p, size_t bytes) {
-  if (bytes == 0) return;
   const uintptr_t a = reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)15;
-  const uintptr_t e = (reinterpret_cast<uintptr_t>(p) + bytes + 15) & ~(uintptr_t)15;
+  const uintptr_t e = (reinterpret_cast<uintptr_t>(p) + bytes) & ~(uintptr_t)15;
+  if (e <= a) return;
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(a), "r"((unsigned)(e - a)) : "memory");
 }
 
@@ -410,7 +412,7 @@ k_spmm_g(const int* __restrict__ rowptr, const int* __restrict__ colidx,
 constexpr int TT_THREADS = 1024;
 constexpr int TT_CWARPS = TT_THREADS / 32 - 1;          // 31 consumer warps + 1 producer warp
 constexpr int TT_STAGE_BYTES = 104 * 1024;
-constexpr int TT_SPIN = 1 << 20;
+constexpr int TT_SPIN = 1 << 22;
 
 __device__ __forceinline__ uint32_t tt_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ bool tt_wait(uint32_t bar, uint32_t parity) {
@@ -420,6 +422,7 @@ __device__ __forceinline__ bool tt_wait(uint32_t bar, uint32_t parity) {
                  "selp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     if (ok) return true;
   }
+  __trap();        // hang guard: never continue on shared memory the copy has not filled
   return false;
 }
 __device__ __forceinline__ void tt_tma(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {

@@ -464,7 +464,7 @@ extern "C" int tsg_gate_score_bwd(const float* dxo, const float* x, const float*
   if (workspace_bytes < tsg_gate_score_bwd_workspace_bytes()) { set_error("gate_score_bwd: workspace too small"); return TSG_EWORKSPACE; }
   cudaStream_t st = (cudaStream_t)stream;
   unsigned* ticket = ticket_next();
-  TSG_REQUIRE(ticket != nullptr, "gate_score_bwd: no ticket pool on this device");
+  TSG_REQUIRE(ticket != nullptr, "gate_score_bwd: call tsg_init_device() once per device first (no counter pool)");
   cudaMemsetAsync(dscore, 0, (size_t)num_nodes * sizeof(float), st);      // dropped nodes
   const int F4 = (int)(F / 4);
   int lp = 1; while (lp < F4 && lp < 32) lp <<= 1;

@@ -19,7 +19,7 @@ namespace tsg {
 constexpr int TC_KC = 32;                 // contraction rows per staged chunk (4 MMA k-steps of 8)
 constexpr int TC_M = 128;
 constexpr int TC_A_BYTES = TC_M * TC_KC * 4;          // 16 KB per (hi | lo)
-constexpr int TC_SPIN_LIMIT = 1 << 14;   // hang guard: a completed MMA batch arrives within microseconds
+constexpr int TC_SPIN_LIMIT = 1 << 22;   // hang guard: a completed MMA batch arrives within microseconds
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -63,6 +63,10 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
                  "selp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     if (ok) return true;
   }
+  // hang guard tripped: carrying on would read TMEM / overwrite shared memory under an unfinished MMA and return
+  // silently corrupt results, so the kernel dies loudly instead (the launch error reaches the caller at its next
+  // CUDA call; `err` is still set by kernels that get that far)
+  __trap();
   return false;
 }
 
@@ -201,7 +205,7 @@ k_seg_contract_tc(const float* __restrict__ X, const float* __restrict__ Y, cons
 // ------------------------------------------------------------------------------------------
 constexpr int KC2 = 16;                   // contraction rows per chunk (2 MMA k-steps of 8)
 constexpr int RAW_STAGES = 4;
-constexpr int TC2_SPIN_LIMIT = 1 << 18;   // hang guard (a wait normally returns within microseconds)
+constexpr int TC2_SPIN_LIMIT = 1 << 22;   // hang guard (a wait normally returns within microseconds)
 
 __device__ __forceinline__ bool mbar_wait2(uint32_t bar, uint32_t parity) {
   for (int spin = 0; spin < TC2_SPIN_LIMIT; ++spin) {
@@ -210,6 +214,10 @@ __device__ __forceinline__ bool mbar_wait2(uint32_t bar, uint32_t parity) {
                  "selp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     if (ok) return true;
   }
+  // hang guard tripped: carrying on would read TMEM / overwrite shared memory under an unfinished MMA and return
+  // silently corrupt results, so the kernel dies loudly instead (the launch error reaches the caller at its next
+  // CUDA call; `err` is still set by kernels that get that far)
+  __trap();
   return false;
 }
 

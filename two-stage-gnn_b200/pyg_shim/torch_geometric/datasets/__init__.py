@@ -1,8 +1,10 @@
-"""torch_geometric.datasets.TUDataset (train*.py:5,161-163).  If <root>/<name>/[raw/]<name>_A.txt exists the
-files are read by the native TU loader (tsg.tu, H1); otherwise (no network, no dataset on the box) graphs of
-the named dataset's SHAPE are generated by tsg.synth (seeded).  Node features are one-hot node labels like
-TUDataset's.  TSG_SYNTH_GRAPHS overrides the synthetic graph count."""
+"""torch_geometric.datasets.TUDataset (train*.py:5,161-163).  <root>/<name>/[raw/]<name>_A.txt is read by the native
+TU loader (tsg.tu, H1).  Missing files raise FileNotFoundError (upstream PyG would download them; there is no network
+here and training on made-up data must never happen silently).  Only with TSG_ALLOW_SYNTH=1 in the environment are
+seeded synthetic graphs of the named dataset's SHAPE generated instead (tsg.synth; DD and PROTEINS shapes only), with
+a warning on stderr; TSG_SYNTH_GRAPHS then overrides the graph count.  Node features are one-hot node labels."""
 import os
+import sys
 
 import torch
 
@@ -23,7 +25,16 @@ class TUDataset(torch.utils.data.Dataset):
             self.corpus, self.attr, self.num_classes = tu.load(prefix, "pyg")
             self.num_features = self.corpus.num_node_labels
         else:
-            shape = _ALIAS.get(name, "DD")
+            if os.environ.get("TSG_ALLOW_SYNTH", "0") != "1":
+                raise FileNotFoundError(
+                    f"TUDataset: no TU files for {name!r} under {root!r} (looked for {name}_A.txt in <root>, "
+                    f"<root>/{name}, <root>/{name}/raw); there is no download path.  Set TSG_ALLOW_SYNTH=1 to train on "
+                    "seeded SYNTHETIC graphs of the dataset's shape instead.")
+            if name not in _ALIAS:
+                raise FileNotFoundError(f"TUDataset: no synthetic shape is defined for {name!r} (known: {sorted(_ALIAS)})")
+            shape = _ALIAS[name]
+            print(f"[tsg] WARNING: TUDataset({root!r}, {name!r}): files not found, TSG_ALLOW_SYNTH=1 -> using SYNTHETIC "
+                  f"{shape}-shape graphs (seed 777); accuracies are meaningless", file=sys.stderr)
             n = int(os.environ.get("TSG_SYNTH_GRAPHS", _COUNT.get(shape, 1168)))
             self.name, self.corpus = name, synth.make_corpus(shape, n, seed=777)
             self.num_classes, self.num_features = 2, self.corpus.num_node_labels

@@ -21,6 +21,7 @@ _PROTOTYPES = {
     "tsg_abi_version": (I, []),
     "tsg_last_error": (c_char_p, []),
     "tsg_check_device": (I, []),
+    "tsg_init_device": (I, []),
     "tsg_pack_batch": (I, [P, P, P, I64, P, P, P, P, P, P, I64, P, P, P, P]),
     "tsg_pack_batch_compact": (I, [P, P, P, I64, P, P, P, P, P, P, P, P, P]),
     "tsg_csr_build_workspace_bytes": (SZ, [I64, I64]),
@@ -146,8 +147,23 @@ def stream_ptr() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+_inited_devices = set()
+
+
+def init_device() -> None:
+    """tsg_init_device() for the current device, once (the only allocating entry point: keeps every compute entry
+    allocation free and stream-capture safe)."""
+    d = torch.cuda.current_device()
+    if d not in _inited_devices:
+        if lib.tsg_init_device() != 0:
+            raise RuntimeError(f"tsg_init_device failed: {last_error()}")
+        _inited_devices.add(d)
+
+
 def call(name: str, *args) -> None:
     global launch_calls, kernel_launches
+    if not _inited_devices or torch.cuda.current_device() not in _inited_devices:
+        init_device()
     if profile is not None:
         s = torch.cuda.Event(enable_timing=True); e = torch.cuda.Event(enable_timing=True)
         s.record()

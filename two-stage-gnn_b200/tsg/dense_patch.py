@@ -29,7 +29,7 @@ class _DenseCsrCache:
     """adjacency tensor -> CSR over all B*N rows.  Keyed on the tensor object + version + options;
     the tensor is held alive so its storage cannot be recycled under the key."""
 
-    def __init__(self, slots: int = 16):
+    def __init__(self, slots: int = 4):
         self.slots, self.items = slots, []
 
     def get(self, mat: torch.Tensor, transpose: bool = False, want_eid: bool = False) -> CSR:
@@ -59,9 +59,15 @@ def graphconv_forward(self, x: torch.Tensor, adj: torch.Tensor) -> torch.Tensor:
     if getattr(self, "dropout", 0.0) > 0.001:
         x = self.dropout_layer(x)
     B, N, Fi = x.shape
-    csr = CACHE.get(adj)
     xf = x.reshape(B * N, Fi)
-    y = ops.spmm(csr, xf)
+    if adj.requires_grad:
+        # DiffPool's post-pool tower (encoders.py:375,378): adj = S^T A S is a dense, DIFFERENTIABLE K x K block whose
+        # gradient trains assign_conv_* / assign_pred_*.  Never cached, never sparsified: adj @ x is the per-graph
+        # row-local product (K7 seg_linear), whose backward returns d(adj) = dY x^T and d(x) = adj^T dY.
+        gptr = torch.arange(B + 1, device=x.device, dtype=torch.int64) * N
+        y = ops.seg_linear(adj.reshape(B * N, adj.size(2)).contiguous(), x.contiguous(), gptr)
+    else:
+        y = ops.spmm(CACHE.get(adj), xf)
     if self.add_self:
         y = y + xf
     out = ops.linear(y, self.weight, self.bias, LIN_NORMALIZE if self.normalize_embedding else 0)

@@ -272,12 +272,14 @@ class PackedSAGNet(torch.nn.Module):
 
     def _level_plan(self, node_ptr_host, dev):
         """(host plan int64 [4, G+1], the same on the device).  Batches that come round again (an epoch over a fixed
-        set of packed batches) reuse their device copy: keyed on the host array's identity, size and checksum."""
-        arr = np.asarray(node_ptr_host)
-        key = (id(node_ptr_host), arr.shape[0], int(arr[-1]), int(arr.sum()), str(dev), self.pooling_ratio)
+        set of packed batches) reuse their device copy.  Keyed on the CONTENT of the offsets (hash of the bytes, then an
+        exact comparison with the stored copy): object identity is not a key -- feeders create a short-lived array per
+        step and CPython reuses ids."""
+        arr = np.ascontiguousarray(np.asarray(node_ptr_host, dtype=np.int64))
+        key = (hash(arr.tobytes()), arr.shape[0], str(dev), self.pooling_ratio)
         cache = self.__dict__.setdefault("_plan_cache", {})
         hit = cache.get(key)
-        if hit is not None:
+        if hit is not None and np.array_equal(hit[0][0], arr):
             return hit
         plan = host_level_ptrs(arr, self.pooling_ratio)
         ptrs = torch.from_numpy(plan).pin_memory().to(dev, non_blocking=True)
