@@ -448,6 +448,13 @@ typedef struct {
   int64_t max_graph_nodes[3];
 } tsg_sag_shape;
 size_t tsg_sag_arena_bytes(const tsg_sag_shape* shape);
+/* Where the forward leaves a saved tensor inside the arena (a pure function of the shape): byte offset and size of
+ * `field` of pooling level `level` (0..2).  What a caller needs to read back SAGPool.forward's other return values
+ * (Code/sag/layers.py:26 returns perm; the parity tests assert it level by level).  perm: int64 [n[level+1]];
+ * score / h / xg: fp32 [n], [n, hidden], [n[level+1], hidden]; CSR arrays: int32 / fp32 of the level's A_hat. */
+enum { TSG_SAG_PERM = 0, TSG_SAG_SCORE = 1, TSG_SAG_H = 2, TSG_SAG_XG = 3, TSG_SAG_ROWPTR = 4, TSG_SAG_COLIDX = 5,
+       TSG_SAG_VAL = 6, TSG_SAG_INV = 7 };
+int tsg_sag_arena_locate(const tsg_sag_shape* shape, int level, int field, size_t* offset, size_t* bytes);
 int tsg_sag_encoder_fwd(const tsg_sag_shape* shape, const float* x, const int64_t* row, const int64_t* col,
                         const int64_t* level_ptr, const float* const* params, float* z,
                         void* arena, size_t arena_bytes, void* stream);

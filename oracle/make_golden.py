@@ -208,16 +208,116 @@ def golden_eigen(eig):
           **_state(model), **grads)
 
 
+# ------------------------------------------------------------------------------------------------------------
+# BASELINE-dimension fixtures: the same REAL modules at the sizes BASELINE.json's configs 3, 4
+# and 5 name, on one synthetic graph of the named dataset shape padded to the reference's default --max-nodes = 1000.
+# Inputs are stored sparse (edge list, real rows only); the tests rebuild the dense wire format.
+# ------------------------------------------------------------------------------------------------------------
+def _synth_graph(shape, lo, hi, seed):
+    """One tsg.synth graph of `shape` with lo <= n <= hi: (n, edge_index int64 [2, E] local ids, labels)."""
+    sys.path.insert(0, os.path.join(ROOT, "two-stage-gnn_b200"))
+    from tsg import synth
+    c = synth.make_corpus(shape, 64, seed=seed)
+    for g in range(c.num_graphs):
+        n = c.num_nodes(g)
+        if lo <= n <= hi:
+            e0, e1 = int(c.edge_ptr[g]), int(c.edge_ptr[g + 1])
+            return n, np.stack([c.row[e0:e1], c.col[e0:e1]]).astype(np.int64), c.node_label[c.node_ptr[g]:c.node_ptr[g + 1]]
+    raise RuntimeError("no graph in range")
+
+
+def _dense_adj(ei, N):
+    a = torch.zeros(1, N, N)
+    a[0, torch.from_numpy(ei[0]), torch.from_numpy(ei[1])] = 1.0
+    return a
+
+
+def golden_gat_cfg3(gat):
+    """Config 3: DGATEncoderGraph(32,32,32,2, L=3, heads [2,2]) -> widths 32 -> 64 -> 64 -> 32, JAN.Y-shape graph
+    (n ~ 203, E ~ 3,732 directed), N = 1000 pad, learnable-style N(0,1) 32-d features (encoders_GAT.py:175-198)."""
+    torch.manual_seed(1003)
+    N, Fi, H, O, L = 1000, 32, 32, 32, 3
+    n, ei, _ = _synth_graph("JANY", 195, 215, seed=303)
+    model = gat.DGATEncoderGraph(Fi, H, O, 2, _Args(), num_layers=L, num_heads=[2, 2],
+                                 neg_input_slopes=[0.2] * 3, dropouts=[0.0] * 3)
+    x = torch.zeros(1, N, Fi); x[0, :n] = torch.randn(n, Fi)
+    readout, out = model(x, _dense_adj(ei, N))
+    cot = torch.randn_like(readout)
+    (readout * cot).sum().backward()
+    _save("dense_gat_cfg3.npz", x=_np(x[0, :n]), ei=ei.astype(np.int32), n=np.array(n), readout=_np(readout), out=_np(out),
+          cot=_np(cot), dims=np.array([N, Fi, H, O, L]), **_state(model), **_grads(model))
+
+
+def golden_diffpool_cfg4(enc):
+    """Config 4: SoftPoolingGcnEncoder(N=1000, 32,32,32,2, L=3, assign_hidden=32, assign_ratio=0.1) -> K = 100, D = 96,
+    assign Linear(164 -> 100); DD-shape graph (n ~ 269); features = rows of a shared N(0, 2^2) table
+    (train_triplet.py:379-385).  encoders.py:327-406."""
+    torch.manual_seed(1004)
+    N, Fi, H, O, L = 1000, 32, 32, 32, 3
+    n, ei, _ = _synth_graph("DD", 255, 285, seed=404)
+    model = enc.SoftPoolingGcnEncoder(N, Fi, H, O, 2, L, assign_hidden_dim=32, assign_ratio=0.1,
+                                      num_pooling=1, bn=True, linkpred=False, args=_Args(), final_dim="output_dim")
+    x = torch.zeros(1, N, Fi); x[0, :n] = torch.randn(n, Fi) * 2
+    readout, ypred = model(x, _dense_adj(ei, N), np.array([n]), assign_x=x)
+    cot = torch.randn_like(readout)
+    (readout * cot).sum().backward()
+    _save("dense_diffpool_cfg4.npz", x=_np(x[0, :n]), ei=ei.astype(np.int32), n=np.array(n), readout=_np(readout),
+          ypred=_np(ypred), assign=_np(model.assign_tensor[0, :n]), cot=_np(cot), dims=np.array([N, Fi, H, O, L]),
+          **_state(model), **_grads(model))
+
+
+def golden_eigen_cfg5(eig):
+    """Config 5: WavePoolingGcnEncoder(N, 89, 32, 32, 2, L=2, num_pool_matrix=1, num_pool_final_matrix=1,
+    pool_sizes=[10], pred_hidden=[50]) -> D = 64, pred input 192; DD-shape graph (n ~ 269 -> 27 clusters of <= 10
+    consecutive nodes), one-hot 89 node labels.  eigengcn/encoders.py:323-378."""
+    torch.manual_seed(1005)
+    N, Fi, H, O, L, csize = 1000, 89, 32, 32, 2, 10
+    n, ei, lab = _synth_graph("DD", 255, 285, seed=505)
+    model = eig.WavePoolingGcnEncoder(N, Fi, H, O, 2, L, num_pool_matrix=1, num_pool_final_matrix=1,
+                                      pool_sizes=[csize], pred_hidden_dims=[50], concat=True, bn=True, mask=1, args=_Args())
+    adj = _dense_adj(ei, N)
+    a_np = adj[0].numpy()
+    nc = -(-n // csize)
+    cl = np.arange(n) // csize
+    pval = np.zeros(n, np.float32)
+    P = np.zeros((N, N), np.float32); omega = np.zeros((N, N), np.float32)
+    for c in range(nc):
+        idx = np.nonzero(cl == c)[0]
+        sub = a_np[np.ix_(idx, idx)]
+        w, v = np.linalg.eigh((np.diag(sub.sum(1)) - sub).astype(np.float64))
+        vec = v[:, 0].copy()
+        if vec[0] < 0:
+            vec = -vec
+        P[idx, c] = vec.astype(np.float32); pval[idx] = vec.astype(np.float32); omega[idx, c] = 1.0
+    adj_pool = omega.T @ a_np @ omega
+    np.fill_diagonal(adj_pool, 0)
+    Pf = np.zeros((N, N), np.float32); Pf[:nc, 0] = 1.0 / np.sqrt(nc)
+    x = torch.zeros(1, N, Fi); x[0, np.arange(n), lab] = 1.0
+    pm = {0: [torch.from_numpy(P)[None]], 1: [torch.from_numpy(Pf)[None]]}
+    y = model(x, adj, [torch.from_numpy(adj_pool.astype(np.float32))[None]], np.array([n]), [np.array([nc])], pm)
+    cot = torch.randn_like(y)
+    (y * cot).sum().backward()
+    grads = {"grad/" + k: _np(p.grad) for k, p in model.named_parameters() if p.grad is not None}
+    _save("dense_eigen_cfg5.npz", label=lab.astype(np.int32), ei=ei.astype(np.int32), n=np.array(n), nc=np.array(nc),
+          cluster=cl.astype(np.int32), pval=pval, adj_pool=adj_pool[:nc, :nc].astype(np.float32), y=_np(y), cot=_np(cot),
+          dims=np.array([N, Fi, H, O, L]), **_state(model), **grads)
+
+
 def main():
     _neutralise_cuda()
+    only = set(sys.argv[1:])
+    want = lambda name: not only or name in only
     enc = _import_from("sage+gat+diffpool", "encoders")
-    golden_base(enc)
-    golden_gcn_forward(enc)
-    golden_diffpool(enc)
+    if want("base"): golden_base(enc)
+    if want("gcn_forward"): golden_gcn_forward(enc)
+    if want("diffpool"): golden_diffpool(enc)
+    if want("diffpool_cfg4"): golden_diffpool_cfg4(enc)
     gat = _import_from("sage+gat+diffpool", "encoders_GAT")
-    golden_gat(gat)
+    if want("gat"): golden_gat(gat)
+    if want("gat_cfg3"): golden_gat_cfg3(gat)
     eig = _import_from("eigengcn", "encoders")
-    golden_eigen(eig)
+    if want("eigen"): golden_eigen(eig)
+    if want("eigen_cfg5"): golden_eigen_cfg5(eig)
 
 
 if __name__ == "__main__":

@@ -119,3 +119,62 @@ def test_gcn_cross_check_dense():
     An = dis.view(-1, 1) * A * dis.view(1, -1)
     ref = D.graph_conv(x[None], An[None], w, bias, normalize_embedding=False)[0]
     assert rel_err(out, ref) <= 1e-5
+
+
+# ---------------------------------------------------------------- BASELINE-dimension fixtures (configs 3, 4, 5)
+def test_gat_cfg3_matches_reference():
+    """Config 3 dims: n = 203-ish JAN.Y-shape graph, N = 1000, heads [2,2], widths 32 -> 64 -> 64 -> 32."""
+    from golden_util import dense_adj, padded
+    d = load("dense_gat_cfg3.npz")
+    N = int(d["dims"][0])
+    layers = gat_layers(d)
+    req = [[dict(w=h["w"].clone().requires_grad_(True), a=h["a"].clone().requires_grad_(True)) for h in hs]
+           for _, hs in layers]
+    out = D.dgat_encoder_readout(padded(d["x"], N), dense_adj(d["ei"], N), req)
+    assert rel_err(out, d["readout"]) <= PIN
+    (out * d["cot"]).sum().backward()
+    for (lname, hs), rq in zip(layers, req):
+        for h, r in enumerate(rq):
+            assert rel_err(r["w"].grad, d[f"grad/{lname}.attention_{h}.w"]) <= 1e-5, (lname, h)
+            assert rel_err(r["a"].grad, d[f"grad/{lname}.attention_{h}.a"]) <= 1e-5, (lname, h)
+
+
+def test_diffpool_cfg4_matches_reference():
+    """Config 4 dims: N = 1000 -> K = 100, D = 96, Linear(164 -> 100), DD-shape graph."""
+    from golden_util import dense_adj, padded
+    d = load("dense_diffpool_cfg4.npz")
+    N, Fi, H, O, L = [int(v) for v in d["dims"]]
+    n = int(d["n"])
+    p = _diffpool_params(d, req=True)
+    out, aux = D.soft_pool_readout(padded(d["x"], N), dense_adj(d["ei"], N), [n], p)
+    assert aux["s"].shape[-1] == 100 and out.shape[-1] == 192
+    assert rel_err(aux["s"][0, :n], d["assign"]) <= PIN
+    assert rel_err(out, d["readout"]) <= PIN
+    (out * d["cot"]).sum().backward()
+    for key, (f, b, l) in dict(conv=("conv_first", "conv_block", "conv_last"),
+                               assign_conv=("assign_conv_first_modules.0", "assign_conv_block_modules.0", "assign_conv_last_modules.0"),
+                               conv_after=("conv_first_after_pool.0", "conv_block_after_pool.0", "conv_last_after_pool.0")).items():
+        for c, nm in zip(p[key], conv_names(f, b, l, L)):
+            assert rel_err(c["weight"].grad, d[f"grad/{nm}.weight"]) <= 1e-5, nm
+    assert rel_err(p["assign_pred.weight"].grad, d["grad/assign_pred_modules.0.weight"]) <= 1e-5
+
+
+def test_eigen_cfg5_matches_reference():
+    """Config 5 dims: 89 one-hot labels, L = 2, D = 64, 27 clusters of <= 10 nodes, pred 192 -> 50 -> 2."""
+    from golden_util import eigen_cfg5_operands
+    d = load("dense_eigen_cfg5.npz")
+    N, Fi, H, O, L = [int(v) for v in d["dims"]]
+    x, adj, ap, P, Pf = eigen_cfg5_operands(d)
+    p = dict(conv=clone_req(convs(d, "conv_first", "conv_block", "conv_last")),
+             conv_after=[clone_req(convs(d, "conv_first_after_pool.0", "conv_block_after_pool.0", "conv_last_after_pool.0"))])
+    out = D.wave_readout(x, adj, [ap], [int(d["n"])], [[int(d["nc"])]], [[P], [Pf]], p, num_pool_matrix=1, num_pool_final_matrix=1)
+    head = [dict(weight=d["param/pred_model.0.weight"], bias=d["param/pred_model.0.bias"]),
+            dict(weight=d["param/pred_model.2.weight"], bias=d["param/pred_model.2.bias"])]
+    y = D.mlp(out, head)
+    assert out.shape[-1] == 192
+    assert rel_err(y, d["y"]) <= PIN
+    (y * d["cot"]).sum().backward()
+    for c, nm in zip(p["conv"], conv_names("conv_first", "conv_block", "conv_last", L)):
+        assert rel_err(c["weight"].grad, d[f"grad/{nm}.weight"]) <= 1e-5, nm
+    for c, nm in zip(p["conv_after"][0], conv_names("conv_first_after_pool.0", "conv_block_after_pool.0", "conv_last_after_pool.0", L)):
+        assert rel_err(c["weight"].grad, d[f"grad/{nm}.weight"]) <= 1e-5, nm

@@ -134,6 +134,30 @@ extern "C" size_t tsg_sag_arena_bytes(const tsg_sag_shape* shape) {
   return a.total;
 }
 
+extern "C" int tsg_sag_arena_locate(const tsg_sag_shape* sh, int level, int field, size_t* offset, size_t* bytes) {
+  TSG_REQUIRE(shape_ok(sh) && level >= 0 && level < 3 && offset && bytes, "sag_arena_locate: bad argument");
+  SagArena a;
+  char* const base = (char*)256;            // any non-null base: only differences are used
+  layout(sh, base, &a);
+  const LevelBuf& b = a.lv[level];
+  const int64_t n = sh->n[level], k = sh->n[level + 1], H = sh->hidden;
+  const void* p = nullptr; size_t sz = 0;
+  switch (field) {
+    case TSG_SAG_PERM: p = b.perm; sz = (size_t)k * 8; break;
+    case TSG_SAG_SCORE: p = b.score; sz = (size_t)n * 4; break;
+    case TSG_SAG_H: p = b.h; sz = (size_t)n * H * 4; break;
+    case TSG_SAG_XG: p = b.xg; sz = (size_t)k * H * 4; break;
+    case TSG_SAG_ROWPTR: p = b.rowptr; sz = (size_t)(n + 1) * 4; break;
+    case TSG_SAG_COLIDX: p = b.colidx; sz = (size_t)(sh->num_edges + n) * 4; break;
+    case TSG_SAG_VAL: p = b.val; sz = (size_t)(sh->num_edges + n) * 4; break;
+    case TSG_SAG_INV: p = b.inv; sz = (size_t)n * 4; break;
+    default: set_error("sag_arena_locate: unknown field %d", field); return TSG_EINVAL;
+  }
+  *offset = (size_t)((const char*)p - base);
+  *bytes = sz;
+  return TSG_OK;
+}
+
 static int sag_fwd(const tsg_sag_shape* sh, const SagInput& in, const int64_t* level_ptr, const float* const* params,
                    float* z, void* arena, size_t arena_bytes, void* stream) {
   SagArena a;

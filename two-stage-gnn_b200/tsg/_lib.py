@@ -76,6 +76,7 @@ _PROTOTYPES = {
     "tsg_tu_fill": (I, [P, P, P, P, P, P, P, P]),
     "tsg_tu_free": (None, [P]),
     "tsg_sag_arena_bytes": (SZ, [P]),
+    "tsg_sag_arena_locate": (I, [P, I, I, P, P]),
     "tsg_sag_encoder_fwd": (I, [P, P, P, P, P, P, P, P, SZ, P]),
     "tsg_sag_encoder_bwd": (I, [P, P, P, P, P, P, P, SZ, P]),
     "tsg_sag_encoder_fwd_compact": (I, [P, P, P, P, P, P, P, P, P, SZ, P]),

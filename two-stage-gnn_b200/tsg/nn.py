@@ -108,6 +108,24 @@ def host_level_ptrs(node_ptr: np.ndarray, ratio: float, levels: int = 3) -> np.n
     return out
 
 
+KEEP_ARENA = False        # tests: keep (shape, arena) of the last executor forward in LAST_ARENA
+LAST_ARENA = None
+SAG_FIELDS = {"perm": (0, torch.int64), "score": (1, torch.float32), "h": (2, torch.float32), "xg": (3, torch.float32),
+              "rowptr": (4, torch.int32), "colidx": (5, torch.int32), "val": (6, torch.float32), "inv": (7, torch.int32)}
+
+
+def sag_arena_view(shape, arena: torch.Tensor, level: int, field: str) -> torch.Tensor:
+    """A saved tensor of the executor's forward, viewed in place inside the arena (tsg_sag_arena_locate): what
+    SAGPool.forward returns besides x (Code/sag/layers.py:26: perm) and the level's CSR, for callers / parity tests."""
+    from . import _lib
+    code, dt = SAG_FIELDS[field]
+    off, nb = ctypes.c_size_t(), ctypes.c_size_t()
+    rc = _lib.lib.tsg_sag_arena_locate(ctypes.byref(shape), int(level), code, ctypes.byref(off), ctypes.byref(nb))
+    if rc != 0:
+        raise RuntimeError(f"tsg_sag_arena_locate failed: {_lib.last_error()}")
+    return arena[off.value:off.value + nb.value].view(dt)
+
+
 class _SagEncoderFn(torch.autograd.Function):
     """The three conv/pool/readout levels through the native executor (K10): two C-ABI calls per step
     instead of ~110.  Same kernels in the same order as the op-by-op path below."""
@@ -128,6 +146,9 @@ class _SagEncoderFn(torch.autograd.Function):
                   parr, _lib.ptr(z), _lib.ptr(arena), arena_bytes, _lib.stream_ptr())
         ctx.shape, ctx.arena, ctx.arena_bytes = shape, arena, arena_bytes
         ctx.save_for_backward(x, ptrs, *params)
+        if KEEP_ARENA:
+            global LAST_ARENA
+            LAST_ARENA = (shape, arena)
         return z
 
     @staticmethod
@@ -163,6 +184,9 @@ class _SagEncoderCompactFn(torch.autograd.Function):
                   _lib.ptr(cb.edge_ptr), _lib.ptr(ptrs), parr, _lib.ptr(z), _lib.ptr(arena), arena_bytes, _lib.stream_ptr())
         ctx.shape, ctx.arena, ctx.arena_bytes, ctx.label = shape, arena, arena_bytes, cb.label
         ctx.save_for_backward(ptrs, *params)
+        if KEEP_ARENA:
+            global LAST_ARENA
+            LAST_ARENA = (shape, arena)
         return z
 
     @staticmethod
