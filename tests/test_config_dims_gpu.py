@@ -78,6 +78,7 @@ def test_diffpool_config4_dims(cuda, tc):
         p64["assign_pred.bias"] = _dbl(d["param/assign_pred_modules.0.bias"])
         o64, _ = D.soft_pool_readout(padded(d["x"], N).double(), adj.double(), [n], p64)
         (o64 * d["cot"].double()).sum().backward()
+        fwd_noise = rel_err(d["readout"], o64)          # the reference's fp32 noise on a well-conditioned quantity
         g64 = {"assign_pred_modules.0.weight": p64["assign_pred.weight"].grad, "assign_pred_modules.0.bias": p64["assign_pred.bias"].grad}
         for key, (f, b, l) in names.items():
             for c, nm in zip(p64[key], conv_names(f, b, l, L)):
@@ -85,7 +86,7 @@ def test_diffpool_config4_dims(cuda, tc):
         checked = 0
         for k, p in model.named_parameters():
             if "grad/" + k in d:
-                grad_check(p.grad, d["grad/" + k], g64.get(k), TOL, f"tc={tc} {k}"); checked += 1
+                grad_check(p.grad, d["grad/" + k], g64.get(k), TOL, f"tc={tc} {k}", fwd_noise); checked += 1
         assert checked >= 20
     finally:
         ops.USE_TCGEN05 = True

@@ -67,7 +67,7 @@ def test_graphconv_and_bn_patch(cuda, add_self):
     out = dense_patch.apply_bn(None, torch.relu(dense_patch.graphconv_forward(me, x.to(cuda), adj.to(cuda))))
     (out * cot.to(cuda)).sum().backward()
     assert rel_err(out, ref) <= TOL
-    assert rel_err(me.weight.grad, wo.grad) <= 2e-5 and rel_err(me.bias.grad, bo.grad) <= 2e-5
+    assert rel_err(me.weight.grad, wo.grad) <= 1e-5 and rel_err(me.bias.grad, bo.grad) <= 1e-5
 
 
 @pytest.mark.gpu
@@ -88,7 +88,7 @@ def test_dgathead_patch_with_padding_and_isolated_nodes(cuda, concat):
     (out * cot.to(cuda)).sum().backward()
     assert out.shape == ref.shape
     assert rel_err(out, ref) <= TOL
-    assert rel_err(me.w.grad, wo.grad) <= 2e-5 and rel_err(me.a.grad, ao.grad) <= 2e-5
+    assert rel_err(me.w.grad, wo.grad) <= 1e-5 and rel_err(me.a.grad, ao.grad) <= 1e-5
 
 
 @pytest.mark.gpu
@@ -160,7 +160,7 @@ def test_softpool_under_the_patch_trains_the_assignment_tower(cuda):
     for k, p in P.items():
         if "grad/" + k in d:
             assert p.grad is not None, f"{k}: no gradient reached it through the patched GraphConv"
-            assert rel_err(p.grad, d["grad/" + k]) <= 3e-5, k
+            assert rel_err(p.grad, d["grad/" + k]) <= 1e-5, k
             checked += k.startswith("assign_")
     assert checked >= 2 * L + 2
     assert len(dense_patch.CACHE.items) <= dense_patch.CACHE.slots

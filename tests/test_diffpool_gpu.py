@@ -91,7 +91,7 @@ def test_diffpool_matches_reference_fixture(cuda, tc):
         assert rel_err(ypred, d["ypred"]) <= TOL
         for k, p in model.named_parameters():
             if "grad/" + k in d:
-                assert rel_err(p.grad, d["grad/" + k]) <= 3e-5, k
+                assert rel_err(p.grad, d["grad/" + k]) <= 1e-5, k
     finally:
         ops.USE_TCGEN05 = True
 
@@ -132,9 +132,9 @@ def test_diffpool_dd_shape_vs_oracle(cuda):
     out = model.readout(dense.pack_rows(x.to(cuda), ns), csr, gptr, has_pad)
     (out * cot.to(cuda)).sum().backward()
     assert rel_err(out, ref) <= TOL
-    assert rel_err(model.conv_first.weight.grad, p["conv"][0]["weight"].grad) <= 3e-5
-    assert rel_err(model.assign_pred_modules[0].weight.grad, p["assign_pred.weight"].grad) <= 3e-5
-    assert rel_err(model.conv_first_after_pool[0].weight.grad, p["conv_after"][0]["weight"].grad) <= 3e-5
+    assert rel_err(model.conv_first.weight.grad, p["conv"][0]["weight"].grad) <= 1e-5
+    assert rel_err(model.assign_pred_modules[0].weight.grad, p["assign_pred.weight"].grad) <= 1e-5
+    assert rel_err(model.conv_first_after_pool[0].weight.grad, p["conv_after"][0]["weight"].grad) <= 1e-5
 
 
 @pytest.mark.parametrize("k,m", [(164, 100), (128, 64), (96, 300)])

@@ -72,7 +72,8 @@ def main(argv=None) -> None:
     install(os.path.dirname(script))
     patch_dense_modules(os.path.dirname(script))
     sys.argv = [script] + argv[1:]
-    os.chdir(os.path.dirname(script)) if os.access(os.path.dirname(script), os.W_OK) else None
+    # the working directory stays the caller's: the scripts' relative paths (`data/<NAME>`, `latest.pth`) resolve
+    # exactly as under `python train.py` run from that directory
     runpy.run_path(script, run_name="__main__")
 
 
