@@ -116,3 +116,17 @@ def test_drop_in_ops_like_layers_py(cuda, shim):
     assert rel_err(out, ref) <= 1e-5
     out.sum().backward()
     assert conv.weight.grad is not None and score_layer.weight.grad is not None
+
+
+@pytest.mark.gpu
+def test_device_hygiene_shims_on_cuda(shim, cuda):
+    """What Code/sag/train_triplet.py:104-130 does on a GPU box: CPU embeddings into a CUDA MLP, CPU target into
+    cross_entropy, CUDA prediction compared with a CPU label, .numpy() on a CUDA tensor."""
+    import torch.nn.functional as F
+    m = torch.nn.Sequential(torch.nn.Linear(3, 2).to(cuda))
+    out = m(torch.randn(3))
+    assert out.is_cuda
+    loss = F.cross_entropy(out.unsqueeze(0), torch.LongTensor([1]))
+    loss.backward()
+    assert out.argmax(dim=0).eq(torch.Tensor([1.0])).sum().item() in (0, 1)
+    assert out.numpy().shape == (2,)

@@ -45,3 +45,18 @@ def load(prefix: str, mode: str = "pyg", max_nodes: int = 0) -> Tuple[Corpus, Op
         _lib.lib.tsg_tu_free(h)
     name = os.path.basename(prefix)
     return Corpus(name, node_ptr, edge_ptr, row, col, label, y, max(L, 1)), attr, C
+
+
+def write(corpus: Corpus, root: str, name: str) -> str:
+    """Export a Corpus in the TU text format (<root>/<name>/<name>_{A,graph_indicator,graph_labels,node_labels}.txt,
+    1-based global node ids, one directed edge per line): the inverse of `load`, used to hand synthetic corpora to the
+    UNMODIFIED reference scripts through their own loaders (tests/test_launcher.py).  Returns the file prefix."""
+    d = os.path.join(root, name)
+    os.makedirs(d, exist_ok=True)
+    prefix = os.path.join(d, name)
+    off = np.repeat(corpus.node_ptr[:-1], np.diff(corpus.edge_ptr))
+    np.savetxt(prefix + "_A.txt", np.stack([corpus.row + off + 1, corpus.col + off + 1], 1), fmt="%d", delimiter=", ")
+    np.savetxt(prefix + "_graph_indicator.txt", np.repeat(np.arange(1, corpus.num_graphs + 1), np.diff(corpus.node_ptr)), fmt="%d")
+    np.savetxt(prefix + "_graph_labels.txt", corpus.y, fmt="%d")
+    np.savetxt(prefix + "_node_labels.txt", corpus.node_label, fmt="%d")
+    return prefix
