@@ -34,11 +34,18 @@ class DeviceCorpus:
         eptr = np.zeros(ids.shape[0] + 1, np.int64); np.cumsum(self.e[ids], out=eptr[1:])
         return ids, nptr, eptr
 
+    def _stage(self, ids_host: np.ndarray):
+        """ids + packed offsets of the chosen graphs as ONE small pinned upload: (meta on the device, B, nptr, eptr)."""
+        ids, nptr, eptr = self.offsets(ids_host)
+        meta = torch.from_numpy(np.concatenate([ids, nptr, eptr])).pin_memory().to(self.device, non_blocking=True)
+        return meta, ids.shape[0], nptr, eptr
+
     def pack(self, ids_host: np.ndarray):
         """-> (x [sum n, F] f32, edge_index [2, sum E] i64, node_ptr_host).  One small H2D (ids + offsets)."""
-        ids, nptr, eptr = self.offsets(ids_host)
-        B = ids.shape[0]
-        meta = torch.from_numpy(np.concatenate([ids, nptr, eptr])).pin_memory().to(self.device, non_blocking=True)
+        return self.pack_staged(*self._stage(ids_host))
+
+    def pack_staged(self, meta: torch.Tensor, B: int, nptr: np.ndarray, eptr: np.ndarray):
+        """`pack` when ids + offsets are already on the device (`meta` = [ids | nptr | eptr], int64)."""
         d_ids, d_nptr, d_eptr = meta[:B], meta[B:2 * B + 1], meta[2 * B + 1:]
         N, E = int(nptr[-1]), int(eptr[-1])
         x = torch.empty(N, self.feat, dtype=torch.float32, device=self.device)
@@ -51,12 +58,12 @@ class DeviceCorpus:
     def pack_compact(self, ids_host: np.ndarray):
         """-> (ops.CompactBatch, node_ptr_host): labels + graph-local int32 endpoints of the chosen graphs, gathered
         on the GPU (4N + 8E bytes written; PackedSAGNet consumes the batch without expanding it)."""
+        return self.pack_compact_staged(*self._stage(ids_host))
+
+    def pack_compact_staged(self, meta: torch.Tensor, B: int, nptr: np.ndarray, eptr: np.ndarray):
         from .ops import CompactBatch
         if self.label is None:
             raise RuntimeError("tsg: the compact batch form needs categorical node labels (corpus holds dense features)")
-        ids, nptr, eptr = self.offsets(ids_host)
-        B = ids.shape[0]
-        meta = torch.from_numpy(np.concatenate([ids, nptr, eptr])).pin_memory().to(self.device, non_blocking=True)
         d_ids, d_nptr, d_eptr = meta[:B], meta[B:2 * B + 1], meta[2 * B + 1:]
         N, E = int(nptr[-1]), int(eptr[-1])
         label = torch.empty(N, dtype=torch.int32, device=self.device)

@@ -111,6 +111,22 @@ class TripletTrainer:
         self.opt.step()
         return loss.detach()
 
+    def step_allgather(self, x, edge_index, node_ptr_host: np.ndarray, triplets_global: torch.Tensor) -> torch.Tensor:
+        """The north-star's formulation for triplets that CROSS ranks (the reference sampler draws positives and negatives
+        from the whole training set, Code/sag/triplet_sampler.py:36-56): every rank embeds its own M graphs, the
+        embeddings are all-gathered into [world * M, D] (row r * M + i = graph i of rank r), every rank evaluates the SAME
+        global loss over `triplets_global` [T_g, 3] (indices into the gathered matrix, identical on all ranks), backward
+        takes this rank's slice of d(loss)/d(embeddings), and one all-reduce(SUM) completes the parameter gradient."""
+        self.model.train()
+        emb = self.model(x, edge_index, node_ptr_host)
+        emb_g = all_gather_rows(emb, self.group)
+        loss, _, _ = ops.triplet_loss(emb_g, triplets_global, self.margin)
+        self.opt.zero_grad(set_to_none=True)
+        loss.backward()
+        all_reduce_grads(list(self.model.parameters()), self.group)
+        self.opt.step()
+        return loss.detach()
+
     def step_from_host(self, x_host: torch.Tensor, edge_index_host: torch.Tensor,
                        node_ptr_host: np.ndarray, triplets_host: torch.Tensor, device) -> float:
         """End-to-end call with (pinned) HOST buffers: H2D copies, the step, and the loss read back."""
@@ -213,6 +229,68 @@ class TripletTrainer:
             else:
                 x, ei = cb, None
             loss = self.step(x, ei, nptr, t["triplets"])
+            h = torch.empty((), dtype=torch.float32, pin_memory=True)
+            h.copy_(loss, non_blocking=True)
+            host_losses.append(h)
+        cur.synchronize()
+        return [float(h) for h in host_losses]
+
+    def run_from_ids(self, corpus, id_batches) -> list:
+        """Pipelined end-to-end loop against an HBM-resident corpus (tsg.feeder.DeviceCorpus): every step the host
+        provides only what a sampler produces -- the step's graph ids and its triplet index rows -- as
+        (graph_ids int64 numpy [B], triplets int64 pinned tensor [T, 3]).  Per step, INSIDE the loop: the packed
+        offsets of the chosen graphs are computed on the host (two cumsums over B sizes), ids + offsets + triplets go
+        up on the copy stream, the batch is assembled on the GPU from the resident corpus (K0 compact gather), the
+        training step runs, and the loss is read back into pinned memory without stalling the enqueue thread.
+        Nothing is pre-packed or cached across steps.  Returns the per-step losses."""
+        dev = corpus.device
+        cur = torch.cuda.current_stream(dev)
+        copy = getattr(self, "_copy_stream", None)
+        if copy is None:
+            copy = self._copy_stream = torch.cuda.Stream(dev)
+        compact = corpus.label is not None and getattr(self.model, "accepts_compact", False)
+
+        def stage(item):
+            ids_host, trip_host = item
+            ids, nptr, eptr = corpus.offsets(ids_host)
+            need = ids.shape[0] + nptr.shape[0] + eptr.shape[0]
+            slot = self._ring_pos = (getattr(self, "_ring_pos", -1) + 1) % 4
+            ring = self.__dict__.setdefault("_meta_ring", [None] * 4)
+            if ring[slot] is None or ring[slot][0].numel() < need:       # pinned staging ring: allocated once, reused
+                ring[slot] = [torch.empty(max(need, 1024), dtype=torch.int64, pin_memory=True), None]
+            buf, busy = ring[slot]
+            if busy is not None:
+                busy.synchronize()             # the upload issued from this slot four stages ago has left it
+            meta_h = buf[:need]
+            np.concatenate([ids, nptr, eptr], out=meta_h.numpy())
+            copy.wait_stream(cur)
+            with torch.cuda.stream(copy):
+                meta = meta_h.to(dev, non_blocking=True)
+                tr = trip_host.to(dev, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy)
+            ring[slot][1] = ev
+            return meta, tr, ids.shape[0], nptr, eptr, ev, meta_h
+
+        it = iter(id_batches)
+        try:
+            nxt = stage(next(it))
+        except StopIteration:
+            return []
+        host_losses = []
+        while nxt is not None:
+            meta, tr, B, nptr, eptr, ev, keep = nxt
+            try:
+                nxt = stage(next(it))
+            except StopIteration:
+                nxt = None
+            cur.wait_event(ev)
+            meta.record_stream(cur); tr.record_stream(cur)
+            if compact:
+                (x, _), ei = corpus.pack_compact_staged(meta, B, nptr, eptr), None
+            else:
+                x, ei, _ = corpus.pack_staged(meta, B, nptr, eptr)
+            loss = self.step(x, ei, nptr, tr)
             h = torch.empty((), dtype=torch.float32, pin_memory=True)
             h.copy_(loss, non_blocking=True)
             host_losses.append(h)
