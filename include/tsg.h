@@ -446,14 +446,28 @@ typedef struct {
   int64_t num_graphs, in_feat, hidden, num_edges;
   int64_t n[4];
   int64_t max_graph_nodes[3];
+  int64_t max_graph_edges;   /* max directed edges of one graph (host knows it from edge_ptr); 0 = unknown: the
+                                graph-resident kernels (K13) are not used */
+  double pooling_ratio;      /* SAGPool ratio (sizes the shared-memory classes of K13; level sizes themselves come from
+                                level_ptr) */
 } tsg_sag_shape;
 size_t tsg_sag_arena_bytes(const tsg_sag_shape* shape);
+/* tsg_sag_encoder_embed_compact (below) is the FORWARD-ONLY form of tsg_sag_encoder_fwd_compact: embeddings for the
+ * reference's evaluation loops (Code/sag/train_triplet.py:36-58,86-99 embed every graph without a backward).  It runs the
+ * graph-resident kernels (K13, k13_sag_fused.cu: one CTA carries one graph through all three levels in shared memory, one
+ * launch per size class instead of 36) when the shape allows it -- hidden in {32, 64, 128}, max_graph_edges given, per-graph
+ * working set within 227 KB of shared memory -- else the kernel-per-operator sequence.  z, and the perm / score / h the
+ * forward leaves in the arena, are bit-identical either way.  tsg_sag_set_fused(0) forces the operator sequence (A/B
+ * measurements, parity tests); returns the previous setting.  Initial value: environment TSG_SAG_FUSED (default 1). */
+int tsg_sag_set_fused(int on);
 /* Where the forward leaves a saved tensor inside the arena (a pure function of the shape): byte offset and size of
  * `field` of pooling level `level` (0..2).  What a caller needs to read back SAGPool.forward's other return values
  * (Code/sag/layers.py:26 returns perm; the parity tests assert it level by level).  perm: int64 [n[level+1]];
  * score / h / xg: fp32 [n], [n, hidden], [n[level+1], hidden]; CSR arrays: int32 / fp32 of the level's A_hat. */
 enum { TSG_SAG_PERM = 0, TSG_SAG_SCORE = 1, TSG_SAG_H = 2, TSG_SAG_XG = 3, TSG_SAG_ROWPTR = 4, TSG_SAG_COLIDX = 5,
-       TSG_SAG_VAL = 6, TSG_SAG_INV = 7 };
+       TSG_SAG_VAL = 6, TSG_SAG_INV = 7, TSG_SAG_STATUS = 8 /* int32: 0, or TSG_FUSED_* bits set by the graph-resident
+       kernels when a graph's edge list is not coalesced + symmetric (any level; XG / CSR fields are only filled by the
+       kernel-per-operator executor, TSG_SAG_FUSED=0) */ };
 int tsg_sag_arena_locate(const tsg_sag_shape* shape, int level, int field, size_t* offset, size_t* bytes);
 int tsg_sag_encoder_fwd(const tsg_sag_shape* shape, const float* x, const int64_t* row, const int64_t* col,
                         const int64_t* level_ptr, const float* const* params, float* z,
@@ -511,6 +525,9 @@ int tsg_sag_conv_bwd_fused(const float* dxo, const int32_t* inv, const float* sc
 int tsg_sag_encoder_fwd_compact(const tsg_sag_shape* shape, const int32_t* label, const int32_t* local_row,
                                 const int32_t* local_col, const int64_t* edge_ptr, const int64_t* level_ptr,
                                 const float* const* params, float* z, void* arena, size_t arena_bytes, void* stream);
+int tsg_sag_encoder_embed_compact(const tsg_sag_shape* shape, const int32_t* label, const int32_t* local_row,
+                                  const int32_t* local_col, const int64_t* edge_ptr, const int64_t* level_ptr,
+                                  const float* const* params, float* z, void* arena, size_t arena_bytes, void* stream);
 int tsg_sag_encoder_bwd_compact(const tsg_sag_shape* shape, const int32_t* label, const int64_t* level_ptr,
                                 const float* const* params, const float* dz, float* const* grads,
                                 void* arena, size_t arena_bytes, void* stream);

@@ -18,6 +18,7 @@
 //     out_l = [gmp(x_{l+1}) || gap(x_{l+1})]                  network.py:36,40,44
 //   z = out_0 + out_1 + out_2                                 network.py:46
 #include "common.cuh"
+#include "sag_fused.cuh"
 
 namespace tsg {
 
@@ -36,6 +37,8 @@ struct SagArena {
   // backward temporaries, sized for level 0 and reused by every level
   float *dxg, *dh, *dhm, *dxw, *dscore, *dsw;
   void* scratch; size_t scratch_bytes;
+  // graph-resident forward (k13_sag_fused.cu): scheduling counters + status word
+  unsigned* sched; int* status;
   size_t total;
 };
 
@@ -86,6 +89,8 @@ static void layout(const tsg_sag_shape* sh, void* arena, SagArena* a) {
   a->dscore = (float*)take(n0 * 4); a->dsw = (float*)take(n0 * 4);
   a->scratch_bytes = scratch_need(sh);
   a->scratch = take(a->scratch_bytes);
+  a->sched = (unsigned*)take(256);
+  a->status = (int*)((char*)a->sched + 128);
   a->total = off;
 }
 
@@ -110,6 +115,36 @@ static bool sag_unfused_env() {        // TSG_SAG_UNFUSED=1: the kernel-per-op b
   return v;
 }
 
+// TSG_SAG_FUSED=0 (or tsg_sag_set_fused(0)): the kernel-per-operator executor of round 1 (A/B runs, parity tests)
+static int g_sag_fused = -1;
+static bool sag_fused_env() {
+  if (g_sag_fused < 0) g_sag_fused = !(getenv("TSG_SAG_FUSED") && getenv("TSG_SAG_FUSED")[0] == '0');
+  return g_sag_fused != 0;
+}
+
+static bool use_fused(const tsg_sag_shape* sh, bool compact) {
+  if (!compact || !sag_fused_env() || sh->max_graph_edges <= 0) return false;
+  for (int l = 0; l < 3; ++l) if (sh->max_graph_nodes[l] > 32767) return false;
+  return fused_supported((int)sh->hidden, (int)sh->in_feat, (int)sh->max_graph_nodes[0], (int)sh->max_graph_nodes[1],
+                         (int)sh->max_graph_edges);
+}
+
+static void fill_fused(FusedArgs& f, const tsg_sag_shape* sh, const SagArena& a, const int32_t* label, const int32_t* lrow,
+                       const int32_t* lcol, const int64_t* edge_ptr, const int64_t* level_ptr, const float* const* params) {
+  f.G = (int)sh->num_graphs; f.L = (int)sh->in_feat; f.H = (int)sh->hidden;
+  for (int l = 0; l < 3; ++l) f.nmax[l] = (int)sh->max_graph_nodes[l];
+  f.emax = (int)sh->max_graph_edges;
+  f.ratio = (float)sh->pooling_ratio; f.avg_degree = (double)sh->num_edges / (double)(sh->n[0] > 0 ? sh->n[0] : 1);
+  f.cls = 0; f.cls_nlo = 0; f.cls_elo = -1;
+  f.label = label; f.lrow = lrow; f.lcol = lcol; f.edge_ptr = edge_ptr; f.level_ptr = level_ptr;
+  for (int i = 0; i < 12; ++i) f.params[i] = params[i];
+  for (int l = 0; l < 3; ++l) {
+    f.h[l] = a.lv[l].h; f.score[l] = a.lv[l].score; f.perm[l] = a.lv[l].perm; f.argmax[l] = a.lv[l].argmax;
+  }
+  f.z = nullptr;
+  f.sched = a.sched; f.status = a.status;
+}
+
 static bool shape_ok(const tsg_sag_shape* sh) {
   if (!sh || sh->num_graphs <= 0 || sh->in_feat <= 0 || sh->hidden <= 0 || sh->num_edges < 0) return false;
   for (int l = 0; l < 4; ++l) if (sh->n[l] <= 0) return false;
@@ -126,6 +161,12 @@ using namespace tsg;
     int _rc = (call);                 \
     if (_rc != TSG_OK) return _rc;    \
   } while (0)
+
+extern "C" int tsg_sag_set_fused(int on) {
+  const int prev = sag_fused_env() ? 1 : 0;
+  g_sag_fused = on ? 1 : 0;
+  return prev;
+}
 
 extern "C" size_t tsg_sag_arena_bytes(const tsg_sag_shape* shape) {
   if (!shape_ok(shape)) return 0;
@@ -151,6 +192,7 @@ extern "C" int tsg_sag_arena_locate(const tsg_sag_shape* sh, int level, int fiel
     case TSG_SAG_COLIDX: p = b.colidx; sz = (size_t)(sh->num_edges + n) * 4; break;
     case TSG_SAG_VAL: p = b.val; sz = (size_t)(sh->num_edges + n) * 4; break;
     case TSG_SAG_INV: p = b.inv; sz = (size_t)n * 4; break;
+    case TSG_SAG_STATUS: p = a.status; sz = 4; break;
     default: set_error("sag_arena_locate: unknown field %d", field); return TSG_EINVAL;
   }
   *offset = (size_t)((const char*)p - base);
@@ -159,12 +201,21 @@ extern "C" int tsg_sag_arena_locate(const tsg_sag_shape* sh, int level, int fiel
 }
 
 static int sag_fwd(const tsg_sag_shape* sh, const SagInput& in, const int64_t* level_ptr, const float* const* params,
-                   float* z, void* arena, size_t arena_bytes, void* stream) {
+                   float* z, void* arena, size_t arena_bytes, void* stream, bool forward_only = false) {
   SagArena a;
   layout(sh, arena, &a);
   if (arena_bytes < a.total) { set_error("sag_encoder_fwd: arena too small (%zu < %zu)", arena_bytes, a.total); return TSG_EWORKSPACE; }
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t G = sh->num_graphs, H = sh->hidden, E = sh->num_edges;
+  // graph-resident path (K13): the whole encoder forward in one kernel per size class.  Forward only: it keeps every
+  // intermediate in shared memory, while the backward below consumes the per-level CSRs / gated rows from the arena.
+  if (forward_only && use_fused(sh, in.label != nullptr)) {
+    FusedArgs f;
+    fill_fused(f, sh, a, in.label, in.lrow, in.lcol, in.edge_ptr, level_ptr, params);
+    f.z = z;
+    cudaMemsetAsync(a.status, 0, sizeof(int), st);
+    return launch_sag_fused_fwd(f, st);
+  }
   const float* xin = in.x;
   for (int l = 0; l < 3; ++l) {
     LevelBuf& b = a.lv[l];
@@ -235,6 +286,20 @@ extern "C" int tsg_sag_encoder_fwd_compact(const tsg_sag_shape* sh, const int32_
               (long long)sh->in_feat, (long long)sh->hidden);
   const SagInput in{nullptr, nullptr, nullptr, label, local_row, local_col, edge_ptr};
   return sag_fwd(sh, in, level_ptr, params, z, arena, arena_bytes, stream);
+}
+
+extern "C" int tsg_sag_encoder_embed_compact(const tsg_sag_shape* sh, const int32_t* label, const int32_t* local_row,
+                                             const int32_t* local_col, const int64_t* edge_ptr, const int64_t* level_ptr,
+                                             const float* const* params, float* z, void* arena, size_t arena_bytes,
+                                             void* stream) {
+  TSG_REQUIRE(shape_ok(sh), "sag_encoder_embed_compact: bad shape");
+  TSG_REQUIRE(label && edge_ptr && level_ptr && params && z && arena && (sh->num_edges == 0 || (local_row && local_col)),
+              "sag_encoder_embed_compact: null pointer");
+  TSG_REQUIRE(tsg_embed_bwd_weight_workspace_bytes(sh->in_feat, sh->hidden) > 0,
+              "sag_encoder_embed_compact: %lld labels x %lld hidden does not fit the label-table kernels; expand with tsg_pack_batch",
+              (long long)sh->in_feat, (long long)sh->hidden);
+  const SagInput in{nullptr, nullptr, nullptr, label, local_row, local_col, edge_ptr};
+  return sag_fwd(sh, in, level_ptr, params, z, arena, arena_bytes, stream, true);
 }
 
 static int sag_bwd(const tsg_sag_shape* sh, const SagInput& in, const int64_t* level_ptr, const float* const* params,

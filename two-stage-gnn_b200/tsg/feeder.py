@@ -70,7 +70,7 @@ class DeviceCorpus:
         rc = torch.empty(2, E, dtype=torch.int32, device=self.device)
         call("tsg_pack_batch_compact", ptr(d_ids), ptr(d_nptr), ptr(d_eptr), B, ptr(self.node_ptr), ptr(self.edge_ptr),
              ptr(self.row), ptr(self.col), ptr(self.label), ptr(label), ptr(rc[0]), ptr(rc[1]), stream_ptr())
-        return CompactBatch(label, rc[0], rc[1], d_nptr, d_eptr, self.feat), nptr
+        return CompactBatch(label, rc[0], rc[1], d_nptr, d_eptr, self.feat, int(np.diff(eptr).max()) if B else 0), nptr
 
 
 def compact_host_batch(corpus: Corpus, graph_ids, triplets: np.ndarray, pin: bool | None = None) -> dict:

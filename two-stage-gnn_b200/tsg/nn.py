@@ -110,7 +110,8 @@ def host_level_ptrs(node_ptr: np.ndarray, ratio: float, levels: int = 3) -> np.n
 
 KEEP_ARENA = False        # tests: keep (shape, arena) of the last executor forward in LAST_ARENA
 LAST_ARENA = None
-SAG_FIELDS = {"perm": (0, torch.int64), "score": (1, torch.float32), "h": (2, torch.float32), "xg": (3, torch.float32),
+PENDING_STATUS = []       # status words of graph-resident forwards not yet looked at (device int32 views)
+SAG_FIELDS = {"status": (8, torch.int32), "perm": (0, torch.int64), "score": (1, torch.float32), "h": (2, torch.float32), "xg": (3, torch.float32),
               "rowptr": (4, torch.int32), "colidx": (5, torch.int32), "val": (6, torch.float32), "inv": (7, torch.int32)}
 
 
@@ -124,6 +125,23 @@ def sag_arena_view(shape, arena: torch.Tensor, level: int, field: str) -> torch.
     if rc != 0:
         raise RuntimeError(f"tsg_sag_arena_locate failed: {_lib.last_error()}")
     return arena[off.value:off.value + nb.value].view(dt)
+
+
+def check_fused_status() -> None:
+    """Look at the status words the graph-resident kernels (K13) left since the last call -- ONE device read, so callers
+    do it where they synchronise anyway (loss read-back, end of a feeder loop, tests).  A non-zero word means a graph's
+    edge list was not what those kernels require (endpoints in range, no self loops, sorted by (row, col), symmetric:
+    the TUDataset / TU-loader form); its embedding was zeroed.  There is no silent fallback: this raises."""
+    global PENDING_STATUS
+    if not PENDING_STATUS:
+        return
+    words, PENDING_STATUS = PENDING_STATUS, []
+    bits = int(torch.stack([w.reshape(()) for w in words]).max().item()) if len(words) > 1 else int(words[0].item())
+    if bits:
+        names = [n for b, n in ((1, "edge endpoint out of range / self loop"), (2, "edge list not sorted by (row, col)"),
+                                (4, "edge list not symmetric")) if bits & b]
+        raise RuntimeError("tsg: the graph-resident SAGPool kernels rejected a graph (" + "; ".join(names) + "). Coalesce the "
+                           "edge lists (TUDataset form) or run with TSG_SAG_FUSED=0 (kernel-per-operator executor).")
 
 
 class _SagEncoderFn(torch.autograd.Function):
@@ -201,6 +219,30 @@ class _SagEncoderCompactFn(torch.autograd.Function):
                   _lib.ptr(dz), garr, _lib.ptr(ctx.arena), ctx.arena_bytes, _lib.stream_ptr())
         ctx.arena = None
         return (None, None, None, *grads)
+
+
+def _sag_embed_compact(cb, ptrs, shape, params):
+    """Forward-only encoder (torch.no_grad(): the evaluation loops of the reference scripts embed every graph and never
+    call backward): tsg_sag_encoder_embed_compact = the graph-resident kernels (K13) where the shape allows them."""
+    from . import _lib
+    dev = cb.label.device
+    params = [p.contiguous() for p in params]
+    arena_bytes = _lib.lib.tsg_sag_arena_bytes(ctypes.byref(shape))
+    if arena_bytes == 0:
+        raise RuntimeError("tsg: bad SAG encoder shape")
+    arena = torch.empty(arena_bytes, dtype=torch.uint8, device=dev)
+    z = torch.empty(shape.num_graphs, 2 * shape.hidden, dtype=torch.float32, device=dev)
+    parr = (ctypes.c_void_p * 12)(*[p.data_ptr() for p in params])
+    _lib.call("tsg_sag_encoder_embed_compact", ctypes.byref(shape), _lib.ptr(cb.label), _lib.ptr(cb.row), _lib.ptr(cb.col),
+              _lib.ptr(cb.edge_ptr), _lib.ptr(ptrs), parr, _lib.ptr(z), _lib.ptr(arena), arena_bytes, _lib.stream_ptr())
+    if shape.max_graph_edges > 0:
+        PENDING_STATUS.append(sag_arena_view(shape, arena, 0, "status"))
+        if len(PENDING_STATUS) > 64:
+            check_fused_status()
+    if KEEP_ARENA:
+        global LAST_ARENA
+        LAST_ARENA = (shape, arena)
+    return z
 
 
 class PackedSAGNet(torch.nn.Module):
@@ -292,6 +334,10 @@ class PackedSAGNet(torch.nn.Module):
         shape = self._sag_shape(plan, cb.num_labels, int(cb.row.shape[0]))
         if shape is None:
             return None
+        shape.max_graph_edges = int(cb.max_graph_edges)
+        shape.pooling_ratio = float(self.pooling_ratio)
+        if not torch.is_grad_enabled():
+            return _sag_embed_compact(cb, ptrs, shape, [p.detach() for p in self._encoder_params()])
         return _SagEncoderCompactFn.apply(cb, ptrs, shape, *self._encoder_params())
 
     def _level_plan(self, node_ptr_host, dev):

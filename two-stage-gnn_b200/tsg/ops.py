@@ -64,6 +64,7 @@ class CompactBatch:
     node_ptr: torch.Tensor
     edge_ptr: torch.Tensor
     num_labels: int
+    max_graph_edges: int = 0      # host-side max of diff(edge_ptr) (0 = unknown: the graph-resident kernels are not used)
 
     def expand(self) -> Tuple[torch.Tensor, torch.Tensor]:
         """(x [N, num_labels] fp32 one-hot, edge_index [2, E] int64 with batch-global ids) via tsg_pack_batch."""

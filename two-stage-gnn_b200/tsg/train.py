@@ -80,6 +80,11 @@ def all_reduce_grads_and_loss(params, loss_local: torch.Tensor, num_local: int, 
     return flat[-2]
 
 
+def _check_status():
+    from . import nn as _nn
+    _nn.check_fused_status()
+
+
 class TripletTrainer:
     """model: tsg.nn.PackedSAGNet (or any module with the same forward signature)."""
 
@@ -175,6 +180,7 @@ class TripletTrainer:
             h.copy_(loss, non_blocking=True)
             host_losses.append(h)
         cur.synchronize()
+        _check_status()
         return [float(h) for h in host_losses]
 
     def run_from_host_compact(self, host_batches, device, num_node_labels: int, expand: bool = False) -> list:
@@ -223,7 +229,8 @@ class TripletTrainer:
                 v.record_stream(cur)
             G, N, E = nptr.shape[0] - 1, int(nptr[-1]), int(eptr[-1])
             d_nptr, d_eptr = t["meta"][:G + 1], t["meta"][G + 1:]
-            cb = ops.CompactBatch(t["label"], t["row"], t["col"], d_nptr, d_eptr, num_node_labels)
+            cb = ops.CompactBatch(t["label"], t["row"], t["col"], d_nptr, d_eptr, num_node_labels,
+                                  int(np.diff(eptr).max()) if G else 0)
             if expand or not getattr(self.model, "accepts_compact", False):
                 x, ei = cb.expand()
             else:
@@ -233,6 +240,7 @@ class TripletTrainer:
             h.copy_(loss, non_blocking=True)
             host_losses.append(h)
         cur.synchronize()
+        _check_status()
         return [float(h) for h in host_losses]
 
     def run_from_ids(self, corpus, id_batches) -> list:
@@ -295,6 +303,7 @@ class TripletTrainer:
             h.copy_(loss, non_blocking=True)
             host_losses.append(h)
         cur.synchronize()
+        _check_status()
         return [float(h) for h in host_losses]
 
     def step_from_ids(self, corpus, graph_ids_host: np.ndarray, triplets_host: torch.Tensor) -> float:
@@ -305,4 +314,6 @@ class TripletTrainer:
         else:
             x, ei, nptr = corpus.pack(graph_ids_host)
         tr = triplets_host.to(corpus.device, non_blocking=True)
-        return float(self.step(x, ei, nptr, tr).item())
+        loss = float(self.step(x, ei, nptr, tr).item())
+        _check_status()
+        return loss
