@@ -83,6 +83,7 @@ def workload_name(a):
 def make_step_batches(a, rank: int, num_batches: int):
     from tsg import synth
     corpus = synth.make_corpus("DD", a.corpus, seed=777 + 1_000_003 * rank)
+    coalesced = synth.is_coalesced_symmetric(corpus)     # TUDataset form (checked once; the kernels re-verify per graph)
     out, compact, id_lists = [], [], []
     T = a.triplets
     tidx = np.stack([np.arange(T), T + np.arange(T), 2 * T + np.arange(T)], 1).astype(np.int64)
@@ -99,7 +100,7 @@ def make_step_batches(a, rank: int, num_batches: int):
                             row=torch.from_numpy(sel.row.astype(np.int32)).pin_memory(),
                             col=torch.from_numpy(sel.col.astype(np.int32)).pin_memory(),
                             node_ptr=sel.node_ptr.copy(), edge_ptr=sel.edge_ptr.copy(),
-                            triplets=torch.from_numpy(tidx).pin_memory()))
+                            triplets=torch.from_numpy(tidx).pin_memory(), coalesced=coalesced))
     return corpus, out, compact, id_lists
 
 
@@ -799,7 +800,8 @@ def main():
     rate = lambda ms, steps=a.steps: world * graphs_per_step * steps / (ms / 1000.0)
     t = lambda v: (torch.from_numpy(v) if isinstance(v, np.ndarray) else v).to(dev)
     dev_compact = [(ops.CompactBatch(t(c["label"]), t(c["row"]), t(c["col"]), t(c["node_ptr"]), t(c["edge_ptr"]),
-                                     corpus.num_node_labels), c["node_ptr"], b["triplets"]) for c, b in zip(compact, dev_batches)]
+                                     corpus.num_node_labels, int(np.diff(c["edge_ptr"]).max()), c["coalesced"]),
+                    c["node_ptr"], b["triplets"]) for c, b in zip(compact, dev_batches)]
 
     def step_wire(i):
         b = dev_batches[i % len(dev_batches)]

@@ -292,6 +292,12 @@ int tsg_topk_sizes(const int64_t* graph_ptr, int64_t num_graphs, float ratio, in
 int tsg_topk(const float* score, const int64_t* graph_ptr, const int64_t* k_ptr,
              int64_t num_graphs, int64_t num_nodes, int64_t* perm,
              void* workspace, size_t workspace_bytes, void* stream);
+/* tsg_topk with the caller's bound on the largest graph (host side, e.g. from the packer): size ranges that cannot be
+ * populated are not launched (n <= 1,024: register-run kernel; <= 4,096: shared-memory bitonic network; larger: rank
+ * selection).  tsg_topk == tsg_topk_bounded(..., max_graph_nodes = num_nodes). */
+int tsg_topk_bounded(const float* score, const int64_t* graph_ptr, const int64_t* k_ptr, int64_t num_graphs,
+                     int64_t num_nodes, int64_t max_graph_nodes, int64_t* perm, void* workspace, size_t workspace_bytes,
+                     void* stream);
 
 /* node offsets from a sorted batch vector: graph_ptr[g] = first i with batch[i] >= g. */
 int tsg_batch_to_ptr(const int64_t* batch, int64_t num_nodes, int64_t num_graphs,
@@ -430,6 +436,16 @@ int tsg_tu_fill(const tsg_tu_handle* h, int64_t* node_ptr, int64_t* edge_ptr, in
                 int32_t* node_label, int64_t* y, float* attr /*nullable*/);
 void tsg_tu_free(tsg_tu_handle* h);
 
+/* K1d: K1b for packed batches whose per-graph edge lists are coalesced and symmetric (sorted by (row, col), loop free,
+ * (r, c) listed <=> (c, r) listed).  One launch, no atomics, no scan, ONE orientation -- the src-major CSR of a symmetric
+ * operator is the same arrays.  rowptr [N+1], colidx / val [E+N]; bit-identical to tsg_csr_build_graphs_local's dst-major
+ * output.  The promise is verified per graph; violations OR TSG_FUSED_* bits (1 range / self loop, 2 order, 4 symmetry)
+ * into *status (device int32, zeroed by the caller) and leave that graph's rows unwritten. */
+int tsg_csr_build_graphs_sym_local(const int32_t* local_row, const int32_t* local_col, const int64_t* edge_ptr,
+                                   const int64_t* node_ptr, int64_t num_graphs, int64_t num_nodes, int64_t num_edges,
+                                   int64_t max_graph_nodes, int32_t* rowptr, int32_t* colidx, float* val,
+                                   int32_t* status, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * K10  native step executor for the SAGPool encoder
  *   replaces the Python-level sequencing of Code/sag/network.py:33-46 (`Net.forward` up to the sum
@@ -450,7 +466,16 @@ typedef struct {
                                 graph-resident kernels (K13) are not used */
   double pooling_ratio;      /* SAGPool ratio (sizes the shared-memory classes of K13; level sizes themselves come from
                                 level_ptr) */
+  int64_t flags;             /* TSG_SAG_COALESCED: the caller promises that every graph's edge list is sorted by (row, col),
+                                loop free and symmetric (TUDataset / TU loader / tsg.synth form).  The compact entries then
+                                build ONE CSR orientation per level (K1d, single-orientation K1c) and use it for both A_hat
+                                and its transpose.  The promise is VERIFIED on the device: a violation sets the arena's
+                                TSG_SAG_STATUS word (the caller must look at it where it synchronises) */
+  int32_t* status;           /* optional DEVICE int32 the verification bits are OR-ed into instead of the arena's own
+                                TSG_SAG_STATUS word (never cleared by the library: one persistent word can collect many
+                                steps and be read once); NULL = the arena's word, zeroed by every forward */
 } tsg_sag_shape;
+#define TSG_SAG_COALESCED 1
 size_t tsg_sag_arena_bytes(const tsg_sag_shape* shape);
 /* tsg_sag_encoder_embed_compact (below) is the FORWARD-ONLY form of tsg_sag_encoder_fwd_compact: embeddings for the
  * reference's evaluation loops (Code/sag/train_triplet.py:36-58,86-99 embed every graph without a backward).  It runs the

@@ -91,7 +91,13 @@ static void layout(const tsg_sag_shape* sh, void* arena, SagArena* a) {
   a->scratch = take(a->scratch_bytes);
   a->sched = (unsigned*)take(256);
   a->status = (int*)((char*)a->sched + 128);
+  if (sh->status && base) a->status = sh->status;      // caller-owned persistent status word
   a->total = off;
+  if (sh->flags & TSG_SAG_COALESCED)          // symmetric operators: the transposed CSR is the same arrays
+    for (int l = 0; l < 3; ++l) {
+      LevelBuf& b = a->lv[l];
+      b.t_rowptr = b.rowptr; b.t_colidx = b.colidx; b.t_val = b.val;
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -179,7 +185,9 @@ extern "C" int tsg_sag_arena_locate(const tsg_sag_shape* sh, int level, int fiel
   TSG_REQUIRE(shape_ok(sh) && level >= 0 && level < 3 && offset && bytes, "sag_arena_locate: bad argument");
   SagArena a;
   char* const base = (char*)256;            // any non-null base: only differences are used
-  layout(sh, base, &a);
+  tsg_sag_shape own = *sh;
+  own.status = nullptr;                     // the arena's own word, not the caller's
+  layout(&own, base, &a);
   const LevelBuf& b = a.lv[level];
   const int64_t n = sh->n[level], k = sh->n[level + 1], H = sh->hidden;
   const void* p = nullptr; size_t sz = 0;
@@ -207,13 +215,13 @@ static int sag_fwd(const tsg_sag_shape* sh, const SagInput& in, const int64_t* l
   if (arena_bytes < a.total) { set_error("sag_encoder_fwd: arena too small (%zu < %zu)", arena_bytes, a.total); return TSG_EWORKSPACE; }
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t G = sh->num_graphs, H = sh->hidden, E = sh->num_edges;
+  if (!sh->status) cudaMemsetAsync(a.status, 0, sizeof(int), st);       // every path leaves a defined status word
   // graph-resident path (K13): the whole encoder forward in one kernel per size class.  Forward only: it keeps every
   // intermediate in shared memory, while the backward below consumes the per-level CSRs / gated rows from the arena.
   if (forward_only && use_fused(sh, in.label != nullptr)) {
     FusedArgs f;
     fill_fused(f, sh, a, in.label, in.lrow, in.lcol, in.edge_ptr, level_ptr, params);
     f.z = z;
-    cudaMemsetAsync(a.status, 0, sizeof(int), st);
     return launch_sag_fused_fwd(f, st);
   }
   const float* xin = in.x;
@@ -223,7 +231,11 @@ static int sag_fwd(const tsg_sag_shape* sh, const SagInput& in, const int64_t* l
     const float *W = params[4 * l], *bias = params[4 * l + 1], *ws = params[4 * l + 2], *bs = params[4 * l + 3];
     const int64_t* ptr_l = level_ptr + (size_t)l * (G + 1);
     const int64_t* ptr_n = level_ptr + (size_t)(l + 1) * (G + 1);
-    if (l == 0 && in.label) {
+    const bool sym = in.label && (sh->flags & TSG_SAG_COALESCED);
+    if (l == 0 && sym) {
+      TSG_TRY(tsg_csr_build_graphs_sym_local(in.lrow, in.lcol, in.edge_ptr, ptr_l, G, n, E, sh->max_graph_nodes[l], b.rowptr,
+                                             b.colidx, b.val, a.status, stream));
+    } else if (l == 0 && in.label) {
       TSG_TRY(tsg_csr_build_graphs_local(in.lrow, in.lcol, in.edge_ptr, ptr_l, G, n, E, sh->max_graph_nodes[l], b.rowptr,
                                          b.colidx, b.val, nullptr, b.t_rowptr, b.t_colidx, b.t_val, nullptr, a.scratch,
                                          a.scratch_bytes, stream));
@@ -233,8 +245,10 @@ static int sag_fwd(const tsg_sag_shape* sh, const SagInput& in, const int64_t* l
                                    nullptr, b.t_rowptr, b.t_colidx, b.t_val, nullptr, a.scratch, a.scratch_bytes, stream));
     } else {        // K1c: the pooled level's CSR straight from the previous level's CSR, perm and inv
       const LevelBuf& pb = a.lv[l - 1];
-      TSG_TRY(tsg_csr_filter(pb.rowptr, pb.colidx, pb.t_rowptr, pb.t_colidx, pb.perm, pb.inv, n, b.rowptr, b.colidx, b.val,
-                             b.t_rowptr, b.t_colidx, b.t_val, a.scratch, a.scratch_bytes, stream));
+      if (sym) TSG_TRY(tsg_csr_filter(pb.rowptr, pb.colidx, nullptr, nullptr, pb.perm, pb.inv, n, b.rowptr, b.colidx, b.val,
+                                      nullptr, nullptr, nullptr, a.scratch, a.scratch_bytes, stream));
+      else TSG_TRY(tsg_csr_filter(pb.rowptr, pb.colidx, pb.t_rowptr, pb.t_colidx, pb.perm, pb.inv, n, b.rowptr, b.colidx, b.val,
+                                  b.t_rowptr, b.t_colidx, b.t_val, a.scratch, a.scratch_bytes, stream));
     }
     static const bool no_label_spmm = getenv("TSG_NO_LABEL_SPMM") != nullptr;
     const bool label_spmm = l == 0 && in.label && H % 4 == 0 && H <= 128 && !no_label_spmm &&
@@ -249,7 +263,7 @@ static int sag_fwd(const tsg_sag_shape* sh, const SagInput& in, const int64_t* l
       TSG_TRY(tsg_spmm_dot(b.rowptr, b.colidx, b.val, b.xw, bias, b.h, ws, b.sw, n, H, TSG_SPMM_RELU, stream));
     }
     TSG_TRY(tsg_spmm(b.rowptr, b.colidx, b.val, b.sw, bs, b.score, n, 1, 0, stream));
-    TSG_TRY(tsg_topk(b.score, ptr_l, ptr_n, G, n, b.perm, a.scratch, a.scratch_bytes, stream));
+    TSG_TRY(tsg_topk_bounded(b.score, ptr_l, ptr_n, G, n, sh->max_graph_nodes[l], b.perm, a.scratch, a.scratch_bytes, stream));
     TSG_TRY(tsg_inv_perm(b.perm, k, n, b.inv, stream));            // filter_adj's relabelling table (layers.py:23)
     static const bool no_gr = getenv("TSG_NO_GATE_READOUT") != nullptr;
     if (H % 4 == 0 && !sag_unfused_env() && !no_gr) {       // gate + readout in one pass (the gated rows are not read back)

@@ -24,8 +24,8 @@ __global__ void k_inv_perm32(const int64_t* __restrict__ perm, int64_t k, int* _
 __global__ void __launch_bounds__(256)
 k_csrf_count(const int* __restrict__ rowptr, const int* __restrict__ colidx, const int* __restrict__ t_rowptr,
              const int* __restrict__ t_colidx, const int64_t* __restrict__ perm, const int* __restrict__ inv,
-             int k, int* __restrict__ cnt) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * k; i += gridDim.x * blockDim.x) {
+             int k, int* __restrict__ cnt, int halves) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < halves * k; i += gridDim.x * blockDim.x) {
     const bool tr = i >= k;
     const int r = (int)perm[tr ? i - k : i];
     const int* rp = tr ? t_rowptr : rowptr;
@@ -44,9 +44,9 @@ k_csrf_write(const int* __restrict__ rowptr, const int* __restrict__ colidx, con
              const int* __restrict__ t_colidx, const int64_t* __restrict__ perm, const int* __restrict__ inv,
              int k, const int* __restrict__ cnt, const int* __restrict__ off,
              int* __restrict__ n_rowptr, int* __restrict__ n_colidx, float* __restrict__ n_val,
-             int* __restrict__ nt_rowptr, int* __restrict__ nt_colidx, float* __restrict__ nt_val) {
+             int* __restrict__ nt_rowptr, int* __restrict__ nt_colidx, float* __restrict__ nt_val, int halves) {
   const int half = off[k];
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * k; i += gridDim.x * blockDim.x) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < halves * k; i += gridDim.x * blockDim.x) {
     const bool tr = i >= k;
     const int row = tr ? i - k : i;
     const int r = (int)perm[row];
@@ -92,8 +92,12 @@ extern "C" int tsg_csr_filter(const int32_t* rowptr, const int32_t* colidx, cons
                               int32_t* out_t_rowptr, int32_t* out_t_colidx, float* out_t_val,
                               void* workspace, size_t workspace_bytes, void* stream) {
   TSG_REQUIRE(num_perm > 0 && num_perm < (int64_t)0x3fffffff, "csr_filter: bad row count");
-  TSG_REQUIRE(rowptr && colidx && t_rowptr && t_colidx && perm && inv_perm && out_rowptr && out_colidx && out_val &&
-              out_t_rowptr && out_t_colidx && out_t_val, "csr_filter: null pointer");
+  // symmetric operators (the src-major CSR is the same arrays as the dst-major one: K1d): pass NULL for every
+  // transposed pointer and only one orientation is counted, scanned and written
+  const bool sym = !t_rowptr && !t_colidx && !out_t_rowptr && !out_t_colidx && !out_t_val;
+  TSG_REQUIRE(rowptr && colidx && perm && inv_perm && out_rowptr && out_colidx && out_val &&
+              (sym || (t_rowptr && t_colidx && out_t_rowptr && out_t_colidx && out_t_val)), "csr_filter: null pointer");
+  const int halves = sym ? 1 : 2;
   if (workspace_bytes < tsg_csr_filter_workspace_bytes(num_perm)) { set_error("csr_filter: workspace too small"); return TSG_EWORKSPACE; }
   cudaStream_t st = (cudaStream_t)stream;
   Workspace ws(workspace, workspace_bytes);
@@ -101,11 +105,11 @@ extern "C" int tsg_csr_filter(const int32_t* rowptr, const int32_t* colidx, cons
   int* cnt = ws.take<int>(2 * num_perm + 2);
   int* off = ws.take<int>(2 * num_perm + 2);
   int* scan_ws = ws.take<int>(scan_ws_ints(2 * num_perm + 1));
-  const int grid = grid_for(2 * num_perm, 256);
-  k_csrf_count<<<grid, 256, 0, st>>>(rowptr, colidx, t_rowptr, t_colidx, perm, inv_perm, k, cnt);
-  int rc = exclusive_scan(CsrfCnt{cnt}, 2 * num_perm, off, scan_ws, st);
+  const int grid = grid_for(halves * num_perm, 256);
+  k_csrf_count<<<grid, 256, 0, st>>>(rowptr, colidx, t_rowptr, t_colidx, perm, inv_perm, k, cnt, halves);
+  int rc = exclusive_scan(CsrfCnt{cnt}, halves * num_perm, off, scan_ws, st);
   if (rc) return rc;
   k_csrf_write<<<grid, 256, 0, st>>>(rowptr, colidx, t_rowptr, t_colidx, perm, inv_perm, k, cnt, off,
-                                     out_rowptr, out_colidx, out_val, out_t_rowptr, out_t_colidx, out_t_val);
+                                     out_rowptr, out_colidx, out_val, out_t_rowptr, out_t_colidx, out_t_val, halves);
   return check_launch("csr_filter");
 }

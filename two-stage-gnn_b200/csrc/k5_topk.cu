@@ -77,7 +77,7 @@ k_topk_rank(const float* __restrict__ score, const int64_t* __restrict__ gptr,
 constexpr int TOPK_SORT_THREADS = 256;
 __global__ void __launch_bounds__(TOPK_SORT_THREADS)
 k_topk_sort(const float* __restrict__ score, const int64_t* __restrict__ gptr, const int64_t* __restrict__ kptr,
-            int64_t* __restrict__ perm, int max_pad) {
+            int64_t* __restrict__ perm, int max_pad, int min_n) {
   extern __shared__ __align__(16) unsigned long long sk[];
   {
     const int g = blockIdx.x;
@@ -87,6 +87,7 @@ k_topk_sort(const float* __restrict__ score, const int64_t* __restrict__ gptr, c
     const int k = (int)(kptr[g + 1] - obase);
     if (n == 0 || k == 0) return;
     if (n > max_pad) return;                       // handled by k_topk_rank (second launch skips the rest)
+    if (n <= min_n) return;                        // handled by k_topk_runs
     int npad = 32; while (npad < n) npad <<= 1;
     for (int i = threadIdx.x; i < npad; i += TOPK_SORT_THREADS)
       sk[i] = i < n ? (((unsigned long long)score_key(score[base + i]) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i)) : 0ull;
@@ -105,6 +106,89 @@ k_topk_sort(const float* __restrict__ score, const int64_t* __restrict__ gptr, c
     }
     for (int i = threadIdx.x; i < k; i += TOPK_SORT_THREADS)
       perm[obase + i] = base + (int64_t)(0xFFFFFFFFu - (unsigned)(sk[i] & 0xFFFFFFFFull));
+  }
+}
+
+
+// Register-run top-k (round 2): graphs of n <= TOPK_RUN_THREADS * 4 keys.  Every warp sorts its own run of 32 * KPT
+// composite keys in REGISTERS (element e = slot * 32 + lane: strides < 32 are shuffles, strides >= 32 register swaps,
+// no barrier), the runs go to shared memory, and a key's rank in the union is its position in its own run plus, for
+// every other run, the number of keys greater than it (binary search; keys are distinct).  Two CTA barriers instead of
+// the 45 of the 512-key network above; identical perm (the order is the same strict total order).
+constexpr int TOPK_RUN_THREADS = 256;
+template <int KPT>
+__device__ __forceinline__ void topk_runs_body(const float* __restrict__ score, int64_t base, int n, int k,
+                                               int64_t obase, int64_t* __restrict__ perm, unsigned long long* runs) {
+  constexpr int NW = TOPK_RUN_THREADS / 32, RL = 32 * KPT;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  unsigned long long key[KPT];
+#pragma unroll
+  for (int s = 0; s < KPT; ++s) {
+    const int i = w * RL + s * 32 + lane;
+    key[s] = i < n ? (((unsigned long long)score_key(score[base + i]) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i)) : 0ull;
+  }
+#pragma unroll
+  for (int kk = 2; kk <= RL; kk <<= 1) {
+#pragma unroll
+    for (int j = kk >> 1; j > 0; j >>= 1) {
+      if (j >= 32) {
+        const int js = j >> 5;
+#pragma unroll
+        for (int s = 0; s < KPT; ++s) {
+          if ((s & js) == 0) {
+            const bool desc = ((s * 32 + lane) & kk) == 0;
+            const unsigned long long x = key[s], y = key[s | js];
+            if ((x < y) == desc) { key[s] = y; key[s | js] = x; }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int s = 0; s < KPT; ++s) {
+          const unsigned long long x = key[s];
+          const unsigned long long y = __shfl_xor_sync(0xffffffffu, x, j);
+          const bool keep_max = ((lane & j) == 0) == ((((s * 32 + lane) & kk)) == 0);
+          key[s] = keep_max ? (x > y ? x : y) : (x < y ? x : y);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < KPT; ++s) runs[w * RL + s * 32 + lane] = key[s];
+  __syncthreads();
+#pragma unroll
+  for (int s = 0; s < KPT; ++s) {
+    const unsigned long long x = key[s];
+    if (x == 0ull) continue;                                // padding
+    int rank = s * 32 + lane;
+    for (int r = 0; r < NW && r * RL < n; ++r) {
+      if (r == w) continue;
+      const unsigned long long* run = runs + r * RL;
+      int lo = 0, hi = RL;                                  // first position whose key is < x (descending run)
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (run[mid] > x) lo = mid + 1; else hi = mid;
+      }
+      rank += lo;
+    }
+    if (rank < k) perm[obase + rank] = base + (int64_t)(0xFFFFFFFFu - (unsigned)(x & 0xFFFFFFFFull));
+  }
+}
+
+__global__ void __launch_bounds__(TOPK_RUN_THREADS)
+k_topk_runs(const float* __restrict__ score, const int64_t* __restrict__ gptr, const int64_t* __restrict__ kptr,
+            int64_t* __restrict__ perm, int G) {
+  __shared__ __align__(16) unsigned long long runs[TOPK_RUN_THREADS * 4];
+  for (int g = blockIdx.x; g < G; g += gridDim.x) {
+    const int64_t base = gptr[g];
+    const int n = (int)(gptr[g + 1] - base);
+    const int64_t obase = kptr[g];
+    const int k = (int)(kptr[g + 1] - obase);
+    if (n > 0 && k > 0 && n <= TOPK_RUN_THREADS * 4) {
+      if (n <= TOPK_RUN_THREADS) topk_runs_body<1>(score, base, n, k, obase, perm, runs);
+      else if (n <= 2 * TOPK_RUN_THREADS) topk_runs_body<2>(score, base, n, k, obase, perm, runs);
+      else topk_runs_body<4>(score, base, n, k, obase, perm, runs);
+    }
+    __syncthreads();                                        // runs[] is reused by the next graph
   }
 }
 
@@ -357,6 +441,12 @@ extern "C" int tsg_topk_sizes(const int64_t* gptr, int64_t G, float ratio, int64
 
 extern "C" int tsg_topk(const float* score, const int64_t* gptr, const int64_t* kptr, int64_t G,
                         int64_t N, int64_t* perm, void* workspace, size_t workspace_bytes, void* stream) {
+  return tsg_topk_bounded(score, gptr, kptr, G, N, N, perm, workspace, workspace_bytes, stream);
+}
+
+extern "C" int tsg_topk_bounded(const float* score, const int64_t* gptr, const int64_t* kptr, int64_t G, int64_t N,
+                                int64_t max_graph_nodes, int64_t* perm, void* workspace, size_t workspace_bytes,
+                                void* stream) {
   TSG_REQUIRE(G >= 0 && N >= 0, "topk: bad sizes");
   if (G == 0 || N == 0) return TSG_OK;
   TSG_REQUIRE(score && gptr && kptr && perm, "topk: null pointer");
@@ -366,11 +456,19 @@ extern "C" int tsg_topk(const float* score, const int64_t* gptr, const int64_t* 
   unsigned long long* gkeys = ws.take<unsigned long long>(N + 1);
   TSG_REQUIRE(G < (int64_t)0x7fffffff, "topk: too many graphs");
   static const bool no_sort = getenv("TSG_TOPK_NOSORT") != nullptr;
+  static const bool no_runs = getenv("TSG_TOPK_NORUNS") != nullptr;      // A/B: round 1's shared-memory bitonic network only
   const int max_pad = no_sort ? 0 : TOPK_SMEM_KEYS;
-  if (!no_sort)
-    k_topk_sort<<<(int)G, TOPK_SORT_THREADS, (size_t)TOPK_SMEM_KEYS * 8, (cudaStream_t)stream>>>(score, gptr, kptr, perm, max_pad);
+  const int runs_upto = (no_sort || no_runs) ? 0 : TOPK_RUN_THREADS * 4;
+  if (runs_upto > 0) {
+    const int grid = (int)(G < (int64_t)TSG_NUM_SMS * 8 ? G : (int64_t)TSG_NUM_SMS * 8);
+    k_topk_runs<<<grid, TOPK_RUN_THREADS, 0, (cudaStream_t)stream>>>(score, gptr, kptr, perm, (int)G);
+  }
+  // the caller's bound on the largest graph decides which of the three size ranges can be populated at all
+  if (!no_sort && max_graph_nodes > runs_upto)
+    k_topk_sort<<<(int)G, TOPK_SORT_THREADS, (size_t)TOPK_SMEM_KEYS * 8, (cudaStream_t)stream>>>(score, gptr, kptr, perm, max_pad, runs_upto);
   // graphs larger than the sort's shared-memory budget (and everything when the sort is disabled)
-  k_topk_rank<<<(int)G, TOPK_THREADS, 0, (cudaStream_t)stream>>>(score, gptr, kptr, perm, gkeys, max_pad);
+  if (max_graph_nodes > max_pad)
+    k_topk_rank<<<(int)G, TOPK_THREADS, 0, (cudaStream_t)stream>>>(score, gptr, kptr, perm, gkeys, max_pad);
   return check_launch("topk");
 }
 

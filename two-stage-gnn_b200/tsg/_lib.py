@@ -30,6 +30,7 @@ _PROTOTYPES = {
     "tsg_csr_build_graphs_workspace_bytes": (SZ, [I64, I64]),
     "tsg_csr_build_graphs": (I, [P, P, P, P, I64, I64, I64, I64, P, P, P, P, P, P, P, P, P, SZ, P]),
     "tsg_csr_build_graphs_local": (I, [P, P, P, P, I64, I64, I64, I64, P, P, P, P, P, P, P, P, P, SZ, P]),
+    "tsg_csr_build_graphs_sym_local": (I, [P, P, P, P, I64, I64, I64, I64, P, P, P, P, P]),
     "tsg_inv_perm": (I, [P, I64, I64, P, P]),
     "tsg_csr_filter_workspace_bytes": (SZ, [I64]),
     "tsg_csr_filter": (I, [P, P, P, P, P, P, I64, P, P, P, P, P, P, P, SZ, P]),
@@ -55,6 +56,7 @@ _PROTOTYPES = {
     "tsg_topk_workspace_bytes": (SZ, [I64, I64]),
     "tsg_topk_sizes": (I, [P, I64, F32, P, P, SZ, P]),
     "tsg_topk": (I, [P, P, P, I64, I64, P, P, SZ, P]),
+    "tsg_topk_bounded": (I, [P, P, P, I64, I64, I64, P, P, SZ, P]),
     "tsg_batch_to_ptr": (I, [P, I64, I64, P, P]),
     "tsg_filter_adj_workspace_bytes": (SZ, [I64]),
     "tsg_filter_adj": (I, [P, P, I64, P, P, I64, I64, P, P, P, P, P, SZ, P]),
@@ -98,7 +100,7 @@ _PROTOTYPES = {
 class SagShape(ctypes.Structure):
     """tsg_sag_shape (include/tsg.h)."""
     _fields_ = [("num_graphs", c_int64), ("in_feat", c_int64), ("hidden", c_int64), ("num_edges", c_int64),
-                ("n", c_int64 * 4), ("max_graph_nodes", c_int64 * 3), ("max_graph_edges", c_int64), ("pooling_ratio", ctypes.c_double)]
+                ("n", c_int64 * 4), ("max_graph_nodes", c_int64 * 3), ("max_graph_edges", c_int64), ("pooling_ratio", ctypes.c_double), ("flags", c_int64), ("status", c_void_p)]
 
 EXPORTS = tuple(_PROTOTYPES)
 

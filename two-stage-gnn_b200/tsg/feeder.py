@@ -22,6 +22,8 @@ class DeviceCorpus:
         t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a.astype(dt))).to(device)
         self.node_ptr, self.edge_ptr = t(corpus.node_ptr, np.int64), t(corpus.edge_ptr, np.int64)
         self.row, self.col = t(corpus.row, np.int32), t(corpus.col, np.int32)
+        from .synth import is_coalesced_symmetric
+        self.coalesced = is_coalesced_symmetric(corpus)      # checked once, here; the kernels re-verify per graph
         if dense_x is None:
             self.label, self.x, self.feat = t(corpus.node_label, np.int32), None, corpus.num_node_labels
         else:
@@ -70,10 +72,12 @@ class DeviceCorpus:
         rc = torch.empty(2, E, dtype=torch.int32, device=self.device)
         call("tsg_pack_batch_compact", ptr(d_ids), ptr(d_nptr), ptr(d_eptr), B, ptr(self.node_ptr), ptr(self.edge_ptr),
              ptr(self.row), ptr(self.col), ptr(self.label), ptr(label), ptr(rc[0]), ptr(rc[1]), stream_ptr())
-        return CompactBatch(label, rc[0], rc[1], d_nptr, d_eptr, self.feat, int(np.diff(eptr).max()) if B else 0), nptr
+        return CompactBatch(label, rc[0], rc[1], d_nptr, d_eptr, self.feat, int(np.diff(eptr).max()) if B else 0,
+                            self.coalesced), nptr
 
 
-def compact_host_batch(corpus: Corpus, graph_ids, triplets: np.ndarray, pin: bool | None = None) -> dict:
+def compact_host_batch(corpus: Corpus, graph_ids, triplets: np.ndarray, pin: bool | None = None,
+                       coalesced: bool | None = None) -> dict:
     """One step's HOST batch in the compact form `TripletTrainer.run_from_host_compact` consumes: the chosen graphs'
     node labels (int32), graph-local edge endpoints (int32), node / edge offsets (int64 numpy) and the triplet index
     rows [T, 3] into `graph_ids` (int64).  What a TU file stores, nothing expanded: 4 n + 8 E bytes per graph.
@@ -88,6 +92,9 @@ def compact_host_batch(corpus: Corpus, graph_ids, triplets: np.ndarray, pin: boo
         raise ValueError("tsg: triplet index outside the batch")
     pin = torch.cuda.is_available() if pin is None else pin
     t = lambda a: (torch.from_numpy(np.ascontiguousarray(a)).pin_memory() if pin else torch.from_numpy(np.ascontiguousarray(a)))
+    if coalesced is None:
+        from .synth import is_coalesced_symmetric
+        coalesced = is_coalesced_symmetric(sel)
     return dict(label=t(sel.node_label.astype(np.int32)), row=t(sel.row.astype(np.int32)), col=t(sel.col.astype(np.int32)),
                 node_ptr=sel.node_ptr.astype(np.int64).copy(), edge_ptr=sel.edge_ptr.astype(np.int64).copy(),
-                triplets=t(trip))
+                triplets=t(trip), coalesced=bool(coalesced))

@@ -110,7 +110,17 @@ def host_level_ptrs(node_ptr: np.ndarray, ratio: float, levels: int = 3) -> np.n
 
 KEEP_ARENA = False        # tests: keep (shape, arena) of the last executor forward in LAST_ARENA
 LAST_ARENA = None
-PENDING_STATUS = []       # status words of graph-resident forwards not yet looked at (device int32 views)
+_STATUS = {}              # device index -> persistent int32 word the verifying kernels (K1d, K13) OR their bits into
+_STATUS_DIRTY = set()     # devices whose word may have been written since the last check
+
+
+def _status_word(dev: torch.device) -> torch.Tensor:
+    i = dev.index if dev.index is not None else torch.cuda.current_device()
+    w = _STATUS.get(i)
+    if w is None:
+        w = _STATUS[i] = torch.zeros(1, dtype=torch.int32, device=dev)
+    _STATUS_DIRTY.add(i)
+    return w
 SAG_FIELDS = {"status": (8, torch.int32), "perm": (0, torch.int64), "score": (1, torch.float32), "h": (2, torch.float32), "xg": (3, torch.float32),
               "rowptr": (4, torch.int32), "colidx": (5, torch.int32), "val": (6, torch.float32), "inv": (7, torch.int32)}
 
@@ -128,20 +138,23 @@ def sag_arena_view(shape, arena: torch.Tensor, level: int, field: str) -> torch.
 
 
 def check_fused_status() -> None:
-    """Look at the status words the graph-resident kernels (K13) left since the last call -- ONE device read, so callers
-    do it where they synchronise anyway (loss read-back, end of a feeder loop, tests).  A non-zero word means a graph's
+    """Look at the status word the verifying kernels (K1d, K13) OR-ed their bits into since the last call -- ONE device
+    read per device, so callers do it where they synchronise anyway (loss read-back, end of a feeder loop, tests).  A non-zero word means a graph's
     edge list was not what those kernels require (endpoints in range, no self loops, sorted by (row, col), symmetric:
     the TUDataset / TU-loader form); its embedding was zeroed.  There is no silent fallback: this raises."""
-    global PENDING_STATUS
-    if not PENDING_STATUS:
+    if not _STATUS_DIRTY:
         return
-    words, PENDING_STATUS = PENDING_STATUS, []
-    bits = int(torch.stack([w.reshape(()) for w in words]).max().item()) if len(words) > 1 else int(words[0].item())
+    bits = 0
+    for i in list(_STATUS_DIRTY):
+        bits |= int(_STATUS[i].item())
+        _STATUS[i].zero_()
+    _STATUS_DIRTY.clear()
     if bits:
         names = [n for b, n in ((1, "edge endpoint out of range / self loop"), (2, "edge list not sorted by (row, col)"),
                                 (4, "edge list not symmetric")) if bits & b]
-        raise RuntimeError("tsg: the graph-resident SAGPool kernels rejected a graph (" + "; ".join(names) + "). Coalesce the "
-                           "edge lists (TUDataset form) or run with TSG_SAG_FUSED=0 (kernel-per-operator executor).")
+        raise RuntimeError("tsg: a graph's edge list is not in the coalesced, symmetric form the caller promised (" +
+                           "; ".join(names) + "); its results are invalid.  Coalesce the edge lists (TUDataset form), or "
+                           "drop CompactBatch.coalesced and run with TSG_SAG_FUSED=0: the general kernels take any list.")
 
 
 class _SagEncoderFn(torch.autograd.Function):
@@ -235,10 +248,6 @@ def _sag_embed_compact(cb, ptrs, shape, params):
     parr = (ctypes.c_void_p * 12)(*[p.data_ptr() for p in params])
     _lib.call("tsg_sag_encoder_embed_compact", ctypes.byref(shape), _lib.ptr(cb.label), _lib.ptr(cb.row), _lib.ptr(cb.col),
               _lib.ptr(cb.edge_ptr), _lib.ptr(ptrs), parr, _lib.ptr(z), _lib.ptr(arena), arena_bytes, _lib.stream_ptr())
-    if shape.max_graph_edges > 0:
-        PENDING_STATUS.append(sag_arena_view(shape, arena, 0, "status"))
-        if len(PENDING_STATUS) > 64:
-            check_fused_status()
     if KEEP_ARENA:
         global LAST_ARENA
         LAST_ARENA = (shape, arena)
@@ -336,6 +345,9 @@ class PackedSAGNet(torch.nn.Module):
             return None
         shape.max_graph_edges = int(cb.max_graph_edges)
         shape.pooling_ratio = float(self.pooling_ratio)
+        shape.flags = 1 if cb.coalesced else 0
+        if cb.coalesced or cb.max_graph_edges > 0:      # K1d / K13 verify the edge lists on the device: persistent status word
+            shape.status = _status_word(cb.label.device).data_ptr()
         if not torch.is_grad_enabled():
             return _sag_embed_compact(cb, ptrs, shape, [p.detach() for p in self._encoder_params()])
         return _SagEncoderCompactFn.apply(cb, ptrs, shape, *self._encoder_params())

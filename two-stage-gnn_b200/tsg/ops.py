@@ -65,6 +65,9 @@ class CompactBatch:
     edge_ptr: torch.Tensor
     num_labels: int
     max_graph_edges: int = 0      # host-side max of diff(edge_ptr) (0 = unknown: the graph-resident kernels are not used)
+    coalesced: bool = False       # promise: every graph's list is sorted by (row, col), loop free and symmetric (the
+                                  # TUDataset / TU loader / tsg.synth form) -> one CSR orientation per level (K1d).  Verified
+                                  # on the device; a violation raises at the next tsg.nn.check_fused_status()
 
     def expand(self) -> Tuple[torch.Tensor, torch.Tensor]:
         """(x [N, num_labels] fp32 one-hot, edge_index [2, E] int64 with batch-global ids) via tsg_pack_batch."""

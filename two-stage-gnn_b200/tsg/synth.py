@@ -80,6 +80,26 @@ def _one_graph(rng: np.random.Generator, n: int, m_undirected: int):
     return r[order], c[order]
 
 
+def is_coalesced_symmetric(c: Corpus) -> bool:
+    """True when every graph's edge list is in range, loop free, sorted by (row, col) without duplicates and symmetric --
+    the TUDataset / TU-loader form `make_corpus` produces.  What `ops.CompactBatch.coalesced` promises (the kernels
+    verify it again per graph on the device).  Vectorised: one lexicographic comparison and one sort over all edges."""
+    E = int(c.edge_ptr[-1])
+    if E == 0:
+        return True
+    g = np.repeat(np.arange(c.num_graphs, dtype=np.int64), np.diff(c.edge_ptr))
+    n = np.diff(c.node_ptr)[g]
+    row, col = c.row.astype(np.int64), c.col.astype(np.int64)
+    if (row < 0).any() or (col < 0).any() or (row >= n).any() or (col >= n).any() or (row == col).any():
+        return False
+    nmax = int(n.max()) + 1
+    key = (g * nmax + row) * nmax + col
+    if not (np.diff(key) > 0).all():
+        return False
+    rkey = np.sort((g * nmax + col) * nmax + row)
+    return bool(np.array_equal(key, rkey))
+
+
 def make_corpus(shape: str, num_graphs: int, seed: int = 777) -> Corpus:
     """Graph g is drawn from `default_rng(seed + g)` so any subset is reproducible."""
     sp = SHAPES[shape]

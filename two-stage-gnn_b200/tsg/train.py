@@ -210,7 +210,7 @@ class TripletTrainer:
                 t["meta"] = meta.to(device, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(copy)
-            return t, b["node_ptr"], b["edge_ptr"], ev
+            return t, b["node_ptr"], b["edge_ptr"], ev, b.get("coalesced", False)
 
         it = iter(host_batches)
         try:
@@ -219,7 +219,7 @@ class TripletTrainer:
             return []
         host_losses = []
         while nxt is not None:
-            t, nptr, eptr, ev = nxt
+            t, nptr, eptr, ev, b_coalesced = nxt
             try:
                 nxt = upload(next(it))
             except StopIteration:
@@ -230,7 +230,7 @@ class TripletTrainer:
             G, N, E = nptr.shape[0] - 1, int(nptr[-1]), int(eptr[-1])
             d_nptr, d_eptr = t["meta"][:G + 1], t["meta"][G + 1:]
             cb = ops.CompactBatch(t["label"], t["row"], t["col"], d_nptr, d_eptr, num_node_labels,
-                                  int(np.diff(eptr).max()) if G else 0)
+                                  int(np.diff(eptr).max()) if G else 0, bool(b_coalesced))
             if expand or not getattr(self.model, "accepts_compact", False):
                 x, ei = cb.expand()
             else:
