@@ -501,6 +501,33 @@ int tsg_sag_encoder_bwd(const tsg_sag_shape* shape, const float* x, const int64_
                         const float* const* params, const float* dz, float* const* grads,
                         void* arena, size_t arena_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * K14  the whole 2stg SAGPool training step in one call
+ *   replaces the body of the stage-1 loop of Code/sag/train_triplet.py:203-212 for a packed batch: TNet forward
+ *   (tripletnet.py:14-24 -> network.py:30-53, head included: lin1 / ReLU / dropout / lin2 / ReLU / lin3 / log_softmax),
+ *   MarginRankingLoss(margin)(d_p, d_n, -1) (train_triplet.py:196,208-211) and loss.backward().  Enqueues: K10 forward,
+ *   head forward, K9 forward + backward, head backward (fixed-order gradient reduction), K10 backward -- without
+ *   returning to the interpreter in between (round 1: 1.46 ms of Python per 1.69 ms step).
+ *   params / grads: 18 device pointers = the 12 of K10, then lin1.weight [H, 2H], lin1.bias [H], lin2.weight [H/2, H],
+ *   lin2.bias, lin3.weight [C, H/2], lin3.bias (torch.nn.Linear layout).  triplets int64 [T, 3] rows of the batch.
+ *   dropout_mask: NULL, or a [G, H] keep-multiplier matrix (0 or 1/(1-p): what parity tests inject); with NULL and
+ *   dropout_p > 0 a counter-based hash of (seed, graph, column) draws the mask.  loss: device float (mean over T);
+ *   emb_out: optional [G, C] embeddings (log-softmax vectors).  Gradients are WRITTEN (not accumulated).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int64_t num_classes;       /* C = final_dim */
+  int64_t num_triplets;      /* T */
+  float margin, eps, dropout_p;
+  uint64_t seed;
+} tsg_sag_head;
+size_t tsg_sag_triplet_step_workspace_bytes(const tsg_sag_shape* shape, const tsg_sag_head* head);
+int tsg_sag_triplet_step_compact(const tsg_sag_shape* shape, const tsg_sag_head* head, const int32_t* label,
+                                 const int32_t* local_row, const int32_t* local_col, const int64_t* edge_ptr,
+                                 const int64_t* level_ptr, const float* const* params, const int64_t* triplets,
+                                 const float* dropout_mask /*nullable*/, float* const* grads, float* loss,
+                                 float* emb_out /*nullable*/, void* arena, size_t arena_bytes, void* workspace,
+                                 size_t workspace_bytes, void* stream);
+
 /* tsg_spmm plus dot_out[r] = Y[r, :] . dot_vec from K2's epilogue (conv + the score layer's h @ ws of
  * Code/sag/layers.py:18 in one pass); bit-identical to tsg_spmm followed by tsg_linear_fwd(Y, dot_vec, out_feat = 1),
  * which is what runs for shapes the epilogue does not cover (feat > 128 or not a multiple of 4). */

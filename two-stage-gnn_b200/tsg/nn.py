@@ -23,6 +23,7 @@ from .ops import CSR, EdgeList
 
 
 USE_EXECUTOR = os.environ.get("TSG_SAG_EXECUTOR", "1") != "0"   # K10 native step executor for PackedSAGNet
+USE_NATIVE_STEP = os.environ.get("TSG_NATIVE_STEP", "1") != "0"  # K14: forward + loss + backward in one C-ABI call
 
 
 def _glorot_(t: torch.Tensor) -> None:
@@ -351,6 +352,81 @@ class PackedSAGNet(torch.nn.Module):
         if not torch.is_grad_enabled():
             return _sag_embed_compact(cb, ptrs, shape, [p.detach() for p in self._encoder_params()])
         return _SagEncoderCompactFn.apply(cb, ptrs, shape, *self._encoder_params())
+
+    # ------------------------------------------------------------------------------------------------------------
+    # K14: the whole training step (forward, MarginRankingLoss, backward) behind one C-ABI call
+    # ------------------------------------------------------------------------------------------------------------
+    def _step_params(self):
+        return self._encoder_params() + [self.lin1.weight, self.lin1.bias, self.lin2.weight, self.lin2.bias,
+                                         self.lin3.weight, self.lin3.bias]
+
+    def _flat_grads(self):
+        """One flat fp32 buffer [all 18 gradients | loss | weight]; every parameter's .grad is a VIEW into it, so the
+        data-parallel all-reduce is one collective on one tensor with no gather / scatter copies around it."""
+        params = self._step_params()
+        fg, views = self.__dict__.get("_flat_grad"), self.__dict__.get("_grad_views")
+        stale = fg is None or fg.device != params[0].device or any(p.grad is not v for p, v in zip(params, views))
+        if stale:
+            n = sum(p.numel() for p in params)
+            fg = torch.zeros(n + 2, dtype=torch.float32, device=params[0].device)
+            views, off = [], 0
+            for p in params:
+                v = fg[off:off + p.numel()].view_as(p); off += p.numel()
+                p.grad = v
+                views.append(v)
+            self.__dict__["_flat_grad"], self.__dict__["_grad_views"] = fg, views
+        return fg, views
+
+    def native_step_supported(self, cb) -> bool:
+        from . import _lib
+        if not (USE_EXECUTOR and USE_NATIVE_STEP and isinstance(cb, ops.CompactBatch)) or self.nhid % 2:
+            return False
+        if cb.num_labels != self.num_features or _lib.lib.tsg_embed_bwd_weight_workspace_bytes(cb.num_labels, self.nhid) == 0:
+            return False
+        return all(p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() for p in self._step_params())
+
+    def native_step(self, cb, node_ptr_host, triplets: torch.Tensor, margin: float = 1.5, eps: float = 1e-6,
+                    dropout_mask: Optional[torch.Tensor] = None, return_emb: bool = False):
+        """Forward + triplet margin loss + backward of the whole model on a CompactBatch through
+        tsg_sag_triplet_step_compact.  Returns the loss (device scalar, a view into the flat gradient buffer) and leaves
+        every parameter's gradient in .grad (written, not accumulated).  Dropout follows self.training; `dropout_mask`
+        [G, nhid] injects the keep multipliers (parity tests)."""
+        from . import _lib
+        dev = cb.label.device
+        plan, ptrs = self._level_plan(node_ptr_host, dev)
+        shape = self._sag_shape(plan, cb.num_labels, int(cb.row.shape[0]))
+        if shape is None:
+            raise RuntimeError("tsg: batch shape outside the executor's range (empty level or a graph beyond the per-graph CSR builder)")
+        shape.max_graph_edges = int(cb.max_graph_edges)
+        shape.pooling_ratio = float(self.pooling_ratio)
+        shape.flags = 1 if cb.coalesced else 0
+        if cb.coalesced:
+            shape.status = _status_word(dev).data_ptr()
+        T = int(triplets.shape[0])
+        count = self.__dict__["_native_steps"] = self.__dict__.get("_native_steps", 0) + 1
+        p_drop = float(self.dropout_ratio) if (self.training and dropout_mask is None) else 0.0
+        head = _lib.SagHead(self.num_classes, T, float(margin), float(eps), p_drop,
+                            (torch.initial_seed() * 0x9E3779B1 + count) & 0xFFFFFFFFFFFFFFFF)
+        params = self._step_params()
+        flat, views = self._flat_grads()
+        arena_bytes = _lib.lib.tsg_sag_arena_bytes(ctypes.byref(shape))
+        ws_bytes = _lib.lib.tsg_sag_triplet_step_workspace_bytes(ctypes.byref(shape), ctypes.byref(head))
+        if arena_bytes == 0 or ws_bytes == 0:
+            raise RuntimeError("tsg: bad shape for the native training step")
+        arena = torch.empty(arena_bytes, dtype=torch.uint8, device=dev)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        emb = torch.empty(shape.num_graphs, self.num_classes, dtype=torch.float32, device=dev) if return_emb else None
+        parr = (ctypes.c_void_p * 18)(*[p.data_ptr() for p in params])
+        garr = (ctypes.c_void_p * 18)(*[v.data_ptr() for v in views])
+        loss = flat[-2:-1]
+        _lib.call("tsg_sag_triplet_step_compact", ctypes.byref(shape), ctypes.byref(head), _lib.ptr(cb.label), _lib.ptr(cb.row),
+                  _lib.ptr(cb.col), _lib.ptr(cb.edge_ptr), _lib.ptr(ptrs), parr, _lib.ptr(triplets.contiguous()),
+                  _lib.ptr(dropout_mask.contiguous()) if dropout_mask is not None else None, garr, loss.data_ptr(),
+                  _lib.ptr(emb), _lib.ptr(arena), arena_bytes, _lib.ptr(ws), ws_bytes, _lib.stream_ptr())
+        if KEEP_ARENA:
+            global LAST_ARENA
+            LAST_ARENA = (shape, arena)
+        return (loss.view(()), emb) if return_emb else loss.view(())
 
     def _level_plan(self, node_ptr_host, dev):
         """(host plan int64 [4, G+1], the same on the device).  Batches that come round again (an epoch over a fixed

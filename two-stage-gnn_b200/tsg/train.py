@@ -103,8 +103,20 @@ class TripletTrainer:
         """x/edge_index/triplets on the device.  `triplets` [T,3] index rows of THIS rank's embedding matrix; with
         world > 1 the returned loss is the mean over the GLOBAL batch and the parameters receive its gradient."""
         self.model.train()
-        emb = self.model(x, edge_index, node_ptr_host)
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        if edge_index is None and getattr(self.model, "native_step_supported", None) and self.model.native_step_supported(x):
+            # K14: forward, loss and backward are ONE C-ABI call; gradients land in views of one flat buffer
+            loss = self.model.native_step(x, node_ptr_host, triplets, self.margin)
+            if world > 1:
+                flat, _ = self.model._flat_grads()
+                flat[-1] = 1.0
+                flat.mul_(float(triplets.size(0)))                       # [T_r * grads, T_r * loss, T_r]
+                dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+                flat.div_(flat[-1].clone())
+            loss = loss.clone()                                           # the buffer is rewritten by the next step
+            self.opt.step()
+            return loss
+        emb = self.model(x, edge_index, node_ptr_host)
         loss, _, _ = ops.triplet_loss(emb, triplets, self.margin)         # mean over THIS rank's triplets
         self.opt.zero_grad(set_to_none=True)
         loss.backward()
