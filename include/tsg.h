@@ -528,6 +528,20 @@ int tsg_sag_triplet_step_compact(const tsg_sag_shape* shape, const tsg_sag_head*
                                  float* emb_out /*nullable*/, void* arena, size_t arena_bytes, void* workspace,
                                  size_t workspace_bytes, void* stream);
 
+/* The two halves of K14 for a loss evaluated outside the call (all-gather formulation: embeddings of every rank are
+ * gathered, the global triplet loss is evaluated on the gathered matrix, this rank's slice of d(loss)/d(emb) comes back):
+ * fwd = encoder + head -> emb [G, C]; bwd = head backward + encoder backward from demb [G, C].  Same arena and workspace
+ * (tsg_sag_triplet_step_workspace_bytes) in both calls. */
+int tsg_sag_step_fwd_compact(const tsg_sag_shape* shape, const tsg_sag_head* head, const int32_t* label,
+                             const int32_t* local_row, const int32_t* local_col, const int64_t* edge_ptr,
+                             const int64_t* level_ptr, const float* const* params, const float* dropout_mask /*nullable*/,
+                             float* emb, void* arena, size_t arena_bytes, void* workspace, size_t workspace_bytes,
+                             void* stream);
+int tsg_sag_step_bwd_compact(const tsg_sag_shape* shape, const tsg_sag_head* head, const int32_t* label,
+                             const int64_t* level_ptr, const float* const* params, const float* emb, const float* demb,
+                             float* const* grads, void* arena, size_t arena_bytes, void* workspace,
+                             size_t workspace_bytes, void* stream);
+
 /* tsg_spmm plus dot_out[r] = Y[r, :] . dot_vec from K2's epilogue (conv + the score layer's h @ ws of
  * Code/sag/layers.py:18 in one pass); bit-identical to tsg_spmm followed by tsg_linear_fwd(Y, dot_vec, out_feat = 1),
  * which is what runs for shapes the epilogue does not cover (feat > 128 or not a multiple of 4). */

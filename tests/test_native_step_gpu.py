@@ -99,3 +99,31 @@ def test_trainer_takes_the_native_path_and_learns(cuda):
         pass
     l1 = float(model.native_step(cb, corpus.node_ptr, trip, 1.5)); l2 = float(model.native_step(cb, corpus.node_ptr, trip, 1.5))
     assert l1 != l2
+
+
+def test_native_halves_equal_the_single_call(cuda):
+    """tsg_sag_step_fwd_compact + K9 through autograd + tsg_sag_step_bwd_compact (the all-gather formulation's path)
+    == tsg_sag_triplet_step_compact: identical embeddings, loss and gradients (same kernels, same order)."""
+    from tsg import nn as tnn, ops
+    from tsg.train import TripletTrainer
+    corpus = synth.make_corpus("DD", 18, seed=77)
+    cb = _compact(corpus, cuda)
+    torch.manual_seed(4)
+    model = tnn.PackedSAGNet(corpus.num_node_labels, 32, 32, 0.5, 0.0).to(cuda)
+    model.train()
+    trip = torch.from_numpy(synth.sample_triplets(corpus.y, 40, seed=2)).to(cuda)
+    loss1, emb1 = model.native_step(cb, corpus.node_ptr, trip, 1.5, return_emb=True)
+    loss1 = loss1.clone()
+    g1 = {k: p.grad.clone() for k, p in model.named_parameters()}
+    emb2, ctx = model.native_forward(cb, corpus.node_ptr)
+    e = emb2.clone().requires_grad_(True)
+    loss2, _, _ = ops.triplet_loss(e, trip, 1.5)
+    loss2.backward()
+    model.native_backward(ctx, e.grad)
+    assert torch.equal(emb1, emb2) and torch.equal(loss1, loss2.detach())
+    for k, p in model.named_parameters():
+        assert torch.equal(g1[k], p.grad), k
+    # and the trainer's all-gather step runs on it (world = 1: the gather is the identity)
+    tr = TripletTrainer(model, lr=1e-3)
+    l = tr.step_allgather(cb, None, corpus.node_ptr, trip)
+    assert torch.isfinite(l)

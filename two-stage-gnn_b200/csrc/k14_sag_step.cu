@@ -266,6 +266,54 @@ extern "C" size_t tsg_sag_triplet_step_workspace_bytes(const tsg_sag_shape* sh, 
   return w.total;
 }
 
+static void head_attr_once() {
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(k_head_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_head_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr = true;
+  }
+}
+
+// encoder forward (K10) + head forward -> emb [G, C]
+static int step_fwd(const tsg_sag_shape* sh, const tsg_sag_head* hd, const int32_t* label, const int32_t* local_row,
+                    const int32_t* local_col, const int64_t* edge_ptr, const int64_t* level_ptr, const float* const* params,
+                    const float* dropout_mask, float* emb, const StepWs& w, void* arena, size_t arena_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int H = (int)sh->hidden, H2 = H / 2, C = (int)hd->num_classes, G = (int)sh->num_graphs;
+  HeadDims d{G, H, H2, C};
+  HeadPtrs P;
+  for (int i = 0; i < 6; ++i) P.hp[i] = params[12 + i];
+  TSG_TRY(tsg_sag_encoder_fwd_compact(sh, label, local_row, local_col, edge_ptr, level_ptr, params, w.z, arena, arena_bytes, stream));
+  const size_t sm_f = ((size_t)head_param_floats(H, H2, C) + (size_t)HEAD_WARPS * (3 * H + H2 + C)) * 4;
+  head_attr_once();
+  k_head_fwd<<<grid_for(G, HEAD_WARPS, 2), HEAD_THREADS, sm_f, st>>>(P, w.z, d, hd->dropout_p, (unsigned long long)hd->seed,
+                                                                       dropout_mask, w.a1, w.m, w.a2, emb);
+  return check_launch("sag_step(head fwd)");
+}
+
+// head backward (dz + fixed-order parameter gradients) + encoder backward (K10), from d(loss)/d(emb)
+static int step_bwd(const tsg_sag_shape* sh, const tsg_sag_head* hd, const int32_t* label, const int64_t* level_ptr,
+                    const float* const* params, const float* emb, const float* demb, float* const* grads, const StepWs& w,
+                    void* arena, size_t arena_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int H = (int)sh->hidden, H2 = H / 2, C = (int)hd->num_classes, G = (int)sh->num_graphs;
+  HeadDims d{G, H, H2, C};
+  HeadPtrs P;
+  for (int i = 0; i < 6; ++i) P.hp[i] = params[12 + i];
+  const size_t sm_b = ((size_t)head_param_floats(H, H2, C) + (size_t)HEAD_WARPS * (4 * H + 2 * H2 + C) + head_grad_floats(H, H2, C)) * 4;
+  head_attr_once();
+  const int ctas = head_ctas(G);
+  const int NG = head_grad_floats(H, H2, C);
+  k_head_bwd<<<ctas, HEAD_THREADS, sm_b, st>>>(P, w.z, d, w.a1, w.m, w.a2, emb, demb, w.dz, w.part);
+  TSG_LAUNCH_CHECK("sag_step(head bwd)");
+  launch_partial_sum_final(w.part, w.packed, NG, nullptr, ctas, NG, st);
+  k_head_unpack<<<(NG + 255) / 256, 256, 0, st>>>(w.packed, grads[12], grads[13], grads[14], grads[15], grads[16], grads[17],
+                                                   H * 2 * H, H, H2 * H, H2, C * H2, C);
+  TSG_LAUNCH_CHECK("sag_step(head grads)");
+  return tsg_sag_encoder_bwd_compact(sh, label, level_ptr, params, w.dz, grads, arena, arena_bytes, stream);
+}
+
 extern "C" int tsg_sag_triplet_step_compact(const tsg_sag_shape* sh, const tsg_sag_head* hd, const int32_t* label,
                                             const int32_t* local_row, const int32_t* local_col, const int64_t* edge_ptr,
                                             const int64_t* level_ptr, const float* const* params, const int64_t* triplets,
@@ -278,40 +326,41 @@ extern "C" int tsg_sag_triplet_step_compact(const tsg_sag_shape* sh, const tsg_s
   step_layout(sh, hd, workspace, &w);
   if (workspace_bytes < w.total) { set_error("sag_triplet_step: workspace too small (%zu < %zu)", workspace_bytes, w.total); return TSG_EWORKSPACE; }
   cudaStream_t st = (cudaStream_t)stream;
-  const int H = (int)sh->hidden, H2 = H / 2, C = (int)hd->num_classes, G = (int)sh->num_graphs;
+  const int C = (int)hd->num_classes, G = (int)sh->num_graphs;
   const int64_t T = hd->num_triplets;
-  HeadDims d{G, H, H2, C};
-  HeadPtrs P;
-  for (int i = 0; i < 6; ++i) P.hp[i] = params[12 + i];
-  // 1. encoder forward (K10)
-  TSG_TRY(tsg_sag_encoder_fwd_compact(sh, label, local_row, local_col, edge_ptr, level_ptr, params, w.z, arena, arena_bytes, stream));
-  // 2. head forward
-  const size_t sm_f = ((size_t)head_param_floats(H, H2, C) + (size_t)HEAD_WARPS * (3 * H + H2 + C)) * 4;
-  const size_t sm_b = ((size_t)head_param_floats(H, H2, C) + (size_t)HEAD_WARPS * (4 * H + 2 * H2 + C) + head_grad_floats(H, H2, C)) * 4;
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(k_head_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(k_head_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr = true;
-  }
   float* emb = emb_out ? emb_out : w.emb;
-  const int fgrid = grid_for(G, HEAD_WARPS, 2);
-  k_head_fwd<<<fgrid, HEAD_THREADS, sm_f, st>>>(P, w.z, d, hd->dropout_p, (unsigned long long)hd->seed, dropout_mask, w.a1, w.m, w.a2, emb);
-  TSG_LAUNCH_CHECK("sag_triplet_step(head fwd)");
-  // 3. triplet loss forward + backward (K9), d(loss) = 1
+  TSG_TRY(step_fwd(sh, hd, label, local_row, local_col, edge_ptr, level_ptr, params, dropout_mask, emb, w, arena, arena_bytes, stream));
+  // triplet loss forward + backward (K9), d(loss) = 1
   TSG_TRY(tsg_triplet_fwd(emb, triplets, T, G, C, hd->margin, hd->eps, w.dp, w.dn, loss, w.trip_ws, w.trip_bytes, stream));
   k_store_one<<<1, 1, 0, st>>>(w.one, 1.0f);
   TSG_TRY(tsg_triplet_bwd(emb, triplets, T, G, C, hd->margin, hd->eps, w.dp, w.dn, w.one, w.demb, w.trip_ws, w.trip_bytes, stream));
-  // 4. head backward: dz + per-CTA partial rows -> fixed-order reduction -> the six gradient tensors
-  const int ctas = head_ctas(G);
-  const int NG = head_grad_floats(H, H2, C);
-  k_head_bwd<<<ctas, HEAD_THREADS, sm_b, st>>>(P, w.z, d, w.a1, w.m, w.a2, emb, w.demb, w.dz, w.part);
-  TSG_LAUNCH_CHECK("sag_triplet_step(head bwd)");
-  launch_partial_sum_final(w.part, w.packed, NG, nullptr, ctas, NG, st);
-  k_head_unpack<<<(NG + 255) / 256, 256, 0, st>>>(w.packed, grads[12], grads[13], grads[14], grads[15], grads[16], grads[17],
-                                                   H * 2 * H, H, H2 * H, H2, C * H2, C);
-  TSG_LAUNCH_CHECK("sag_triplet_step(head grads)");
-  // 5. encoder backward (K10)
-  TSG_TRY(tsg_sag_encoder_bwd_compact(sh, label, level_ptr, params, w.dz, grads, arena, arena_bytes, stream));
-  return TSG_OK;
+  return step_bwd(sh, hd, label, level_ptr, params, emb, w.demb, grads, w, arena, arena_bytes, stream);
+}
+
+/* The two halves of the step for losses evaluated OUTSIDE the call (the all-gather formulation: embeddings of every rank
+ * are gathered, the global triplet loss is evaluated on the gathered matrix, this rank's slice of its gradient comes
+ * back).  Same arena / workspace in both calls; num_triplets of `head` only sizes the workspace (>= 1). */
+extern "C" int tsg_sag_step_fwd_compact(const tsg_sag_shape* sh, const tsg_sag_head* hd, const int32_t* label,
+                                        const int32_t* local_row, const int32_t* local_col, const int64_t* edge_ptr,
+                                        const int64_t* level_ptr, const float* const* params, const float* dropout_mask,
+                                        float* emb, void* arena, size_t arena_bytes, void* workspace, size_t workspace_bytes,
+                                        void* stream) {
+  TSG_REQUIRE(head_ok(sh, hd), "sag_step_fwd: bad head / shape");
+  TSG_REQUIRE(params && emb && workspace, "sag_step_fwd: null pointer");
+  StepWs w;
+  step_layout(sh, hd, workspace, &w);
+  if (workspace_bytes < w.total) { set_error("sag_step_fwd: workspace too small"); return TSG_EWORKSPACE; }
+  return step_fwd(sh, hd, label, local_row, local_col, edge_ptr, level_ptr, params, dropout_mask, emb, w, arena, arena_bytes, stream);
+}
+
+extern "C" int tsg_sag_step_bwd_compact(const tsg_sag_shape* sh, const tsg_sag_head* hd, const int32_t* label,
+                                        const int64_t* level_ptr, const float* const* params, const float* emb,
+                                        const float* demb, float* const* grads, void* arena, size_t arena_bytes,
+                                        void* workspace, size_t workspace_bytes, void* stream) {
+  TSG_REQUIRE(head_ok(sh, hd), "sag_step_bwd: bad head / shape");
+  TSG_REQUIRE(params && emb && demb && grads && workspace, "sag_step_bwd: null pointer");
+  StepWs w;
+  step_layout(sh, hd, workspace, &w);
+  if (workspace_bytes < w.total) { set_error("sag_step_bwd: workspace too small"); return TSG_EWORKSPACE; }
+  return step_bwd(sh, hd, label, level_ptr, params, emb, demb, grads, w, arena, arena_bytes, stream);
 }

@@ -385,12 +385,7 @@ class PackedSAGNet(torch.nn.Module):
             return False
         return all(p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() for p in self._step_params())
 
-    def native_step(self, cb, node_ptr_host, triplets: torch.Tensor, margin: float = 1.5, eps: float = 1e-6,
-                    dropout_mask: Optional[torch.Tensor] = None, return_emb: bool = False):
-        """Forward + triplet margin loss + backward of the whole model on a CompactBatch through
-        tsg_sag_triplet_step_compact.  Returns the loss (device scalar, a view into the flat gradient buffer) and leaves
-        every parameter's gradient in .grad (written, not accumulated).  Dropout follows self.training; `dropout_mask`
-        [G, nhid] injects the keep multipliers (parity tests)."""
+    def _native_setup(self, cb, node_ptr_host, num_triplets, margin, eps, dropout_mask):
         from . import _lib
         dev = cb.label.device
         plan, ptrs = self._level_plan(node_ptr_host, dev)
@@ -402,21 +397,32 @@ class PackedSAGNet(torch.nn.Module):
         shape.flags = 1 if cb.coalesced else 0
         if cb.coalesced:
             shape.status = _status_word(dev).data_ptr()
-        T = int(triplets.shape[0])
         count = self.__dict__["_native_steps"] = self.__dict__.get("_native_steps", 0) + 1
         p_drop = float(self.dropout_ratio) if (self.training and dropout_mask is None) else 0.0
-        head = _lib.SagHead(self.num_classes, T, float(margin), float(eps), p_drop,
+        head = _lib.SagHead(self.num_classes, max(int(num_triplets), 1), float(margin), float(eps), p_drop,
                             (torch.initial_seed() * 0x9E3779B1 + count) & 0xFFFFFFFFFFFFFFFF)
-        params = self._step_params()
-        flat, views = self._flat_grads()
         arena_bytes = _lib.lib.tsg_sag_arena_bytes(ctypes.byref(shape))
         ws_bytes = _lib.lib.tsg_sag_triplet_step_workspace_bytes(ctypes.byref(shape), ctypes.byref(head))
         if arena_bytes == 0 or ws_bytes == 0:
             raise RuntimeError("tsg: bad shape for the native training step")
         arena = torch.empty(arena_bytes, dtype=torch.uint8, device=dev)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        emb = torch.empty(shape.num_graphs, self.num_classes, dtype=torch.float32, device=dev) if return_emb else None
+        params = self._step_params()
         parr = (ctypes.c_void_p * 18)(*[p.data_ptr() for p in params])
+        return shape, head, ptrs, arena, arena_bytes, ws, ws_bytes, parr
+
+    def native_step(self, cb, node_ptr_host, triplets: torch.Tensor, margin: float = 1.5, eps: float = 1e-6,
+                    dropout_mask: Optional[torch.Tensor] = None, return_emb: bool = False):
+        """Forward + triplet margin loss + backward of the whole model on a CompactBatch through
+        tsg_sag_triplet_step_compact.  Returns the loss (device scalar, a view into the flat gradient buffer) and leaves
+        every parameter's gradient in .grad (written, not accumulated).  Dropout follows self.training; `dropout_mask`
+        [G, nhid] injects the keep multipliers (parity tests)."""
+        from . import _lib
+        dev = cb.label.device
+        shape, head, ptrs, arena, arena_bytes, ws, ws_bytes, parr = self._native_setup(
+            cb, node_ptr_host, triplets.shape[0], margin, eps, dropout_mask)
+        flat, views = self._flat_grads()
+        emb = torch.empty(shape.num_graphs, self.num_classes, dtype=torch.float32, device=dev) if return_emb else None
         garr = (ctypes.c_void_p * 18)(*[v.data_ptr() for v in views])
         loss = flat[-2:-1]
         _lib.call("tsg_sag_triplet_step_compact", ctypes.byref(shape), ctypes.byref(head), _lib.ptr(cb.label), _lib.ptr(cb.row),
@@ -427,6 +433,28 @@ class PackedSAGNet(torch.nn.Module):
             global LAST_ARENA
             LAST_ARENA = (shape, arena)
         return (loss.view(()), emb) if return_emb else loss.view(())
+
+    def native_forward(self, cb, node_ptr_host, dropout_mask: Optional[torch.Tensor] = None):
+        """First half of the native step: embeddings [G, C] (no autograd graph) + the context native_backward needs."""
+        from . import _lib
+        dev = cb.label.device
+        shape, head, ptrs, arena, arena_bytes, ws, ws_bytes, parr = self._native_setup(cb, node_ptr_host, 1, 0.0, 1e-6, dropout_mask)
+        emb = torch.empty(shape.num_graphs, self.num_classes, dtype=torch.float32, device=dev)
+        _lib.call("tsg_sag_step_fwd_compact", ctypes.byref(shape), ctypes.byref(head), _lib.ptr(cb.label), _lib.ptr(cb.row),
+                  _lib.ptr(cb.col), _lib.ptr(cb.edge_ptr), _lib.ptr(ptrs), parr,
+                  _lib.ptr(dropout_mask.contiguous()) if dropout_mask is not None else None, _lib.ptr(emb), _lib.ptr(arena),
+                  arena_bytes, _lib.ptr(ws), ws_bytes, _lib.stream_ptr())
+        return emb, (shape, head, ptrs, arena, arena_bytes, ws, ws_bytes, parr, cb.label, emb)
+
+    def native_backward(self, ctx, demb: torch.Tensor) -> None:
+        """Second half: d(loss)/d(emb) [G, C] -> every parameter's .grad (views of the flat buffer, written)."""
+        from . import _lib
+        shape, head, ptrs, arena, arena_bytes, ws, ws_bytes, parr, label, emb = ctx
+        flat, views = self._flat_grads()
+        garr = (ctypes.c_void_p * 18)(*[v.data_ptr() for v in views])
+        _lib.call("tsg_sag_step_bwd_compact", ctypes.byref(shape), ctypes.byref(head), _lib.ptr(label), _lib.ptr(ptrs), parr,
+                  _lib.ptr(emb), _lib.ptr(demb.contiguous()), garr, _lib.ptr(arena), arena_bytes, _lib.ptr(ws), ws_bytes,
+                  _lib.stream_ptr())
 
     def _level_plan(self, node_ptr_host, dev):
         """(host plan int64 [4, G+1], the same on the device).  Batches that come round again (an epoch over a fixed

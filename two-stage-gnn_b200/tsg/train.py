@@ -136,6 +136,26 @@ class TripletTrainer:
         global loss over `triplets_global` [T_g, 3] (indices into the gathered matrix, identical on all ranks), backward
         takes this rank's slice of d(loss)/d(embeddings), and one all-reduce(SUM) completes the parameter gradient."""
         self.model.train()
+        if edge_index is None and getattr(self.model, "native_step_supported", None) and self.model.native_step_supported(x):
+            # native halves (K14): forward to the embeddings, gather, loss + its gradient on the gathered matrix (K9),
+            # this rank's slice back into the native backward
+            emb, ctx = self.model.native_forward(x, node_ptr_host)
+            world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+            if world > 1:
+                emb_g = torch.empty(world * emb.size(0), emb.size(1), dtype=emb.dtype, device=emb.device)
+                dist.all_gather_into_tensor(emb_g, emb, group=self.group)
+            else:
+                emb_g = emb.clone()
+            emb_g.requires_grad_(True)
+            loss, _, _ = ops.triplet_loss(emb_g, triplets_global, self.margin)
+            loss.backward()
+            r = dist.get_rank(self.group) if world > 1 else 0
+            self.model.native_backward(ctx, emb_g.grad[r * emb.size(0):(r + 1) * emb.size(0)])
+            if world > 1:
+                flat, _ = self.model._flat_grads()
+                dist.all_reduce(flat[:-2], op=dist.ReduceOp.SUM, group=self.group)
+            self.opt.step()
+            return loss.detach()
         emb = self.model(x, edge_index, node_ptr_host)
         emb_g = all_gather_rows(emb, self.group)
         loss, _, _ = ops.triplet_loss(emb_g, triplets_global, self.margin)
