@@ -573,61 +573,78 @@ def run_config4(a, dev, kt, peaks, cpu):
 
 
 class Config5:
-    """EigenGCN 2stg+ stage-1 triplet step on an HBM-resident DD-shape corpus: the corpus (adjacency as RAW CSR source
-    lists, one-hot labels, BFS-chunk cluster labels) lives on the device; a step gathers 3T graphs by id, builds the
-    pooling operators P^T and the coarsened adjacency ON THE GPU (K11) and trains WavePoolingGcnEncoder."""
+    """EigenGCN 2stg+ stage-1 triplet step against an HBM-RESIDENT corpus of `num_graphs` DD-shape graphs (BASELINE
+    config 5: 1 M graphs), sharded graph_id % world.  The corpus is the 1,168-graph DD-shape base corpus tiled to
+    `num_graphs` ids; this rank's shard is materialised IN HBM by one K0 gather from the base (compact form:
+    node labels, graph-local int32 endpoints, per-node cluster labels, per-cluster final-pooling weights; 13 GB for 1 M
+    graphs on one GPU).  A step: the host samples 3T graph ids of the shard (anchor / positive / negative by label) and
+    computes their packed offsets; the GPU gathers the batch from the resident corpus, expands it (K0), builds the RAW CSR
+    (K1), the pooling operators P^T and the coarsened adjacency (K11), trains WavePoolingGcnEncoder + triplet loss + Adam.
+    Nothing about a batch is cached between steps."""
 
     def __init__(self, dev, num_graphs, rank=0, world=1, base_graphs=1168):
         from tsg import dense, eigen_synth, synth
-        self.dev = dev
+        from tsg.feeder import DeviceCorpus, DeviceRagged
+        self.dev, self.rank, self.world, self.num_graphs = dev, rank, world, num_graphs
         base = synth.make_corpus("DD", base_graphs, seed=777)
-        self.base = base
         opnd = eigen_synth.make_operands(base, pool_size=10, num_pool_matrix=1, num_pool_final_matrix=1)
-        self.opnd = opnd
-        # corpus of `num_graphs` graphs = the base corpus tiled cyclically (SURVEY 8d; tsg.synth.tile_corpus), sharded by
-        # graph_id % world: this rank owns ids rank, rank + world, ...  Only the base graphs are stored; a corpus id maps
-        # to its base graph, labels y follow the base graph.
-        self.num_graphs, self.rank, self.world = num_graphs, rank, world
-        self.owned = np.arange(rank, num_graphs, world, dtype=np.int64)
+        self.base, self.opnd = base, opnd
+        owned = np.arange(rank, num_graphs, world, dtype=np.int64)
+        bseq = owned % base.num_graphs                       # corpus id -> base graph
+        self.owned, self.y = owned, base.y[bseq]
+        base_dc = DeviceCorpus(base, dev)
+        cb, nptr = base_dc.pack_compact(bseq)                # the shard, assembled on the GPU
+        _, _, eptr = base_dc.offsets(bseq)
+        self.corpus = DeviceCorpus.from_device(cb.label, cb.row, cb.col, nptr, eptr, base.num_node_labels, base_dc.coalesced)
+        t = lambda v, dt: torch.from_numpy(np.ascontiguousarray(v.astype(dt))).to(dev)
+        cl_base = DeviceRagged(base.node_ptr, t(opnd.cluster_of, np.int32))
+        fw_base = DeviceRagged(opnd.cluster_ptr, t(opnd.final_w[0], np.float32))
+        cl_vals, _ = cl_base.gather(bseq)
+        fw_vals, cptr = fw_base.gather(bseq)
+        self.cluster = DeviceRagged(nptr, cl_vals)
+        self.final_w = DeviceRagged(cptr, fw_vals)
+        self.nc = np.diff(cptr).astype(np.int64)
+        self.resident_bytes = int(cb.label.numel() * 4 + cb.row.numel() * 8 + cl_vals.numel() * 4 + fw_vals.numel() * 4
+                                  + 3 * 8 * (owned.shape[0] + 1))
         torch.manual_seed(777)
         self.model = dense.PackedWaveEncoder(base.num_node_labels, 32, 32, 2, 2, num_pool_matrix=1, num_pool_final_matrix=1,
                                              pool_sizes=[10], pred_hidden_dims=[50]).to(dev)
         self.opt = torch.optim.Adam(self.model.parameters(), lr=1e-3)
-        self._batches = {}
 
-    def batch(self, seed, T):
-        """3T owned corpus graphs (anchor / positive / negative by label) -> device operands."""
-        from tsg import dense, eigen_synth, eigenpool, ops, synth
-        if seed in self._batches:
-            return self._batches[seed]
-        dev, base = self.dev, self.base
+    def sample(self, seed, T):
+        """host sampler: local shard indices of T anchors, positives (same label) and negatives (other label)"""
         rng = np.random.default_rng(10_000 * self.rank + seed)
-        owned_base = self.owned[rng.integers(0, self.owned.shape[0], size=4 * T)] % base.num_graphs
-        y = base.y[owned_base]
-        pos_pool, neg_pool = owned_base[y == 1], owned_base[y == 0]
-        anchors = owned_base[:T]
-        ya = base.y[anchors]
-        pos = np.where(ya == 1, pos_pool[rng.integers(0, len(pos_pool), T)], neg_pool[rng.integers(0, len(neg_pool), T)])
-        neg = np.where(ya == 1, neg_pool[rng.integers(0, len(neg_pool), T)], pos_pool[rng.integers(0, len(pos_pool), T)])
-        ids = np.concatenate([anchors, pos, neg])
-        tidx = np.stack([np.arange(T), T + np.arange(T), 2 * T + np.arange(T)], 1).astype(np.int64)
-        sel = synth.select(base, ids)
-        pk = synth.pack(sel)
-        x = torch.from_numpy(pk["x"]).to(dev)
-        ei = torch.from_numpy(pk["edge_index"]).to(dev)
-        N, E = int(sel.node_ptr[-1]), int(ei.size(1))
-        csr_adj = ops.build_csr(ops.EdgeList.from_edge_index(ei), N, mode=ops.CSR_RAW)
-        po = eigen_synth.pack_operands(base, self.opnd, ids)
-        NC, G = int(po["cluster_ptr"][-1]), ids.shape[0]
-        t = lambda v: torch.from_numpy(np.ascontiguousarray(v)).to(dev)
-        cl = t(po["pool"][0][1].astype(np.int32))
-        src, dst, w = po["final"][0]
-        final = [dense.build_rect_csr(ops.EdgeList(t(src), t(dst), int(src.shape[0])), t(w), G, NC)]
-        b = dict(x=x, ei=ei, csr_adj=csr_adj, cl=cl, NC=NC, G=G, N=N, E=E, final=final, gptr=t(po["node_ptr"]),
-                 cptr=t(po["cluster_ptr"]), fptr=torch.arange(G + 1, device=dev, dtype=torch.int64),
-                 tr=torch.from_numpy(tidx).to(dev), el=ops.EdgeList.from_edge_index(ei))
-        self._batches[seed] = b
-        return b
+        M = self.owned.shape[0]
+        pool = {k: np.nonzero(self.y == k)[0] for k in (0, 1)}
+        anchors = rng.integers(0, M, T)
+        ya = self.y[anchors]
+        pos = np.where(ya == 1, pool[1][rng.integers(0, len(pool[1]), T)], pool[0][rng.integers(0, len(pool[0]), T)])
+        neg = np.where(ya == 1, pool[0][rng.integers(0, len(pool[0]), T)], pool[1][rng.integers(0, len(pool[1]), T)])
+        return np.concatenate([anchors, pos, neg]).astype(np.int64)
+
+    def assemble(self, ids):
+        """3T shard indices -> device operands of the step (everything on the GPU from the resident corpus)."""
+        from tsg import dense, ops
+        dev = self.dev
+        cb, nptr = self.corpus.pack_compact(ids)
+        x, ei = cb.expand()                                   # K0: one-hot x [N, 89], int64 edge_index
+        N, E, G = int(nptr[-1]), int(ei.size(1)), ids.shape[0]
+        el = ops.EdgeList.from_edge_index(ei)
+        csr_adj = ops.build_csr(el, N, mode=ops.CSR_RAW)
+        cl_local, _ = self.cluster.gather(ids)
+        fw, cptr = self.final_w.gather(ids)
+        NC = int(cptr[-1])
+        nc = np.diff(cptr)
+        small = torch.from_numpy(np.concatenate([cptr[:-1], np.diff(nptr), nc, cptr])).pin_memory().to(dev, non_blocking=True)
+        coff, n_dev, nc_dev, cptr_dev = small[:G], small[G:2 * G], small[2 * G:3 * G], small[3 * G:]
+        cl = (cl_local + torch.repeat_interleave(coff, n_dev, output_size=N).to(torch.int32)).contiguous()
+        fsrc = torch.arange(NC, device=dev, dtype=torch.int64)
+        fdst = torch.repeat_interleave(torch.arange(G, device=dev, dtype=torch.int64), nc_dev, output_size=NC)
+        final = [dense.build_rect_csr(ops.EdgeList(fsrc, fdst, NC), fw, G, NC)]
+        T = G // 3
+        tidx = torch.from_numpy(np.stack([np.arange(T), T + np.arange(T), 2 * T + np.arange(T)], 1).astype(np.int64)).pin_memory().to(dev, non_blocking=True)
+        return dict(x=x, el=el, csr_adj=csr_adj, cl=cl, NC=NC, G=G, N=N, E=E, final=final, gptr=cb.node_ptr, cptr=cptr_dev,
+                    fptr=torch.arange(G + 1, device=dev, dtype=torch.int64), tr=tidx)
 
     def step(self, b, group=None):
         from tsg import eigenpool, ops
@@ -642,29 +659,37 @@ class Config5:
         self.opt.step()
         return loss.detach()
 
+    def step_from_ids(self, ids, group=None):
+        return self.step(self.assemble(ids), group)
+
 
 def run_config5(a, dev, kt, peaks, cpu):
-    from tsg import ops
-    c5 = Config5(dev, 1168)
+    from tsg import eigenpool, ops
+    c5 = Config5(dev, a.corpus5)
     T = 1168
-    bs = [c5.batch(s, T) for s in range(2)]
-    ms, loss = _timed_steps(lambda i: c5.step(bs[i % 2]), a.config_steps, 3)
-    b = bs[0]
-    from tsg import eigenpool
+    id_lists = [c5.sample(s, T) for s in range(4)]
+    ms, loss = _timed_steps(lambda i: c5.step_from_ids(id_lists[i % 4]), a.config_steps, 3)
+    b = c5.assemble(id_lists[0])
+    ms_dev, _ = _timed_steps(lambda i: c5.step(b), a.config_steps, 2)
     built = eigenpool.build(b["csr_adj"], b["el"], b["cl"], b["NC"], 1)
     P = built["pool"][0]
     D = 64
     z = torch.randn(b["N"], D, device=dev)
     kms = kt(lambda: ops.spmm_raw(P.rowptr, P.colidx, P.val, z))
     alg = 4 * (b["N"] * D + b["NC"] * D) + 8 * b["N"]
-    out = {"workload": f"EigenGCN 2stg+ stage-1 triplet step, DD-shape, 3x{T} graphs packed, WavePoolingGcnEncoder(89,32,32,2,"
-                       "L=2,num_pool_matrix=1,num_pool_final_matrix=1,pool_sizes [10],pred_hidden [50]); pooling operators "
-                       "built on the GPU every step (K11)",
+    out = {"workload": f"EigenGCN 2stg+ stage-1 triplet step against an HBM-resident corpus of {a.corpus5:,} DD-shape graphs "
+                       f"({c5.resident_bytes / 1e9:.1f} GB on this GPU), 3x{T} graphs per step gathered by id on the GPU, "
+                       "WavePoolingGcnEncoder(89,32,32,2,L=2,num_pool_matrix=1,num_pool_final_matrix=1,pool_sizes [10],"
+                       "pred_hidden [50]); CSR + pooling operators (K11) built on the GPU every step",
            "value": b["G"] / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "graphs_per_step": b["G"], "nodes_per_step": b["N"],
-           "directed_edges_per_step": b["E"], "clusters_per_step": b["NC"], "loss": loss,
+           "directed_edges_per_step": b["E"], "clusters_per_step": b["NC"], "loss": loss, "corpus_graphs": a.corpus5,
+           "corpus_resident_bytes": c5.resident_bytes,
+           "value_batch_resident": {"value": b["G"] / (ms_dev / 1e3), "ms_per_step": ms_dev,
+                                    "note": "same step on one batch already assembled in HBM (no gather / expand / CSR build)"},
            "roofline": roofline_block(f"k_spmm_g on P^T (eigen pooling, N={b['N']}, clusters={b['NC']}, D={D})", alg, kms, peaks)}
     if cpu:
         out["cpu_baseline"] = _cpu_wave(c5, 3.0)
+    del c5
     return out
 
 
@@ -958,15 +983,17 @@ def main():
         for p in c5.model.parameters():
             dist.broadcast(p.data, 0)
         T5 = 1168
-        bs5 = [c5.batch(s, T5) for s in range(2)]
+        ids5 = [c5.sample(s, T5) for s in range(4)]
         for i in range(3):
-            c5.step(bs5[i % 2])
-        ms5 = timed(lambda i: c5.step(bs5[i % 2]), a.config_steps)
+            c5.step_from_ids(ids5[i % 4])
+        ms5 = timed(lambda i: c5.step_from_ids(ids5[i % 4]), a.config_steps)
         config5_dp = {"value": world * 3 * T5 * a.config_steps / (ms5 / 1e3), "unit": UNIT, "ms_per_step": ms5 / a.config_steps,
                       "corpus_graphs": a.corpus5, "graphs_owned_per_rank": int(c5.owned.shape[0]),
+                      "corpus_resident_bytes_per_rank": c5.resident_bytes,
                       "sharding": "graph_id % world", "graphs_per_step_per_gpu": 3 * T5,
-                      "note": "EigenGCN (config 5) stage-1 triplet step, data-parallel: each rank samples triplets among the corpus "
-                              "graphs it owns, one all-reduce per step; corpus = DD-shape base graphs tiled to corpus_graphs ids"}
+                      "note": "EigenGCN (config 5) stage-1 triplet step, data-parallel: each rank holds its shard of the corpus in HBM, "
+                              "samples triplets among the graphs it owns, gathers the batch by id on the GPU, one all-reduce per step"}
+        del c5
 
     # ---- CPU baselines (rank 0, N=1 only)
     cpu_baseline = None

@@ -29,6 +29,21 @@ class DeviceCorpus:
         else:
             self.label, self.x, self.feat = None, t(dense_x, np.float32), int(dense_x.shape[1])
 
+    @classmethod
+    def from_device(cls, label: torch.Tensor, row: torch.Tensor, col: torch.Tensor, node_ptr_host: np.ndarray,
+                    edge_ptr_host: np.ndarray, num_labels: int, coalesced: bool) -> "DeviceCorpus":
+        """A corpus whose arrays already live in HBM (e.g. a shard assembled on the GPU from a smaller base corpus:
+        bench.py's 1 M-graph config-5 corpus); only the two offset arrays come from the host."""
+        self = cls.__new__(cls)
+        self.device = label.device
+        self.n = np.diff(node_ptr_host).astype(np.int64); self.e = np.diff(edge_ptr_host).astype(np.int64)
+        self.num_graphs = int(self.n.shape[0])
+        self.node_ptr = torch.from_numpy(np.ascontiguousarray(node_ptr_host, dtype=np.int64)).to(self.device)
+        self.edge_ptr = torch.from_numpy(np.ascontiguousarray(edge_ptr_host, dtype=np.int64)).to(self.device)
+        self.row, self.col, self.label, self.x, self.feat = row, col, label, None, int(num_labels)
+        self.coalesced = bool(coalesced)
+        return self
+
     def offsets(self, ids_host: np.ndarray):
         """Packed offsets for a list of graph ids (host numpy; int64 [B+1] each)."""
         ids = np.asarray(ids_host, dtype=np.int64)
@@ -74,6 +89,32 @@ class DeviceCorpus:
              ptr(self.row), ptr(self.col), ptr(self.label), ptr(label), ptr(rc[0]), ptr(rc[1]), stream_ptr())
         return CompactBatch(label, rc[0], rc[1], d_nptr, d_eptr, self.feat, int(np.diff(eptr).max()) if B else 0,
                             self.coalesced), nptr
+
+
+class DeviceRagged:
+    """Per-graph variable-length rows of 32-bit values resident in HBM (cluster labels per node, pooling weights per
+    cluster, ...), gathered by graph id with the same kernel as the corpus itself (K0 compact with no edges)."""
+
+    def __init__(self, ptr_host: np.ndarray, values: torch.Tensor):
+        assert values.dtype in (torch.int32, torch.float32)
+        self.device = values.device
+        self.len = np.diff(ptr_host).astype(np.int64)
+        self.ptr = torch.from_numpy(np.ascontiguousarray(ptr_host, dtype=np.int64)).to(self.device)
+        self.values = values.contiguous()
+        self._zero_ptr = torch.zeros(self.len.shape[0] + 1, dtype=torch.int64, device=self.device)
+        self._dummy = torch.zeros(4, dtype=torch.int32, device=self.device)
+
+    def gather(self, ids_host: np.ndarray):
+        """-> (values of the chosen graphs, concatenated; their offsets on the host [B+1])."""
+        ids = np.asarray(ids_host, dtype=np.int64)
+        B = ids.shape[0]
+        optr = np.zeros(B + 1, np.int64); np.cumsum(self.len[ids], out=optr[1:])
+        meta = torch.from_numpy(np.concatenate([ids, optr, np.zeros(B + 1, np.int64)])).pin_memory().to(self.device, non_blocking=True)
+        out = torch.empty(int(optr[-1]), dtype=torch.int32, device=self.device)
+        call("tsg_pack_batch_compact", ptr(meta[:B]), ptr(meta[B:2 * B + 1]), ptr(meta[2 * B + 1:]), B, ptr(self.ptr),
+             ptr(self._zero_ptr), ptr(self._dummy), ptr(self._dummy), ptr(self.values.view(torch.int32)), ptr(out),
+             ptr(self._dummy), ptr(self._dummy), stream_ptr())
+        return (out.view(self.values.dtype), optr)
 
 
 def compact_host_batch(corpus: Corpus, graph_ids, triplets: np.ndarray, pin: bool | None = None,
