@@ -207,6 +207,7 @@ int tsg_relu_bwd_colsum_rank1(const float* dY, const float* Y /*nullable*/, cons
 #define TSG_LIN_NORMALIZE 1
 #define TSG_LIN_RELU 2
 #define TSG_LIN_NODEBN 4
+#define TSG_LIN_SOFTMAX 8    /* row softmax of the product (DiffPool assignment, encoders.py:369); not combined with the others */
 int tsg_linear_fwd(const float* X, const float* W, const float* bias /*nullable*/, float* Y,
                    int64_t num_rows, int64_t in_feat, int64_t out_feat, int w_transposed, int flags,
                    void* stream);
@@ -541,6 +542,10 @@ int tsg_sag_step_bwd_compact(const tsg_sag_shape* shape, const tsg_sag_head* hea
                              const int64_t* level_ptr, const float* const* params, const float* emb, const float* demb,
                              float* const* grads, void* arena, size_t arena_bytes, void* workspace,
                              size_t workspace_bytes, void* stream);
+
+/* Row-softmax backward from the saved output of tsg_linear_fwd(..., TSG_LIN_SOFTMAX): dL = S * (dS - rowsum(S * dS))
+ * (SoftPoolingGcnEncoder's assignment, encoders.py:369). */
+int tsg_softmax_bwd(const float* S, const float* dS, float* dL, int64_t num_rows, int64_t num_cols, void* stream);
 
 /* tsg_spmm plus dot_out[r] = Y[r, :] . dot_vec from K2's epilogue (conv + the score layer's h @ ws of
  * Code/sag/layers.py:18 in one pass); bit-identical to tsg_spmm followed by tsg_linear_fwd(Y, dot_vec, out_feat = 1),

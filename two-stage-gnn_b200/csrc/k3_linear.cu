@@ -84,6 +84,13 @@ __device__ __forceinline__ float group_sum(float v, unsigned mask) {
   return v;
 }
 
+template <int CG>
+__device__ __forceinline__ float group_max(float v, unsigned mask) {
+#pragma unroll
+  for (int d = CG / 2; d > 0; d >>= 1) v = fmaxf(v, __shfl_xor_sync(mask, v, d));
+  return v;
+}
+
 // epilogue on one row held as 4 columns per lane across CG lanes. `ok[c]` masks padded columns.
 template <int CG>
 __device__ __forceinline__ void row_epilogue(float (&u)[4], const bool (&ok)[4], int M, int flags,
@@ -113,6 +120,18 @@ __device__ __forceinline__ void row_epilogue(float (&u)[4], const bool (&ok)[4],
     float rstd = 1.0f / sqrtf(var + BN_EPS);
 #pragma unroll
     for (int c = 0; c < 4; ++c) u[c] = (u[c] - mean) * rstd;
+  }
+  if (flags & TSG_LIN_SOFTMAX) {                 // DiffPool's assignment: softmax over the row (encoders.py:369)
+    float mx = -3.4e38f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) if (ok[c]) mx = fmaxf(mx, u[c]);
+    mx = group_max<CG>(mx, gmask);
+    float se = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { u[c] = ok[c] ? expf(u[c] - mx) : 0.f; se += u[c]; }
+    se = group_sum<CG>(se, gmask);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) u[c] = u[c] / se;
   }
 }
 
@@ -351,6 +370,25 @@ k_dense_epilogue_bwd(const float* __restrict__ X, const float* __restrict__ W, c
       for (int c = 0; c < 4; ++c) {
         u[j][c] += b4[c];
         g[c] = (live && ok[c]) ? dO[(size_t)(r0 + r) * M + cg * 4 + c] : 0.f;
+      }
+      if (flags & TSG_LIN_SOFTMAX) {             // dL = S * (dS - rowsum(S * dS)), S recomputed from the logits
+        float mx = -3.4e38f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) if (ok[c]) mx = fmaxf(mx, u[j][c]);
+        mx = group_max<CG>(mx, gmask);
+        float se = 0.f, sm4[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { sm4[c] = ok[c] ? expf(u[j][c] - mx) : 0.f; se += sm4[c]; }
+        se = group_sum<CG>(se, gmask);
+        float dot = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { sm4[c] = sm4[c] / se; dot += sm4[c] * g[c]; }
+        dot = group_sum<CG>(dot, gmask);
+        if (live) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) if (ok[c]) dU[(size_t)(r0 + r) * M + cg * 4 + c] = sm4[c] * (g[c] - dot);
+        }
+        continue;
       }
       // forward recompute
       float nrm = 1.f, v[4], rl[4];
@@ -851,4 +889,33 @@ extern "C" int tsg_linear_bwd_weight(const float* X, const float* dY, float* dW,
   }
   launch_partial_sum_final(part, dW, (int)(K * M), nullptr, grid, (int)(K * M), st);
   return check_launch("linear_bwd_weight");
+}
+
+
+// Row-softmax backward from the SAVED output: dL = S * (dS - rowsum(S * dS)).  Warp per row.  (The epilogue backward
+// above could recompute S from the logits, but that re-does the 164 x 100 product of DiffPool's assignment layer:
+// +1 ms per step measured; the forward already wrote S.)
+namespace tsg {
+__global__ void __launch_bounds__(256)
+k_softmax_bwd(const float* __restrict__ S, const float* __restrict__ dS, float* __restrict__ dL, int64_t N, int M) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < N; r += nwarps) {
+    const float* s = S + r * M; const float* g = dS + r * M;
+    float dot = 0.f;
+    for (int c = lane; c < M; c += 32) dot = fmaf(s[c], g[c], dot);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    for (int c = lane; c < M; c += 32) dL[r * M + c] = s[c] * (g[c] - dot);
+  }
+}
+}  // namespace tsg
+
+extern "C" int tsg_softmax_bwd(const float* S, const float* dS, float* dL, int64_t N, int64_t M, void* stream) {
+  TSG_REQUIRE(N >= 0 && M > 0 && M < (int64_t)0x7fffffff, "softmax_bwd: bad shape");
+  if (N == 0) return TSG_OK;
+  TSG_REQUIRE(S && dS && dL, "softmax_bwd: null pointer");
+  tsg::k_softmax_bwd<<<tsg::grid_for(N, 8), 256, 0, (cudaStream_t)stream>>>(S, dS, dL, N, (int)M);
+  return tsg::check_launch("softmax_bwd");
 }

@@ -42,6 +42,7 @@ _PROTOTYPES = {
     "tsg_relu_bwd_colsum_rank1": (I, [P, P, P, P, P, P, I64, I64, P, SZ, P]),
     "tsg_linear_fwd": (I, [P, P, P, P, I64, I64, I64, I, I, P]),
     "tsg_dense_epilogue_bwd": (I, [P, P, P, P, P, I64, I64, I64, I, P]),
+    "tsg_softmax_bwd": (I, [P, P, P, I64, I64, P]),
     "tsg_linear_bwd_weight_workspace_bytes": (SZ, [I64, I64]),
     "tsg_linear_bwd_weight": (I, [P, P, P, P, I64, I64, I64, P, SZ, P]),
     "tsg_dense_to_coo_workspace_bytes": (SZ, [I64, I64]),

@@ -73,7 +73,7 @@ class PackedSoftPoolEncoder(nn.Module):
                              self.assign_conv_last_modules[0])
         za = gcn_forward(x, csr, aconvs, self.bn)                                            # :365
         ap = self.assign_pred_modules[0]
-        s = F.softmax(ops.linear(za, ap.weight.t(), ap.bias), dim=-1)                        # :369
+        s = ops.linear(za, ap.weight.t(), ap.bias, ops.LIN_SOFTMAX)                          # :366-369: Linear + softmax in K3's epilogue
         t = ops.spmm(csr, s)                                                                 # adj @ S
         c = ops.seg_contract(s, torch.cat([z, t], dim=1), graph_ptr)                         # :374-375
         D = z.size(1)

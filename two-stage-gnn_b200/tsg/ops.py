@@ -23,7 +23,7 @@ SPMM_RELU = 1
 SPMM_EXACT = 2
 SPMM_EXACT_DEFAULT = False   # True: separately rounded products everywhere (6 % slower K2)
 READOUT_MAX, READOUT_MEAN, READOUT_SUM = 1, 2, 4
-LIN_NORMALIZE, LIN_RELU, LIN_NODEBN = 1, 2, 4
+LIN_NORMALIZE, LIN_RELU, LIN_NODEBN, LIN_SOFTMAX = 1, 2, 4, 8
 
 
 # --------------------------------------------------------------------------------------------
@@ -350,16 +350,21 @@ class _Linear(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, w, bias, flags: int):
+        x, w = x.contiguous(), w.contiguous()
         y = linear_raw(x, w, bias, False, flags)
         ctx.flags = flags
-        ctx.save_for_backward(x, w, bias)
+        ctx.save_for_backward(x, w, bias, y if flags == LIN_SOFTMAX else None)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, w, bias = ctx.saved_tensors
+        x, w, bias, y = ctx.saved_tensors
         dy = dy.contiguous()
-        if ctx.flags:
+        if ctx.flags == LIN_SOFTMAX:               # from the saved output: no recomputation of the product
+            du = torch.empty_like(dy)
+            call("tsg_softmax_bwd", ptr(y), ptr(dy), ptr(du), dy.size(0), dy.size(1), stream_ptr())
+            dy = du
+        elif ctx.flags:
             du = torch.empty_like(dy)
             n, k = x.shape
             call("tsg_dense_epilogue_bwd", ptr(x), ptr(w), ptr(bias), ptr(dy), ptr(du), n, k, dy.size(1),
