@@ -80,6 +80,36 @@ def all_reduce_grads_and_loss(params, loss_local: torch.Tensor, num_local: int, 
     return flat[-2]
 
 
+class CapturedStep:
+    """A whole training step (forward through the tsg operators, loss, backward, clipping, optimiser) captured ONCE into a
+    CUDA graph and replayed -- for steps whose shapes do not change between iterations (the reference's "original"
+    setting trains on the same packed corpus every epoch, Code/sage+gat+diffpool/train.py:85-152): ~200 launches of a few
+    microseconds each become one graph launch.  This is what the C ABI's contract buys (include/tsg.h: every compute
+    entry point only enqueues on the caller's stream, never allocates, never synchronises; tsg_init_device() runs
+    before the capture): the library's kernels, memsets and last-CTA reduction tickets are all capturable.
+
+    `body()` must read its inputs from tensors that stay alive and in place (update them with copy_()), use an optimiser
+    built with `capturable=True`, and return a tensor (the loss); its value after each replay() is in `.out`."""
+
+    def __init__(self, body, warmup: int = 3):
+        from . import _lib
+        _lib.init_device()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                    # warm-up on a side stream (allocator, lazy inits, autotuned paths)
+            for _ in range(warmup):
+                body()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = body()
+
+    def replay(self) -> torch.Tensor:
+        self.graph.replay()
+        return self.out
+
+
 def _check_status():
     from . import nn as _nn
     _nn.check_fused_status()
