@@ -140,7 +140,7 @@ class TripletTrainer:
             if world > 1:
                 flat, _ = self.model._flat_grads()
                 flat[-1:].fill_(1.0)           # (NOT flat[-1] = 1.0: a Python scalar store is a blocking H2D copy -- measured
-                                               # 1.2 ms of host stall per step, 1.43 -> 1.87 ms at any N > 1: scratch/scale_probe2.py)
+                                               # 1.2 ms of host stall per step, 1.43 -> 1.87 ms at any N > 1: profiles/tools/scale_probe2.py)
                 flat.mul_(float(triplets.size(0)))                       # [T_r * grads, T_r * loss, T_r]
                 dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
                 flat.div_(flat[-1].clone())
