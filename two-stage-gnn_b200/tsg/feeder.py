@@ -13,6 +13,31 @@ from ._lib import call, ptr, stream_ptr
 from .synth import Corpus
 
 
+class _PinnedRing:
+    """Four reusable page-locked int64 staging buffers: a per-step `.pin_memory()` on a fresh tensor is a host
+    allocation + registration every call.  A slot is reused only after the upload issued from it has left it."""
+
+    def __init__(self):
+        self.slots, self.pos = [None] * 4, -1
+
+    def stage(self, parts, device) -> torch.Tensor:
+        need = sum(int(p.shape[0]) for p in parts)
+        self.pos = (self.pos + 1) % 4
+        slot = self.slots[self.pos]
+        if slot is None or slot[0].numel() < need:
+            slot = self.slots[self.pos] = [torch.empty(max(need, 1024), dtype=torch.int64, pin_memory=True), None]
+        buf, busy = slot
+        if busy is not None:
+            busy.synchronize()
+        host = buf[:need]
+        np.concatenate(parts, out=host.numpy())
+        dev = host.to(device, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        slot[1] = ev
+        return dev
+
+
 class DeviceCorpus:
     def __init__(self, corpus: Corpus, device, dense_x: np.ndarray | None = None):
         self.device = device
@@ -54,8 +79,10 @@ class DeviceCorpus:
     def _stage(self, ids_host: np.ndarray):
         """ids + packed offsets of the chosen graphs as ONE small pinned upload: (meta on the device, B, nptr, eptr)."""
         ids, nptr, eptr = self.offsets(ids_host)
-        meta = torch.from_numpy(np.concatenate([ids, nptr, eptr])).pin_memory().to(self.device, non_blocking=True)
-        return meta, ids.shape[0], nptr, eptr
+        ring = self.__dict__.get("_ring")
+        if ring is None:
+            ring = self.__dict__["_ring"] = _PinnedRing()
+        return ring.stage([ids, nptr, eptr], self.device), ids.shape[0], nptr, eptr
 
     def pack(self, ids_host: np.ndarray):
         """-> (x [sum n, F] f32, edge_index [2, sum E] i64, node_ptr_host).  One small H2D (ids + offsets)."""
@@ -103,13 +130,14 @@ class DeviceRagged:
         self.values = values.contiguous()
         self._zero_ptr = torch.zeros(self.len.shape[0] + 1, dtype=torch.int64, device=self.device)
         self._dummy = torch.zeros(4, dtype=torch.int32, device=self.device)
+        self._ring = _PinnedRing()
 
     def gather(self, ids_host: np.ndarray):
         """-> (values of the chosen graphs, concatenated; their offsets on the host [B+1])."""
         ids = np.asarray(ids_host, dtype=np.int64)
         B = ids.shape[0]
         optr = np.zeros(B + 1, np.int64); np.cumsum(self.len[ids], out=optr[1:])
-        meta = torch.from_numpy(np.concatenate([ids, optr, np.zeros(B + 1, np.int64)])).pin_memory().to(self.device, non_blocking=True)
+        meta = self._ring.stage([ids, optr, np.zeros(B + 1, np.int64)], self.device)
         out = torch.empty(int(optr[-1]), dtype=torch.int32, device=self.device)
         call("tsg_pack_batch_compact", ptr(meta[:B]), ptr(meta[B:2 * B + 1]), ptr(meta[2 * B + 1:]), B, ptr(self.ptr),
              ptr(self._zero_ptr), ptr(self._dummy), ptr(self._dummy), ptr(self.values.view(torch.int32)), ptr(out),
