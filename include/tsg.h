@@ -419,6 +419,21 @@ int tsg_mlp1_train(const float* emb, const int64_t* labels, int64_t num_samples,
                    float* losses /*nullable*/, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * K15  DiffPool link-prediction loss
+ *   replaces the `self.linkpred` branch of SoftPoolingGcnEncoder.loss (Code/sage+gat+diffpool/encoders.py:416-440):
+ *   L = sum_g sum_{i,j<n_g} [-A_ij log(P_ij + eps) - (1 - A_ij) log(1 - P_ij + eps)] / num_entries, P = min(S S^T, 1),
+ *   num_entries = sum_g n_g^2 (host), on packed assignment rows S [sum n, K] (K <= 128) and the RAW CSR of the 0/1
+ *   adjacency (column ids global, as built by tsg_csr_build(TSG_CSR_RAW)).  P is never materialised.  bwd writes dS.
+ * ------------------------------------------------------------------------------------------ */
+size_t tsg_linkpred_workspace_bytes(int64_t num_graphs);
+int tsg_linkpred_loss_fwd(const float* S, const int64_t* graph_ptr, const int32_t* rowptr, const int32_t* colidx,
+                          int64_t num_graphs, int64_t assign_dim, double num_entries, float eps, float* loss,
+                          void* workspace, size_t workspace_bytes, void* stream);
+int tsg_linkpred_loss_bwd(const float* S, const int64_t* graph_ptr, const int32_t* rowptr, const int32_t* colidx,
+                          int64_t num_graphs, int64_t assign_dim, double num_entries, float eps, const float* dloss,
+                          float* dS, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * H1  TU-format dataset loader -> packed corpus arrays.  HOST pointers throughout.
  *   replaces `read_graphfile` (Code/sage+gat+diffpool/load_data.py:12-126, Code/eigengcn/load_data.py) in
  *   TSG_TU_NETWORKX mode (node set / order / labels exactly as the networkx graphs the reference builds) and

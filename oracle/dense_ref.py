@@ -147,6 +147,16 @@ def soft_pool_readout(x: Tensor, adj: Tensor, batch_num_nodes, p: Dict, bn: bool
     return torch.cat([out0, out1], dim=1), dict(s=s, xp=xp, ap=ap, z=z)
 
 
+def link_pred_loss(s: Tensor, adj: Tensor, batch_num_nodes, eps: float = 1e-7) -> Tensor:
+    """The linkpred branch of SoftPoolingGcnEncoder.loss (encoders.py:416-440, adj_hop = 1) with the intended clamp at 1:
+    s [B, N, K] masked assignment, adj [B, N, N]; entries outside the n x n block are dropped; normalised by sum n^2."""
+    pred = torch.clamp(s @ s.transpose(1, 2), max=1.0)
+    ll = -adj * torch.log(pred + eps) - (1 - adj) * torch.log(1 - pred + eps)
+    mask = construct_mask(adj.size(1), batch_num_nodes).to(s.dtype)
+    ll = ll * (mask @ mask.transpose(1, 2))
+    return ll.sum() / float(sum(int(n) * int(n) for n in batch_num_nodes))
+
+
 # ---------------------------------------------------------------------------------------------
 # EigenPooling  (Code/eigengcn/encoders.py:396-417 Pool; :323-378 WavePoolingGcnEncoder.forward)
 # ---------------------------------------------------------------------------------------------

@@ -166,6 +166,46 @@ def golden_diffpool(enc):
           dims=np.array([N, Fi, H, O, L]), **_state(model), **_grads(model))
 
 
+def golden_linkpred(enc):
+    """SoftPoolingGcnEncoder.loss with linkpred=True (encoders.py:409-441).  Two upstream defects have to be papered
+    over to RUN it at all, both recorded here because they shape the fixture: (1) `self.link_loss[1-adj_mask.byte()] = 0.0`
+    indexes with a uint8 mask (an error since torch 1.2): uint8 masks are converted to bool for the duration of the
+    call; (2) the clamp `torch.min(pred_adj, torch.Tensor(1).cuda())` uses an UNINITIALISED one-element tensor: the
+    call is given the intended constant 1.0 (for softmax rows S S^T <= 1, so the intended clamp is the identity)."""
+    torch.manual_seed(782)
+    rng = np.random.default_rng(782)
+    N, Fi, H, O, L, n = 24, 8, 8, 8, 3, 17
+    model = enc.SoftPoolingGcnEncoder(N, Fi, H, O, 2, L, assign_hidden_dim=8, assign_ratio=0.25, num_pooling=1, bn=True,
+                                      linkpred=True, args=_Args(), final_dim="number_classes")
+    adj = torch.from_numpy(_graph(rng, n, N))[None]
+    x = torch.zeros(1, N, Fi); x[0, :n] = torch.randn(n, Fi)
+    out, ypred = model(x, adj, np.array([n]), assign_x=x)
+    model.assign_tensor.retain_grad()
+    _setitem, _Tensor = torch.Tensor.__setitem__, torch.Tensor
+
+    def setitem(self, idx, val):
+        if getattr(idx, "dtype", None) == torch.uint8:
+            idx = idx.bool()
+        return _setitem(self, idx, val)
+
+    class _T(torch.Tensor):                    # torch.Tensor(1) -> tensor([1.]) (the intended clamp constant)
+        def __new__(cls, *a, **k):
+            if len(a) == 1 and a[0] == 1 and not k:
+                return torch.ones(1)
+            return _Tensor(*a, **k)
+    torch.Tensor.__setitem__ = setitem
+    torch.Tensor = _T
+    try:
+        total = model.loss(ypred, torch.tensor([1]), adj, np.array([n]))
+    finally:
+        torch.Tensor = _Tensor
+        torch.Tensor.__setitem__ = _setitem
+    link = model.link_loss
+    link.backward()
+    _save("dense_linkpred.npz", adj=_np(adj), n=np.array(n), assign=_np(model.assign_tensor), link_loss=_np(link),
+          total_loss=_np(total), dassign=_np(model.assign_tensor.grad), dims=np.array([N, Fi, H, O, L]))
+
+
 def golden_eigen(eig):
     torch.manual_seed(781)
     rng = np.random.default_rng(781)
@@ -312,6 +352,7 @@ def main():
     if want("gcn_forward"): golden_gcn_forward(enc)
     if want("diffpool"): golden_diffpool(enc)
     if want("diffpool_cfg4"): golden_diffpool_cfg4(enc)
+    if want("linkpred"): golden_linkpred(enc)
     gat = _import_from("sage+gat+diffpool", "encoders_GAT")
     if want("gat"): golden_gat(gat)
     if want("gat_cfg3"): golden_gat_cfg3(gat)

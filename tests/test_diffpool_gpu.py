@@ -152,3 +152,44 @@ def test_linear_bwd_weight_tensor_core_route(cuda, k, m):
     assert rel_err(db, dy.double().sum(0)) <= 1e-5
     dw2, _ = ops.linear_bwd_weight(x, dy, want_bias=False)
     assert torch.equal(dw, dw2)
+
+
+def test_linkpred_loss_matches_reference_fixture_and_oracle(cuda):
+    """K15 vs the fixture produced by the REAL SoftPoolingGcnEncoder.loss(linkpred=True), and vs the oracle on a packed
+    batch of DD-shape graphs at K = 100 (sizes that cross the 32-row tile, a 1-node graph, an asymmetric adjacency)."""
+    from tsg import dense, ops
+    d = load("dense_linkpred.npz")
+    n = int(d["n"])
+    csr, _, _ = dense.dense_to_csr(d["adj"].to(cuda), [n], [n])
+    s = d["assign"][0, :n].to(cuda).clone().requires_grad_(True)
+    gptr = torch.tensor([0, n], device=cuda)
+    l = ops.linkpred_loss(s, gptr, csr, float(n * n))
+    l.backward()
+    assert rel_err(l, torch.tensor(float(d["link_loss"]))) <= TOL
+    assert rel_err(s.grad, d["dassign"][0, :n]) <= TOL
+    # packed batch vs oracle
+    rng = np.random.default_rng(5)
+    ns = [269, 1, 33, 64, 100, 7]
+    B, N, K = len(ns), 300, 100
+    adj = np.zeros((B, N, N), np.float32)
+    for b, m in enumerate(ns):
+        a = (rng.random((m, m)) < 0.03)
+        a = np.triu(a, 1); a = (a | a.T).astype(np.float32)
+        adj[b, :m, :m] = a
+    adj[3, 0, 5] = 1.0; adj[3, 5, 0] = 0.0                     # asymmetric entry
+    adj = torch.from_numpy(adj)
+    g = torch.Generator().manual_seed(1)
+    S = torch.softmax(torch.randn(B, N, K, generator=g) * 2, dim=-1)
+    for b, m in enumerate(ns):
+        S[b, m:] = 0
+    So = S.clone().requires_grad_(True)
+    lo = D.link_pred_loss(So, adj, ns)
+    (lo * 3.0).backward()
+    csr, _, _ = dense.dense_to_csr(adj.to(cuda), ns, ns)
+    sp = dense.pack_rows(S.to(cuda), ns).clone().requires_grad_(True)
+    gptr = torch.tensor(np.concatenate([[0], np.cumsum(ns)]), device=cuda)
+    lg = ops.linkpred_loss(sp, gptr, csr, float(sum(m * m for m in ns)))
+    (lg * 3.0).backward()
+    assert rel_err(lg, lo) <= TOL
+    ref = torch.cat([So.grad[b, :m] for b, m in enumerate(ns)])
+    assert rel_err(sp.grad, ref) <= TOL

@@ -178,3 +178,13 @@ def test_eigen_cfg5_matches_reference():
         assert rel_err(c["weight"].grad, d[f"grad/{nm}.weight"]) <= 1e-5, nm
     for c, nm in zip(p["conv_after"][0], conv_names("conv_first_after_pool.0", "conv_block_after_pool.0", "conv_last_after_pool.0", L)):
         assert rel_err(c["weight"].grad, d[f"grad/{nm}.weight"]) <= 1e-5, nm
+
+
+def test_linkpred_loss_matches_reference():
+    """encoders.py:416-440 run for real (two upstream defects papered over by the generator, see golden_linkpred)."""
+    d = load("dense_linkpred.npz")
+    s = d["assign"].clone().requires_grad_(True)
+    l = D.link_pred_loss(s, d["adj"], [int(d["n"])])
+    l.backward()
+    assert abs(float(l) - float(d["link_loss"])) <= PIN * abs(float(d["link_loss"]))
+    assert rel_err(s.grad, d["dassign"]) <= 5e-6

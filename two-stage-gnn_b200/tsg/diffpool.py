@@ -86,6 +86,13 @@ class PackedSoftPoolEncoder(nn.Module):
         out = torch.cat([out0, out1], dim=1)
         return (out, dict(s=s, xp=xp, ap=apool)) if return_aux else out
 
+    def link_loss(self, s, csr: CSR, graph_ptr, num_nodes_host):
+        """The `--linkpred` term of SoftPoolingGcnEncoder.loss (encoders.py:416-440) for the assignment `s` returned by
+        readout(..., return_aux=True)["s"]; `num_nodes_host` = graph sizes (numpy / list) for the normaliser sum n^2."""
+        import numpy as np
+        n = np.asarray(num_nodes_host, dtype=np.float64)
+        return ops.linkpred_loss(s, graph_ptr, csr, float((n * n).sum()))
+
     def forward(self, x, csr: CSR, graph_ptr, has_pad):
         output = self.readout(x, csr, graph_ptr, has_pad)
         if self.final_dim == "pretrain":

@@ -637,3 +637,35 @@ def seg_contract(x, y, graph_ptr):
 
 def seg_linear(x, w, graph_ptr):
     return _SegLinear.apply(x, w, graph_ptr)
+
+
+# --------------------------------------------------------------------------------------------
+# K15 DiffPool link-prediction loss
+# --------------------------------------------------------------------------------------------
+class _LinkPredLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, s, graph_ptr, csr: CSR, num_entries: float, eps: float):
+        s = s.contiguous()
+        G, K = graph_ptr.numel() - 1, s.size(1)
+        loss = torch.empty((), dtype=torch.float32, device=s.device)
+        wsb = lib.tsg_linkpred_workspace_bytes(G)
+        ws = workspace(wsb, s.device)
+        call("tsg_linkpred_loss_fwd", ptr(s), ptr(graph_ptr), ptr(csr.rowptr), ptr(csr.colidx), G, K, float(num_entries),
+             float(eps), ptr(loss), ptr(ws), wsb, stream_ptr())
+        ctx.csr, ctx.num_entries, ctx.eps = csr, float(num_entries), float(eps)
+        ctx.save_for_backward(s, graph_ptr)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        s, gptr = ctx.saved_tensors
+        ds = torch.empty_like(s)
+        call("tsg_linkpred_loss_bwd", ptr(s), ptr(gptr), ptr(ctx.csr.rowptr), ptr(ctx.csr.colidx), gptr.numel() - 1, s.size(1),
+             ctx.num_entries, ctx.eps, ptr(dloss.contiguous().view(1)), ptr(ds), stream_ptr())
+        return ds, None, None, None, None
+
+
+def linkpred_loss(s: torch.Tensor, graph_ptr: torch.Tensor, csr_raw: CSR, num_entries: float, eps: float = 1e-7):
+    """K15: SoftPoolingGcnEncoder.loss's link-prediction term (Code/sage+gat+diffpool/encoders.py:416-440) on packed
+    assignment rows s [sum n, K] and the RAW CSR of the 0/1 adjacency; num_entries = sum_g n_g^2 (host)."""
+    return _LinkPredLoss.apply(s, graph_ptr, csr_raw, num_entries, eps)

@@ -26,7 +26,9 @@ SURVEY A.3, with the reference file:line it papers over):
     * `Tensor.numpy()` on a CUDA / grad tensor goes through `.detach().cpu()` (Code/sag/train_triplet.py:49,91);
     * `nn.Sequential.forward` moves a CPU input to the module's device, `F.cross_entropy` its target to the input's
       device and `Tensor.eq` its other operand to self's device (sag/train_triplet.py:104-130 feeds CPU tensors to a
-      CUDA MLP and compares a CUDA prediction with a CPU label).
+      CUDA MLP and compares a CUDA prediction with a CPU label);
+    * index assignment through a uint8 mask (an error since torch 1.2) is taken as the bool mask it meant
+      (sage+gat+diffpool/encoders.py:436, the --linkpred loss).
   script text (compiled from an AST of the file, the file itself is only read)
     * `def evaluate(train_loader, val_loader, model, device)` called as `evaluate(a, b, model, name=..., max_num_examples=...)`
       (sag/train_triplet_pre_train.py:34 vs :242,277,282,285): the definition gains `device=None, **_ignored`, a missing
@@ -193,6 +195,15 @@ def _install_device_hygiene() -> None:
             return _ce(input, target, *a, **k)
         cross_entropy._tsg = True
         F.cross_entropy = cross_entropy
+    if not getattr(torch.Tensor.__setitem__, "_tsg", False):
+        _setitem = torch.Tensor.__setitem__
+
+        def __setitem__(self, idx, val):             # encoders.py:436: link_loss[1 - adj_mask.byte()] = 0.0 (uint8 mask)
+            if getattr(idx, "dtype", None) == torch.uint8:
+                idx = idx.bool()
+            return _setitem(self, idx, val)
+        __setitem__._tsg = True
+        torch.Tensor.__setitem__ = __setitem__
     if not getattr(torch.Tensor.eq, "_tsg", False):
         _eq = torch.Tensor.eq
 
