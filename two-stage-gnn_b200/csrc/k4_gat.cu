@@ -16,6 +16,7 @@
 //           order)  +  k_gat_bwd_row (per row: ds1_i).  Sequential per segment: deterministic, no atomics.
 // HBM-bound gathers; scores are 4-byte scattered reads that stay in L2 (the whole graph block is ~100 KB).
 #include "common.cuh"
+#include <stdlib.h>
 #include <float.h>
 
 namespace tsg {
@@ -265,6 +266,128 @@ k_gat_bwd_col_v4(const int* __restrict__ t_rowptr, const int* __restrict__ t_col
   }
 }
 
+
+// v5 (round 2): ONE gathering sweep instead of two.  ncu on the config-3 shape (profiles/r02_kernels_ncu.md): v4 is
+// issue bound (76 % issue active, 7 % of the HBM peak, 1.14 ms = 39 % of the GAT step) and half of its instructions are
+// the second sweep re-gathering the dhp rows.  Only dz_ij = alpha_ij (dhp_i . h_j - t) lrelu'(pre_ij) needs the column
+// total t; dh_j = sum_i alpha_ij dhp_i does not.  So the sweep accumulates dh_j and t together and parks (alpha_ij *
+// lrelu', dhp_i . h_j) per entry in a per-warp shared-memory strip; a second, gather-free pass (one LANE per entry)
+// finishes dz and ds2.  Columns longer than the strip (GB5_CAP entries) take v4's two-sweep body.
+constexpr int GB5_CAP = 192;
+template <int GB_MAXF4>
+__global__ void __launch_bounds__(256)
+k_gat_bwd_col_v5(const int* __restrict__ t_rowptr, const int* __restrict__ t_colidx, const int* __restrict__ t_eid,
+                 const float* __restrict__ h, const float* __restrict__ s1, const float* __restrict__ s2,
+                 const float* __restrict__ mx, const float* __restrict__ zs, const float* __restrict__ dhp,
+                 int n, int heads, int F, float slope, float* __restrict__ dz_coo,
+                 float* __restrict__ dh, float* __restrict__ ds2) {
+  __shared__ float s_asf[8][GB5_CAP], s_part[8][GB5_CAP];
+  const int lane = threadIdx.x & 31, grp = lane >> 3, l = lane & 7, wib = threadIdx.x >> 5;
+  const int W4 = heads * F / 4, F4 = F / 4;
+  const int64_t items = (int64_t)n * heads;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const float4* h4 = reinterpret_cast<const float4*>(h);
+  const float4* d4p = reinterpret_cast<const float4*>(dhp);
+  for (int64_t it = warp; it < items; it += nwarps) {
+    const int j = (int)(it / heads), hd = (int)(it - (int64_t)j * heads);
+    const int p0 = t_rowptr[j], p1 = t_rowptr[j + 1];
+    const int deg = p1 - p0;
+    const float sj = s2[it], m = mx[it], z = zs[it];
+    const bool strip = deg <= GB5_CAP;
+    float4 hj[GB_MAXF4];
+#pragma unroll
+    for (int q = 0; q < GB_MAXF4; ++q)
+      hj[q] = (l + 8 * q < F4) ? h4[(int64_t)j * W4 + hd * F4 + l + 8 * q] : make_float4(0.f, 0.f, 0.f, 0.f);
+    float t = 0.f;
+    float4 acc[GB_MAXF4];
+#pragma unroll
+    for (int q = 0; q < GB_MAXF4; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // the gathering sweep: t = sum_i alpha_ij (dhp_i . h_j), dh_j = sum_i alpha_ij dhp_i
+    for (int pb = p0; pb < p1; pb += 4) {
+      const int p = pb + grp;
+      const bool valid = p < p1;
+      const int i = valid ? t_colidx[p] : j;
+      float4 d[GB_MAXF4];
+      float part = 0.f;
+#pragma unroll
+      for (int q = 0; q < GB_MAXF4; ++q) {
+        if (l + 8 * q < F4) {
+          d[q] = d4p[(int64_t)i * W4 + hd * F4 + l + 8 * q];
+          part += d[q].x * hj[q].x + d[q].y * hj[q].y + d[q].z * hj[q].z + d[q].w * hj[q].w;
+        } else {
+          d[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      part += __shfl_xor_sync(0xffffffffu, part, 1);
+      part += __shfl_xor_sync(0xffffffffu, part, 2);
+      part += __shfl_xor_sync(0xffffffffu, part, 4);
+      const float pre = s1[(int64_t)i * heads + hd] + sj;
+      const float a = expf(lrelu(pre, slope) - m) / z;
+      if (valid) {
+        t += a * part;
+        if (strip && l == 0) { s_asf[wib][p - p0] = a * (pre > 0.f ? 1.f : slope); s_part[wib][p - p0] = part; }
+#pragma unroll
+        for (int q = 0; q < GB_MAXF4; ++q) {
+          acc[q].x = fmaf(a, d[q].x, acc[q].x); acc[q].y = fmaf(a, d[q].y, acc[q].y);
+          acc[q].z = fmaf(a, d[q].z, acc[q].z); acc[q].w = fmaf(a, d[q].w, acc[q].w);
+        }
+      }
+    }
+    t += __shfl_xor_sync(0xffffffffu, t, 8);
+    t += __shfl_xor_sync(0xffffffffu, t, 16);
+#pragma unroll
+    for (int q = 0; q < GB_MAXF4; ++q) {
+#pragma unroll
+      for (int o = 8; o <= 16; o <<= 1) {
+        acc[q].x += __shfl_xor_sync(0xffffffffu, acc[q].x, o); acc[q].y += __shfl_xor_sync(0xffffffffu, acc[q].y, o);
+        acc[q].z += __shfl_xor_sync(0xffffffffu, acc[q].z, o); acc[q].w += __shfl_xor_sync(0xffffffffu, acc[q].w, o);
+      }
+      if (grp == 0 && l + 8 * q < F4)
+        reinterpret_cast<float4*>(dh)[(int64_t)j * W4 + hd * F4 + l + 8 * q] = acc[q];
+    }
+    float dsum = 0.f;
+    if (strip) {                                     // gather-free finish: one lane per entry
+      __syncwarp();
+      for (int e = lane; e < deg; e += 32) {
+        const float dzv = s_asf[wib][e] * (s_part[wib][e] - t);
+        dsum += dzv;
+        dz_coo[(int64_t)t_eid[p0 + e] * heads + hd] = dzv;
+      }
+      __syncwarp();                                  // the strip is reused by this warp's next item
+#pragma unroll
+      for (int o = 1; o <= 16; o <<= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
+    } else {                                         // long column: second gathering sweep (v4)
+      for (int pb = p0; pb < p1; pb += 4) {
+        const int p = pb + grp;
+        const bool valid = p < p1;
+        const int i = valid ? t_colidx[p] : j;
+        float part = 0.f;
+#pragma unroll
+        for (int q = 0; q < GB_MAXF4; ++q) {
+          if (l + 8 * q < F4) {
+            const float4 d = d4p[(int64_t)i * W4 + hd * F4 + l + 8 * q];
+            part += d.x * hj[q].x + d.y * hj[q].y + d.z * hj[q].z + d.w * hj[q].w;
+          }
+        }
+        part += __shfl_xor_sync(0xffffffffu, part, 1);
+        part += __shfl_xor_sync(0xffffffffu, part, 2);
+        part += __shfl_xor_sync(0xffffffffu, part, 4);
+        const float pre = s1[(int64_t)i * heads + hd] + sj;
+        const float a = expf(lrelu(pre, slope) - m) / z;
+        if (valid) {
+          const float dzv = a * (part - t) * (pre > 0.f ? 1.f : slope);
+          dsum += dzv;
+          if (l == 0) dz_coo[(int64_t)t_eid[p] * heads + hd] = dzv;
+        }
+      }
+      dsum += __shfl_xor_sync(0xffffffffu, dsum, 8);
+      dsum += __shfl_xor_sync(0xffffffffu, dsum, 16);
+    }
+    if (lane == 0) ds2[it] = dsum;
+  }
+}
+
 __global__ void __launch_bounds__(256)
 k_gat_bwd_row(const int* __restrict__ rowptr, const int* __restrict__ eid, const float* __restrict__ dz_coo,
               int n, int heads, float* __restrict__ ds1) {
@@ -338,7 +461,9 @@ extern "C" int tsg_gat_bwd(const int32_t* rowptr, const int32_t* eid, const int3
   float* dz = ws.take<float>((nnz + 1) * heads);
   if (F % 4 == 0 && ((((uintptr_t)h) | ((uintptr_t)dhp) | ((uintptr_t)dh)) & 15) == 0)
   {
-#define TSG_GB(Q) k_gat_bwd_col_v4<Q><<<grid_for(n * heads, 8), 256, 0, st>>>(t_rowptr, t_colidx, t_eid, h, s1, s2, mx, zs, dhp, (int)n, (int)heads, (int)F, slope, dz, dh, ds2)
+    static const bool v4 = getenv("TSG_GAT_BWD_V4") != nullptr;        // A/B: the two-sweep kernel of round 1
+#define TSG_GB(Q) do { if (v4) k_gat_bwd_col_v4<Q><<<grid_for(n * heads, 8), 256, 0, st>>>(t_rowptr, t_colidx, t_eid, h, s1, s2, mx, zs, dhp, (int)n, (int)heads, (int)F, slope, dz, dh, ds2); \
+                      else k_gat_bwd_col_v5<Q><<<grid_for(n * heads, 8), 256, 0, st>>>(t_rowptr, t_colidx, t_eid, h, s1, s2, mx, zs, dhp, (int)n, (int)heads, (int)F, slope, dz, dh, ds2); } while (0)
     if (F <= 32) TSG_GB(1); else if (F <= 64) TSG_GB(2); else TSG_GB(4);
 #undef TSG_GB
   }
