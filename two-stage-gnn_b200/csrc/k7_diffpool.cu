@@ -16,6 +16,7 @@
 //   * tcgen05 (k_seg_contract_tc, see k7_tc.cuh): 3xTF32 error-compensated split, fp32 accumulators
 //     in TMEM, one CTA per graph, M = 128 x N <= 256 tile.  Selected by `use_tensor_cores`.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace tsg {
 
@@ -137,6 +138,78 @@ k_seg_linear(const float* __restrict__ X, const float* __restrict__ W, const int
   }
 }
 
+// Wide variant (round 2) for M > 64 output columns per launch (all 32 lanes of a warp share their rows, so the x loads
+// are warp broadcasts whatever the pitch).  The launch list of the DiffPool step (profiles/r02_launches_diffpool_step.csv)
+// showed where k_seg_linear's time is: the backward of the tcgen05 contraction -- dS = [Z|T] dC^T (K_in = 196, M = 100)
+// and d[Z|T] = S dC (K_in = 100, M = 196) -- 2.9 + 2.8 ms of a 24.5 ms step at 13 TFLOP/s: the 2 x 4 micro-tile issues 3
+// shared-memory loads per 8 FMAs.  Here a thread owns 4 rows x 4 columns and walks k four at a time: 8 128-bit loads per
+// 64 FMAs.  Per output the products are still added in k-ascending order with FMA (zero padding adds fma(0, 0, acc) =
+// acc): bit-identical to k_seg_linear.  (A 64 x 128 tile kernel with K chunked through shared memory was measured
+// first: slower, 25.9 vs 24.3 ms per step -- two barriers per 16-deep chunk with the loads exposed.)
+__global__ void __launch_bounds__(256)
+k_seg_linear_wide(const float* __restrict__ X, const float* __restrict__ W, const int64_t* __restrict__ gptr,
+                  int Kin, int M, int Mfull, int m0, int w_transposed, float* __restrict__ Y) {
+  extern __shared__ __align__(16) float sl_smem[];
+  constexpr int CG = 32, RS = 256 / CG, R = RS * 4;              // 8 row slots x 4 rows = 32 rows per tile
+  const int Mp = CG * 4;
+  const int Kp = (Kin + 3) & ~3;
+  float* Ws = sl_smem;                                            // [Kp][Mp]
+  float* Xs = sl_smem + (size_t)Kp * Mp;                          // [R][Kp]
+  const int g = blockIdx.x;
+  const int64_t lo = gptr[g], hi = gptr[g + 1];
+  const float* Wg = W + (int64_t)g * Kin * Mfull;
+  const int cg = threadIdx.x % CG, rs = threadIdx.x / CG;
+  for (int i = threadIdx.x; i < Kp * Mp; i += 256) {
+    const int k = i / Mp, m = i - k * Mp;
+    float w = 0.f;
+    if (m < M && k < Kin) w = w_transposed ? Wg[(int64_t)(m0 + m) * Kin + k] : Wg[(int64_t)k * Mfull + m0 + m];
+    Ws[i] = w;
+  }
+  for (int64_t r0 = lo; r0 < hi; r0 += R) {
+    const int rows = (int)min((int64_t)R, hi - r0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < R * Kp; i += 256) {
+      const int r = i / Kp, k = i - r * Kp;
+      Xs[i] = (r < rows && k < Kin) ? X[(r0 + r) * Kin + k] : 0.f;
+    }
+    __syncthreads();
+    float acc[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[j][c] = 0.f;
+    for (int k = 0; k < Kp; k += 4) {
+      float4 xv[4], w[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) xv[j] = *reinterpret_cast<const float4*>(Xs + (rs + j * RS) * Kp + k);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) w[q] = *reinterpret_cast<const float4*>(Ws + (k + q) * Mp + cg * 4);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        acc[j][0] = fmaf(xv[j].x, w[0].x, acc[j][0]); acc[j][1] = fmaf(xv[j].x, w[0].y, acc[j][1]);
+        acc[j][2] = fmaf(xv[j].x, w[0].z, acc[j][2]); acc[j][3] = fmaf(xv[j].x, w[0].w, acc[j][3]);
+        acc[j][0] = fmaf(xv[j].y, w[1].x, acc[j][0]); acc[j][1] = fmaf(xv[j].y, w[1].y, acc[j][1]);
+        acc[j][2] = fmaf(xv[j].y, w[1].z, acc[j][2]); acc[j][3] = fmaf(xv[j].y, w[1].w, acc[j][3]);
+        acc[j][0] = fmaf(xv[j].z, w[2].x, acc[j][0]); acc[j][1] = fmaf(xv[j].z, w[2].y, acc[j][1]);
+        acc[j][2] = fmaf(xv[j].z, w[2].z, acc[j][2]); acc[j][3] = fmaf(xv[j].z, w[2].w, acc[j][3]);
+        acc[j][0] = fmaf(xv[j].w, w[3].x, acc[j][0]); acc[j][1] = fmaf(xv[j].w, w[3].y, acc[j][1]);
+        acc[j][2] = fmaf(xv[j].w, w[3].z, acc[j][2]); acc[j][3] = fmaf(xv[j].w, w[3].w, acc[j][3]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = rs + j * RS;
+      if (r < rows) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int m = cg * 4 + c;
+          if (m < M) Y[(r0 + r) * Mfull + m0 + m] = acc[j][c];
+        }
+      }
+    }
+  }
+}
+
 }  // namespace tsg
 
 #include "k7_tc.cuh"
@@ -164,8 +237,22 @@ extern "C" int tsg_seg_linear(const float* X, const float* W, const int64_t* gra
   if (G == 0) return TSG_OK;
   TSG_REQUIRE(X && W && graph_ptr && Y, "seg_linear: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
+  static const bool no_gemm = getenv("TSG_SEG_LINEAR_SIMPLE") != nullptr;      // A/B: round 1's 2 x 4 micro-tile kernel only
   for (int64_t m0 = 0; m0 < M; m0 += 128) {            // <= 128 output columns per launch
     int mc = (int)(M - m0 < 128 ? M - m0 : 128);
+    if (!no_gemm && mc > 64) {                          // wide outputs: 4 x 4 micro-tile, k four at a time (bit-identical)
+      const int Kp = (int)((Kin + 3) & ~(int64_t)3);
+      const size_t smw = ((size_t)Kp * 128 + (size_t)32 * Kp) * sizeof(float);
+      if (smw <= 227 * 1024) {
+        static size_t configured = 0;
+        if (smw > 48 * 1024 && smw > configured) {
+          cudaFuncSetAttribute(k_seg_linear_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+          configured = 227 * 1024;
+        }
+        k_seg_linear_wide<<<(int)G, 256, smw, st>>>(X, W, graph_ptr, (int)Kin, mc, (int)M, (int)m0, w_transposed, Y);
+        continue;
+      }
+    }
     int cg = 1; while (cg * 4 < mc && cg < 32) cg <<= 1;
     while (cg < 32 && (size_t)(256 / cg) * 2 * (size_t)(Kin | 1) * 4 > 64 * 1024) cg <<= 1;
     size_t smem = ((size_t)Kin * cg * 4 + (size_t)(256 / cg) * 2 * (Kin | 1)) * sizeof(float);
