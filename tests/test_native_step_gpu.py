@@ -101,6 +101,27 @@ def test_trainer_takes_the_native_path_and_learns(cuda):
     assert l1 != l2
 
 
+def test_trainer_falls_back_when_a_graph_exceeds_the_executor_limits(cuda, monkeypatch):
+    """a graph larger than the per-graph CSR budget: the native step declines, the autograd path takes the batch"""
+    from tsg import _lib, nn as tnn, ops
+    from tsg.train import TripletTrainer
+    corpus = synth.make_corpus("DD", 12, seed=6)
+    cb = _compact(corpus, cuda)
+    torch.manual_seed(0)
+    model = tnn.PackedSAGNet(corpus.num_node_labels, 32, 32, 0.5, 0.0).to(cuda)
+    trainer = TripletTrainer(model, lr=1e-3, weight_decay=0.0, margin=1.5)
+    trip = torch.from_numpy(synth.sample_triplets(corpus.y, 24, seed=1)).to(cuda)
+    assert model.native_step_supported(cb, corpus.node_ptr)
+    ref = float(trainer.step(cb, None, corpus.node_ptr, trip))
+    monkeypatch.setattr(ops, "GRAPH_CSR_MAX_NODES", int(np.diff(corpus.node_ptr).max()) - 1)
+    assert not model.native_step_supported(cb, corpus.node_ptr)
+    torch.manual_seed(0)
+    model2 = tnn.PackedSAGNet(corpus.num_node_labels, 32, 32, 0.5, 0.0).to(cuda)
+    trainer2 = TripletTrainer(model2, lr=1e-3, weight_decay=0.0, margin=1.5)
+    got = float(trainer2.step(cb, None, corpus.node_ptr, trip))
+    assert abs(got - ref) <= 1e-5 * max(abs(ref), 1.0)
+
+
 def test_native_halves_equal_the_single_call(cuda):
     """tsg_sag_step_fwd_compact + K9 through autograd + tsg_sag_step_bwd_compact (the all-gather formulation's path)
     == tsg_sag_triplet_step_compact: identical embeddings, loss and gradients (same kernels, same order)."""

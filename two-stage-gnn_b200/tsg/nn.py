@@ -377,12 +377,19 @@ class PackedSAGNet(torch.nn.Module):
             self.__dict__["_flat_grad"], self.__dict__["_grad_views"] = fg, views
         return fg, views
 
-    def native_step_supported(self, cb) -> bool:
+    def native_step_supported(self, cb, node_ptr_host=None) -> bool:
+        """Can K14 take this batch?  (Compact input, even hidden width, label table within the kernels' range, float32
+        CUDA parameters, and -- when the offsets are given -- every graph within the executor's per-graph limits;
+        otherwise the caller uses the autograd path, which handles anything.)"""
         from . import _lib
         if not (USE_EXECUTOR and USE_NATIVE_STEP and isinstance(cb, ops.CompactBatch)) or self.nhid % 2:
             return False
         if cb.num_labels != self.num_features or _lib.lib.tsg_embed_bwd_weight_workspace_bytes(cb.num_labels, self.nhid) == 0:
             return False
+        if node_ptr_host is not None:
+            plan, _ = self._level_plan(node_ptr_host, cb.label.device)
+            if self._sag_shape(plan, cb.num_labels, int(cb.row.shape[0])) is None:
+                return False
         return all(p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() for p in self._step_params())
 
     def _native_setup(self, cb, node_ptr_host, num_triplets, margin, eps, dropout_mask):

@@ -134,7 +134,8 @@ class TripletTrainer:
         world > 1 the returned loss is the mean over the GLOBAL batch and the parameters receive its gradient."""
         self.model.train()
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
-        if edge_index is None and getattr(self.model, "native_step_supported", None) and self.model.native_step_supported(x):
+        if (edge_index is None and getattr(self.model, "native_step_supported", None)
+                and self.model.native_step_supported(x, node_ptr_host)):
             # K14: forward, loss and backward are ONE C-ABI call; gradients land in views of one flat buffer
             loss = self.model.native_step(x, node_ptr_host, triplets, self.margin)
             if world > 1:
@@ -166,7 +167,8 @@ class TripletTrainer:
         global loss over `triplets_global` [T_g, 3] (indices into the gathered matrix, identical on all ranks), backward
         takes this rank's slice of d(loss)/d(embeddings), and one all-reduce(SUM) completes the parameter gradient."""
         self.model.train()
-        if edge_index is None and getattr(self.model, "native_step_supported", None) and self.model.native_step_supported(x):
+        if (edge_index is None and getattr(self.model, "native_step_supported", None)
+                and self.model.native_step_supported(x, node_ptr_host)):
             # native halves (K14): forward to the embeddings, gather, loss + its gradient on the gathered matrix (K9),
             # this rank's slice back into the native backward
             emb, ctx = self.model.native_forward(x, node_ptr_host)
