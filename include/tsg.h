@@ -576,6 +576,17 @@ int tsg_gate_readout_fwd(const float* x, const float* score, const int64_t* perm
                          int64_t num_graphs, int64_t feat, float* xo, float* out, int64_t out_stride,
                          int32_t* argmax, void* stream);
 
+/* Gate + readout plus the NEXT GCNConv's feature transform (Code/sag/network.py:38,42 -> PyG GCNConv: x W before the
+ * propagation): xw_next[i] = xo[i] @ w_next, w_next [feat, feat] row-major as [in, out].  feat = 32 / 64: one flat pass
+ * gates the rows and multiplies them by w_next while they are on chip (the pooled rows are not read back from HBM for
+ * the product), then the readout runs on xo.  xo, out, argmax and xw_next are bit-identical to tsg_gate_gather_fwd,
+ * tsg_readout_fwd and tsg_linear_fwd(xo, w_next); other widths, or w_next / xw_next NULL, run tsg_gate_readout_fwd
+ * (+ tsg_linear_fwd).  num_rows_out = graph_ptr_out[G] (known on the host). */
+int tsg_gate_readout_linear_fwd(const float* x, const float* score, const int64_t* perm, const int64_t* graph_ptr_out,
+                                int64_t num_graphs, int64_t num_rows_out, int64_t feat, float* xo, float* out,
+                                int64_t out_stride, int32_t* argmax, const float* w_next /*nullable*/,
+                                float* xw_next /*nullable*/, void* stream);
+
 /* Score-side gate backward driven by perm (the other half of tsg_sag_conv_bwd_fused): dscore[perm[i]] =
  * (dxo[i] . x[perm[i]]) * (1 - tanh(score)^2), zero for dropped nodes, and dbias_score = sum(dscore) (the score
  * GCNConv's bias gradient).  dscore bit-identical to tsg_gate_gather_bwd; feat % 4 == 0. */

@@ -225,6 +225,7 @@ static int sag_fwd(const tsg_sag_shape* sh, const SagInput& in, const int64_t* l
     return launch_sag_fused_fwd(f, st);
   }
   const float* xin = in.x;
+  bool xw_ready = false;         // b.xw already written by the previous level's gate kernel
   for (int l = 0; l < 3; ++l) {
     LevelBuf& b = a.lv[l];
     const int64_t n = sh->n[l], k = sh->n[l + 1], fin = l == 0 ? sh->in_feat : H;
@@ -258,7 +259,7 @@ static int sag_fwd(const tsg_sag_shape* sh, const SagInput& in, const int64_t* l
       TSG_TRY(tsg_spmm_label_dot(b.rowptr, b.colidx, b.val, W, in.label, fin, bias, b.h, ws, b.sw, n, H, TSG_SPMM_RELU, stream));
     } else {
       if (l == 0 && in.label) TSG_TRY(tsg_embed_fwd(W, in.label, b.xw, n, fin, H, stream));     // onehot(label) @ W
-      else TSG_TRY(tsg_linear_fwd(xin, W, nullptr, b.xw, n, fin, H, 0, 0, stream));
+      else if (!xw_ready) TSG_TRY(tsg_linear_fwd(xin, W, nullptr, b.xw, n, fin, H, 0, 0, stream));
       // h = ReLU(A_hat xw + b) and, from the same registers, sw = h ws (the score layer's product)
       TSG_TRY(tsg_spmm_dot(b.rowptr, b.colidx, b.val, b.xw, bias, b.h, ws, b.sw, n, H, TSG_SPMM_RELU, stream));
     }
@@ -266,9 +267,14 @@ static int sag_fwd(const tsg_sag_shape* sh, const SagInput& in, const int64_t* l
     TSG_TRY(tsg_topk_bounded(b.score, ptr_l, ptr_n, G, n, sh->max_graph_nodes[l], b.perm, a.scratch, a.scratch_bytes, stream));
     TSG_TRY(tsg_inv_perm(b.perm, k, n, b.inv, stream));            // filter_adj's relabelling table (layers.py:23)
     static const bool no_gr = getenv("TSG_NO_GATE_READOUT") != nullptr;
-    if (H % 4 == 0 && !sag_unfused_env() && !no_gr) {       // gate + readout in one pass (the gated rows are not read back)
-      TSG_TRY(tsg_gate_readout_fwd(b.h, b.score, b.perm, ptr_n, G, H, b.xg, b.out, 2 * H, b.argmax, stream));
+    if (H % 4 == 0 && !sag_unfused_env() && !no_gr) {
+      // gate + readout in one pass (the gated rows are not read back), and the next level's x W from the same rows
+      const bool next_xw = l < 2 && (((uintptr_t)params[4 * (l + 1)]) & 15) == 0;
+      TSG_TRY(tsg_gate_readout_linear_fwd(b.h, b.score, b.perm, ptr_n, G, k, H, b.xg, b.out, 2 * H, b.argmax,
+                                          next_xw ? params[4 * (l + 1)] : nullptr, next_xw ? a.lv[l + 1].xw : nullptr, stream));
+      xw_ready = next_xw;
     } else {
+      xw_ready = false;
       TSG_TRY(tsg_gate_gather_fwd(b.h, b.score, b.perm, nullptr, b.xg, nullptr, k, H, stream));
       TSG_TRY(tsg_readout_fwd(b.xg, ptr_n, G, H, TSG_READOUT_MAX | TSG_READOUT_MEAN, b.out, 2 * H, b.argmax, stream));
     }

@@ -15,6 +15,7 @@
 namespace tsg {
 
 constexpr int RO_THREADS = 128;   // 4 graphs per block
+constexpr int RO_U = 8;            // k_readout_fwd: rows per lane group in flight
 constexpr int RO_BWD_THREADS = 256;
 
 template <int VEC, int LPR>
@@ -37,7 +38,26 @@ k_readout_fwd(const float* __restrict__ x, const int64_t* __restrict__ gptr, int
 #pragma unroll
       for (int v = 0; v < VEC; ++v) { mx[v] = -FLT_MAX; sm[v] = 0.f; am[v] = -1; }
       if (fok) {
-        for (int i = sub; i < n; i += RPW) {
+        int i = sub;
+        if (VEC == 4) {
+          // RO_U rows per sub-group in flight (the loads do not depend on the sums): a graph's walk is RO_U times
+          // shorter -- the launch lasts as long as its largest graph.  Same order of additions as the plain loop below.
+          for (; i + (RO_U - 1) * RPW < n; i += RO_U * RPW) {
+            float4 t[RO_U];
+#pragma unroll
+            for (int u = 0; u < RO_U; ++u) t[u] = __ldg(reinterpret_cast<const float4*>(x) + (lo + i + u * RPW) * FV + f);
+#pragma unroll
+            for (int u = 0; u < RO_U; ++u) {
+              const float vals[4] = {t[u].x, t[u].y, t[u].z, t[u].w};
+#pragma unroll
+              for (int v = 0; v < VEC; ++v) {
+                sm[v] += vals[v % 4];
+                if (vals[v % 4] > mx[v] || am[v] < 0) { mx[v] = vals[v % 4]; am[v] = i + u * RPW; }
+              }
+            }
+          }
+        }
+        for (; i < n; i += RPW) {
           float vals[VEC];
           if (VEC == 4) {
             float4 t = __ldg(reinterpret_cast<const float4*>(x) + (lo + i) * FV + f);
@@ -171,6 +191,101 @@ k_gate_readout_fwd(const float4* __restrict__ x, const float* __restrict__ score
   }
 }
 
+// Gate + the next conv's x W in one flat pass over the pooled rows (round 2):
+//     xo[i] = x[perm[i]] * tanh(score[perm[i]])        layers.py:21
+//     xw[i] = xo[i] @ W_next                           network.py:38,42 -> GCNConv: x W before the propagation
+// No graph structure: a warp takes RPW * GL_WU consecutive rows, gates them into xo and into a private shared-memory tile,
+// and multiplies the tile by W_next with k_linear_fwd_dense's k-ascending FMA chain per output, so xo is bit-identical
+// to k_gate_gather_fwd and xw to tsg_linear_fwd on xo -- without reading the pooled rows back from HBM, and with one
+// launch less per level.  The readout then runs on xo (k_readout_fwd).
+//   Tried first and measured slower (profiles/r02f_gate_readout.md): doing the readout in the same kernel, a CTA per
+//   graph with the ordered sum taken from shared-memory tiles -- the readout's fixed summation order needs a per-graph
+//   owner, and per-graph owners mean either few graphs in flight (CTA per graph) or long dependent walks (warp per
+//   graph); a flat pass has neither.
+constexpr int GL_THREADS = 256;
+constexpr int GL_WU = 4;              // rows per lane group
+
+// 4 outputs of `ROWS` rows: acc[u][c] = sum_k a_u[k] * W[k][4l + c], k ascending, one FMA per term (k_linear_fwd_dense)
+template <int F, int ROWS>
+__device__ __forceinline__ void gl_rows_times_w(const float* __restrict__ Ws, const float* const (&arow)[ROWS], int l,
+                                                float (&acc)[ROWS][4]) {
+#pragma unroll
+  for (int u = 0; u < ROWS; ++u)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[u][c] = 0.f;
+#pragma unroll 2
+  for (int k = 0; k < F; k += 4) {
+    float4 wq[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) wq[q] = *reinterpret_cast<const float4*>(Ws + (k + q) * F + 4 * l);
+#pragma unroll
+    for (int u = 0; u < ROWS; ++u) {
+      const float4 a = *reinterpret_cast<const float4*>(arow[u] + k);
+      acc[u][0] = fmaf(a.x, wq[0].x, acc[u][0]); acc[u][1] = fmaf(a.x, wq[0].y, acc[u][1]);
+      acc[u][2] = fmaf(a.x, wq[0].z, acc[u][2]); acc[u][3] = fmaf(a.x, wq[0].w, acc[u][3]);
+      acc[u][0] = fmaf(a.y, wq[1].x, acc[u][0]); acc[u][1] = fmaf(a.y, wq[1].y, acc[u][1]);
+      acc[u][2] = fmaf(a.y, wq[1].z, acc[u][2]); acc[u][3] = fmaf(a.y, wq[1].w, acc[u][3]);
+      acc[u][0] = fmaf(a.z, wq[2].x, acc[u][0]); acc[u][1] = fmaf(a.z, wq[2].y, acc[u][1]);
+      acc[u][2] = fmaf(a.z, wq[2].z, acc[u][2]); acc[u][3] = fmaf(a.z, wq[2].w, acc[u][3]);
+      acc[u][0] = fmaf(a.w, wq[3].x, acc[u][0]); acc[u][1] = fmaf(a.w, wq[3].y, acc[u][1]);
+      acc[u][2] = fmaf(a.w, wq[3].z, acc[u][2]); acc[u][3] = fmaf(a.w, wq[3].w, acc[u][3]);
+    }
+  }
+}
+
+template <int LPR>
+__global__ void __launch_bounds__(GL_THREADS)
+k_gate_linear(const float4* __restrict__ x, const float* __restrict__ score, const int64_t* __restrict__ perm, int64_t K,
+              float4* __restrict__ xo, const float* __restrict__ Wn, float4* __restrict__ xw) {
+  constexpr int F4 = LPR, F = 4 * LPR;
+  constexpr int RPW = 32 / LPR;
+  constexpr int WROWS = RPW * GL_WU;                  // rows per warp: 16 (F = 32), 8 (F = 64)
+  constexpr int PITCH = F + 4;                        // float4-aligned, rows of the warp's lane groups on distinct banks
+  extern __shared__ __align__(16) float gl_smem[];
+  float* Ws = gl_smem;                                // [F][F]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane / LPR, l = lane % LPR;
+  float* Tw = gl_smem + F * F + warp * WROWS * PITCH;
+  const int64_t base = ((int64_t)blockIdx.x * (GL_THREADS / 32) + warp) * WROWS;
+  int64_t j[GL_WU];
+#pragma unroll
+  for (int u = 0; u < GL_WU; ++u) {                   // the dependent chain perm -> score / x starts before the W fill
+    const int64_t i = base + sub + u * RPW;
+    j[u] = i < K ? __ldg(perm + i) : -1;
+  }
+  for (int i = threadIdx.x; i < F * F / 4; i += GL_THREADS)
+    reinterpret_cast<float4*>(Ws)[i] = __ldg(reinterpret_cast<const float4*>(Wn) + i);
+  float tv[GL_WU]; float4 xv[GL_WU];
+#pragma unroll
+  for (int u = 0; u < GL_WU; ++u) {
+    tv[u] = 0.f; xv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (j[u] >= 0) { tv[u] = __ldg(score + j[u]); xv[u] = __ldg(x + j[u] * F4 + l); }
+  }
+#pragma unroll
+  for (int u = 0; u < GL_WU; ++u) {
+    if (j[u] < 0) continue;
+    const float th = tanhf(tv[u]);
+    float4 w = xv[u];
+    w.x *= th; w.y *= th; w.z *= th; w.w *= th;
+    xo[(base + sub + u * RPW) * F4 + l] = w;
+    *reinterpret_cast<float4*>(Tw + (sub + u * RPW) * PITCH + 4 * l) = w;
+  }
+  __syncthreads();                                    // Ws (whole CTA) and Tw (this warp)
+#pragma unroll
+  for (int half = 0; half < GL_WU; half += 2) {       // two rows at a time: register budget
+    if (base + half * RPW >= K) break;                // warp-uniform: no row of this half exists
+    const float* arow[2] = {Tw + (sub + half * RPW) * PITCH, Tw + (sub + (half + 1) * RPW) * PITCH};
+    float acc[2][4];
+    gl_rows_times_w<F, 2>(Ws, arow, l, acc);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int64_t i = base + sub + (half + u) * RPW;
+      if (i < K)     // "+ 0.f" = the bias-less add of k_linear_fwd_dense (turns -0 into +0 as it does)
+        xw[i * F4 + l] = make_float4(acc[u][0] + 0.f, acc[u][1] + 0.f, acc[u][2] + 0.f, acc[u][3] + 0.f);
+    }
+  }
+}
+
 template <int VEC, int LPR>
 __global__ void __launch_bounds__(RO_BWD_THREADS)
 k_readout_bwd(const float* __restrict__ dout, int64_t dstride, const int* __restrict__ argmax,
@@ -300,4 +415,37 @@ extern "C" int tsg_gate_readout_fwd(const float* x, const float* score, const in
   }
 #undef TSG_GR
   return check_launch("gate_readout_fwd");
+}
+
+/* Gate + readout + (when w_next is given) xw_next = xo @ w_next, the next GCNConv's x W (network.py:38,42).
+ * feat = 32 / 64 with w_next: k_gate_linear (gate and product in one flat pass) + k_readout_fwd on xo; without w_next or for
+ * other widths: tsg_gate_readout_fwd (+ tsg_linear_fwd).  Either way bit-identical to gate_gather, readout, linear_fwd. */
+extern "C" int tsg_gate_readout_linear_fwd(const float* x, const float* score, const int64_t* perm, const int64_t* gptr,
+                                           int64_t G, int64_t num_rows_out, int64_t F, float* xo, float* out,
+                                           int64_t out_stride, int32_t* argmax, const float* w_next, float* xw_next,
+                                           void* stream) {
+  TSG_REQUIRE(G >= 0 && num_rows_out >= 0 && F > 0 && F % 4 == 0 && G < (int64_t)0x7fffffff, "gate_readout_linear_fwd: bad shape");
+  TSG_REQUIRE((w_next == nullptr) == (xw_next == nullptr), "gate_readout_linear_fwd: w_next and xw_next go together");
+  if (G == 0) return TSG_OK;
+  static const bool v1 = getenv("TSG_GATE_V1") != nullptr;
+  const bool aligned = ((((uintptr_t)x) | ((uintptr_t)xo) | ((uintptr_t)xw_next) | ((uintptr_t)w_next)) & 15) == 0;
+  if (v1 || !w_next || !(F == 32 || F == 64) || !aligned) {
+    int rc = tsg_gate_readout_fwd(x, score, perm, gptr, G, F, xo, out, out_stride, argmax, stream);
+    if (rc == TSG_OK && w_next && num_rows_out > 0) rc = tsg_linear_fwd(xo, w_next, nullptr, xw_next, num_rows_out, F, F, 0, 0, stream);
+    return rc;
+  }
+  TSG_REQUIRE(x && score && perm && gptr && xo && out && argmax, "gate_readout_linear_fwd: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (num_rows_out > 0) {
+    const int wrows = (32 / (int)(F / 4)) * GL_WU;
+    const int64_t rows_per_cta = (int64_t)(GL_THREADS / 32) * wrows;
+    const int64_t grid = (num_rows_out + rows_per_cta - 1) / rows_per_cta;
+    TSG_REQUIRE(grid < (int64_t)0x7fffffff, "gate_readout_linear_fwd: too many rows");
+    const size_t smem = ((size_t)F * F + (size_t)(GL_THREADS / 32) * wrows * (F + 4)) * sizeof(float);
+    if (F == 32) k_gate_linear<8><<<(int)grid, GL_THREADS, smem, st>>>((const float4*)x, score, perm, num_rows_out, (float4*)xo, w_next, (float4*)xw_next);
+    else k_gate_linear<16><<<(int)grid, GL_THREADS, smem, st>>>((const float4*)x, score, perm, num_rows_out, (float4*)xo, w_next, (float4*)xw_next);
+    int rc = check_launch("gate_readout_linear_fwd");
+    if (rc) return rc;
+  }
+  return tsg_readout_fwd(xo, gptr, G, F, TSG_READOUT_MAX | TSG_READOUT_MEAN, out, out_stride, argmax, stream);
 }
