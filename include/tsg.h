@@ -279,6 +279,11 @@ int tsg_seg_contract(const float* X, const float* Y, const int64_t* graph_ptr, i
                      int32_t* status_dev /*nullable unless tensor cores*/, void* stream);
 int tsg_seg_linear(const float* X, const float* W, const int64_t* graph_ptr, int64_t num_graphs,
                    int64_t in_feat, int64_t out_feat, int w_transposed, float* Y, void* stream);
+/* tsg_seg_linear on tcgen05 (kind::tf32, 3xTF32 split, TMEM accumulators; the rows of a graph are the MMA's M dimension,
+ * 128 at a time, the contraction runs over Kin in chunks of 32).  Needs M <= 256, M % 4 == 0, Kin % 4 == 0 and 16-byte
+ * aligned operands (TSG_EINVAL otherwise: call tsg_seg_linear); status_dev as for tsg_seg_contract. */
+int tsg_seg_linear_tc(const float* X, const float* W, const int64_t* graph_ptr, int64_t num_graphs, int64_t Kin, int64_t M,
+                      int w_transposed, float* Y, int32_t* status_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * K5a  per-graph top-k (deterministic: descending score, ties -> lower node id, NaN first)

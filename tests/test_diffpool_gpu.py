@@ -63,6 +63,31 @@ def test_seg_linear_and_autograd(cuda, kin, m):
     assert rel_err(yg, yo) <= TOL and rel_err(xg.grad, xo.grad) <= TOL and rel_err(wg.grad, wo.grad) <= TOL
 
 
+@pytest.mark.parametrize("tc", [False, True])
+@pytest.mark.parametrize("transposed", [False, True])
+@pytest.mark.parametrize("kin,m", [(196, 100), (100, 196), (32, 256), (36, 4), (256, 64)])
+def test_seg_linear_raw_tcgen05_and_simt(cuda, tc, transposed, kin, m):
+    """the row-local product on tcgen05 (rows = the MMA's M dimension, 128 at a time; 3xTF32) and on the SIMT kernels, both
+    weight layouts, ragged graphs around the 128-row tile incl. empty ones, vs float64"""
+    from tsg import _lib, ops
+    sizes = [269, 0, 1, 127, 128, 129, 1000, 31, 0, 256]
+    g = torch.Generator().manual_seed(kin * 7 + m)
+    n = sum(sizes)
+    x = torch.randn(n, kin, generator=g)
+    w = torch.randn(len(sizes), m, kin, generator=g) if transposed else torch.randn(len(sizes), kin, m, generator=g)
+    ptr = torch.tensor(np.concatenate([[0], np.cumsum(sizes)]), dtype=torch.int64)
+    ref = torch.cat([x[ptr[i]:ptr[i + 1]].double() @ (w[i].double().t() if transposed else w[i].double()) for i in range(len(sizes))])
+    prof = {}
+    _lib.profile = prof
+    try:
+        y = ops.seg_linear_raw(x.to(cuda), w.to(cuda), ptr.to(cuda), transposed, tensor_cores=tc)
+        torch.cuda.synchronize()
+    finally:
+        _lib.profile = None
+    assert ("tsg_seg_linear_tc" in prof) == tc and ("tsg_seg_linear" in prof) == (not tc)
+    assert rel_err(y, ref) <= TOL, f"tensor_cores={tc} transposed={transposed}"
+
+
 def _load_diffpool(d, cuda):
     from tsg import diffpool
     N, Fi, H, O, L = [int(v) for v in d["dims"]]

@@ -268,3 +268,11 @@ extern "C" int tsg_seg_linear(const float* X, const float* W, const int64_t* gra
   }
   return check_launch("seg_linear");
 }
+
+extern "C" int tsg_seg_linear_tc(const float* X, const float* W, const int64_t* graph_ptr, int64_t G, int64_t Kin, int64_t M,
+                                 int w_transposed, float* Y, int32_t* status_dev, void* stream) {
+  TSG_REQUIRE(G >= 0 && Kin > 0 && M > 0 && G < (int64_t)0x7fffffff && Kin < (int64_t)0x7fffffff, "seg_linear_tc: bad shape");
+  if (G == 0) return TSG_OK;
+  TSG_REQUIRE(X && W && graph_ptr && Y && status_dev, "seg_linear_tc: null pointer");
+  return launch_seg_linear_tc(X, W, graph_ptr, (int)G, (int)Kin, (int)M, w_transposed, Y, status_dev, (cudaStream_t)stream);
+}

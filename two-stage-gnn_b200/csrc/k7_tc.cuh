@@ -428,4 +428,200 @@ static int launch_seg_contract_tc(const float* X, const float* Y, const int64_t*
   return check_launch("seg_contract(tcgen05)");
 }
 
+// ------------------------------------------------------------------------------------------
+// Row-local product on tcgen05 (round 2):  Y[r, :] = X[r, :] . W_g   (W_g [Kin, M])   or   X[r, :] . W_g^T   (W_g [M, Kin])
+// for r in graph g -- the backward of the contraction above (dS = [Z | AS] dC^T, d[Z | AS] = S dC: 970 k rows x
+// 100 / 196 columns at config-4 size, 1.6 ms each on the SIMT kernel = 21 % of the DiffPool step).
+//   * MMA: D [128 rows, N = M <= 256] += A [128 rows, K] . B [N, K]^T, the contraction index is the FEATURE index Kin,
+//     walked in chunks of SL_KC = 32 (4 k-steps of 8); a CTA takes a graph and walks its rows 128 at a time.
+//   * operands go global -> registers -> hi/lo TF32 tiles in the canonical K-major no-swizzle layout (the 3xTF32 split has
+//     to pass through registers anyway); A rows are K-major in memory (no transpose), B is K-major when W is stored
+//     transposed and MN-major otherwise (transposed on the fly, as in k_seg_contract_tc2).  Lane mapping: 8 rows x 4
+//     k-quads per warp, so a warp's 16-byte shared-memory stores cover all 32 banks per quarter and its global reads are
+//     64-byte row pieces.
+//   * pipeline: two MMA tile sets; the 16 transform warps fill set (i & 1) while the tensor pipe works on the other;
+//     the issuer lane commits each chunk to an mbarrier; the same 16 warps run the epilogue (tcgen05.ld, thread =
+//     row) at the end of every 128-row tile.
+// Needs Kin % 4 == 0, M % 4 == 0, M <= 256, 16-byte aligned operands.
+// ------------------------------------------------------------------------------------------
+constexpr int SL_KC = 32;
+constexpr int SL_THREADS = 512;
+
+// K-major source: element (row, k) = src[row * ld + k]; rows >= nrows and k >= klen are zero
+__device__ __forceinline__ void sl_transform_kmajor(const float* __restrict__ src, int64_t ld, int nrows, int klen,
+                                                    int tile_rows, char* hi, char* lo) {
+  constexpr uint32_t SBO = (SL_KC / 4) * 128;
+  const int items = tile_rows * (SL_KC / 4);
+  for (int j = threadIdx.x; j < items; j += SL_THREADS) {
+    const int r7 = j & 7, kqlo = (j >> 3) & 3, u = j >> 5;
+    const int ngroups = tile_rows >> 3;
+    const int rowgroup = u % ngroups, kqhi = u / ngroups;
+    const int row = rowgroup * 8 + r7, kq = kqhi * 4 + kqlo;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < nrows && kq * 4 < klen) v = __ldg(reinterpret_cast<const float4*>(src + (int64_t)row * ld + kq * 4));
+    const float f[4] = {v.x, v.y, v.z, v.w};
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { h[i] = to_tf32(f[i]); l[i] = to_tf32(f[i] - __uint_as_float(h[i])); }
+    const uint32_t off = (uint32_t)(row >> 3) * SBO + (uint32_t)kq * 128 + (uint32_t)(row & 7) * 16;
+    *reinterpret_cast<uint4*>(hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+
+// MN-major source: element (n, k) = src[k * ld + n]; n >= ncols is never stored by the epilogue, k >= klen is zero
+__device__ __forceinline__ void sl_transform_mnmajor(const float* __restrict__ src, int64_t ld, int ncols, int klen,
+                                                     int tile_cols, char* hi, char* lo) {
+  constexpr uint32_t SBO = (SL_KC / 4) * 128;
+  const int items = tile_cols * (SL_KC / 4);
+  for (int j = threadIdx.x; j < items; j += SL_THREADS) {
+    const int n = j % tile_cols, kq = j / tile_cols;
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int k = kq * 4 + i;
+      const float v = (n < ncols && k < klen) ? __ldg(src + (int64_t)k * ld + n) : 0.f;
+      h[i] = to_tf32(v);
+      l[i] = to_tf32(v - __uint_as_float(h[i]));
+    }
+    const uint32_t off = (uint32_t)(n >> 3) * SBO + (uint32_t)kq * 128 + (uint32_t)(n & 7) * 16;
+    *reinterpret_cast<uint4*>(hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+
+template <int NPAD>
+__global__ void __launch_bounds__(SL_THREADS + 32)
+k_seg_linear_tc(const float* __restrict__ X, const float* __restrict__ W, const int64_t* __restrict__ gptr, int Kin, int M,
+                int Nmma, int w_transposed, float* __restrict__ Y, int* __restrict__ err) {
+  extern __shared__ __align__(128) char sltc_smem[];
+  constexpr int A_BYTES = TC_M * SL_KC * 4, B_BYTES = NPAD * SL_KC * 4;
+  constexpr int MMA_SET = 2 * A_BYTES + 2 * B_BYTES;                 // a_hi a_lo b_hi b_lo
+  constexpr int TWARPS = SL_THREADS / 32;
+  __shared__ __align__(8) uint64_t bar_full[2];                      // tile set written (TWARPS arrivals)
+  __shared__ __align__(8) uint64_t bar_mma[2];                       // MMAs that read the set are done (commit)
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = blockIdx.x;
+  const int64_t lo_r = gptr[g], hi_r = gptr[g + 1];
+  const int nk = (Kin + SL_KC - 1) / SL_KC;
+  const float* Wg = W + (int64_t)g * Kin * M;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "r"((uint32_t)NPAD) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&bar_full[i])), "r"((uint32_t)TWARPS) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&bar_mma[i])), "r"(1u) : "memory");
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_base_s;
+  bool ok = true;
+  int ci = 0;                                                        // chunks issued so far (every role counts alike)
+
+  for (int64_t r0 = lo_r; r0 < hi_r; r0 += TC_M) {
+    const int rows = (int)min((int64_t)TC_M, hi_r - r0);
+    if (warp == TWARPS) {
+      // ---------------- issuer lane
+      if (lane == 0) {
+        const uint32_t idesc = make_idesc(TC_M, Nmma);
+        constexpr uint32_t SBO = (SL_KC / 4) * 128, LBO = 128;
+        for (int c = 0; c < nk && ok; ++c) {
+          const int i = ci + c, t = i & 1;
+          ok = mbar_wait2(smem_u32(&bar_full[t]), (uint32_t)((i >> 1) & 1));
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a_hi = smem_u32(sltc_smem + (size_t)t * MMA_SET), a_lo = a_hi + A_BYTES;
+          const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < SL_KC / 8; ++ks) {
+            const uint32_t koff = ks * 2 * 128;
+            const uint64_t ah = make_desc(a_hi + koff, LBO, SBO), al = make_desc(a_lo + koff, LBO, SBO);
+            const uint64_t bh = make_desc(b_hi + koff, LBO, SBO), bl = make_desc(b_lo + koff, LBO, SBO);
+            mma_tf32(tmem, al, bh, idesc, (c > 0 || ks > 0) ? 1u : 0u);  // small terms first
+            mma_tf32(tmem, ah, bl, idesc, 1u);
+            mma_tf32(tmem, ah, bh, idesc, 1u);
+          }
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&bar_mma[t])) : "memory");
+        }
+      }
+    } else {
+      // ---------------- transform warps
+      for (int c = 0; c < nk && ok; ++c) {
+        const int i = ci + c, t = i & 1;
+        const int k0 = c * SL_KC, klen = min(SL_KC, Kin - k0);
+        if (i >= 2) ok = mbar_wait2(smem_u32(&bar_mma[t]), (uint32_t)(((i >> 1) - 1) & 1));     // MMA(i-2) left set t
+        char* set = sltc_smem + (size_t)t * MMA_SET;
+        sl_transform_kmajor(X + r0 * Kin + k0, Kin, rows, klen, TC_M, set, set + A_BYTES);
+        if (w_transposed) sl_transform_kmajor(Wg + k0, Kin, M, klen, Nmma, set + 2 * A_BYTES, set + 2 * A_BYTES + B_BYTES);
+        else sl_transform_mnmajor(Wg + (int64_t)k0 * M, M, M, klen, Nmma, set + 2 * A_BYTES, set + 2 * A_BYTES + B_BYTES);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes -> async proxy
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(&bar_full[t])) : "memory");
+      }
+    }
+    ci += nk;
+    if (ok) {                                                          // the last commit covers every earlier MMA of the tile
+      const int last = ci - 1;
+      ok = mbar_wait2(smem_u32(&bar_mma[last & 1]), (uint32_t)((last >> 1) & 1));
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // epilogue: warp w reads its TMEM lane quarter 32 * (w % 4) and the column slabs 32 * (w / 4), + 128; thread = row
+    if (warp < TWARPS) {
+      const int m = (warp & 3) * 32 + lane;
+      for (int c0 = (warp >> 2) * 32; c0 < Nmma; c0 += 32 * (SL_THREADS / 128)) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+              "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+              "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr) : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (m < rows) {
+          float* dst = Y + (r0 + m) * M + c0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (c0 + 4 * i < M)                                          // M % 4 == 0: whole float4s
+              reinterpret_cast<float4*>(dst)[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                                              __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();                                                     // TMEM is overwritten by the next tile's first MMA
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  }
+  if (!ok) atomicExch(err, 1);
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"((uint32_t)NPAD) : "memory");
+  }
+}
+
+static int launch_seg_linear_tc(const float* X, const float* W, const int64_t* gptr, int G, int Kin, int M, int w_transposed,
+                                float* Y, int* err, cudaStream_t st) {
+  if (M > 256 || M % 4 || Kin % 4 || ((((uintptr_t)X) | ((uintptr_t)W) | ((uintptr_t)Y)) & 15)) {
+    set_error("seg_linear(tcgen05): needs M <= 256, M %% 4 == 0, Kin %% 4 == 0 and 16-byte aligned operands (got Kin %d, M %d)", Kin, M);
+    return TSG_EINVAL;
+  }
+  int Nmma = (M + 15) / 16 * 16;
+  const int npad = Nmma <= 64 ? 64 : (Nmma <= 128 ? 128 : 256);
+  const size_t smem = 2 * (2 * (size_t)TC_M * SL_KC * 4 + 2 * (size_t)npad * SL_KC * 4) + 128;
+#define TSG_GOSL(NP)                                                                                     \
+  cudaFuncSetAttribute(k_seg_linear_tc<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
+  k_seg_linear_tc<NP><<<G, SL_THREADS + 32, smem, st>>>(X, W, gptr, Kin, M, Nmma, w_transposed, Y, err)
+  if (npad == 64) { TSG_GOSL(64); } else if (npad == 128) { TSG_GOSL(128); } else { TSG_GOSL(256); }
+#undef TSG_GOSL
+  return check_launch("seg_linear(tcgen05)");
+}
+
 }  // namespace tsg

@@ -589,14 +589,24 @@ def seg_contract_raw(x: torch.Tensor, y: torch.Tensor, graph_ptr: torch.Tensor,
     return c
 
 
-def seg_linear_raw(x: torch.Tensor, w: torch.Tensor, graph_ptr: torch.Tensor, transposed: bool = False):
-    """y[r,:] = x[r,:] . w[g]  (w [G, Kin, M])  or  x[r,:] . w[g]^T  (w [G, M, Kin]) for r in graph g."""
+SEG_LINEAR_TC = os.environ.get("TSG_SEG_LINEAR_NOTC", "0") != "1"
+
+
+def seg_linear_raw(x: torch.Tensor, w: torch.Tensor, graph_ptr: torch.Tensor, transposed: bool = False,
+                   tensor_cores: Optional[bool] = None):
+    """y[r,:] = x[r,:] . w[g]  (w [G, Kin, M])  or  x[r,:] . w[g]^T  (w [G, M, Kin]) for r in graph g.
+    tensor_cores (default ops.USE_TCGEN05): the tcgen05 3xTF32 kernel where the shape allows it, else fp32 SIMT."""
     x = x.contiguous(); w = w.contiguous()
     G, kin = graph_ptr.numel() - 1, x.size(1)
     m = w.size(1) if transposed else w.size(2)
     if (w.size(2) if transposed else w.size(1)) != kin or w.size(0) != G:
         raise RuntimeError(f"tsg.seg_linear: shape mismatch x{tuple(x.shape)} w{tuple(w.shape)} T={transposed}")
     y = torch.empty(x.size(0), m, dtype=torch.float32, device=x.device)
+    tc = USE_TCGEN05 if tensor_cores is None else tensor_cores
+    if tc and SEG_LINEAR_TC and kin % 4 == 0 and m % 4 == 0 and m <= 256 and kin >= 32:
+        status = torch.zeros(1, dtype=torch.int32, device=x.device)
+        call("tsg_seg_linear_tc", ptr(x), ptr(w), ptr(graph_ptr), G, kin, m, int(transposed), ptr(y), ptr(status), stream_ptr())
+        return y
     call("tsg_seg_linear", ptr(x), ptr(w), ptr(graph_ptr), G, kin, m, int(transposed), ptr(y), stream_ptr())
     return y
 
