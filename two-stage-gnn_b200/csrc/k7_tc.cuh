@@ -433,7 +433,9 @@ static int launch_seg_contract_tc(const float* X, const float* Y, const int64_t*
 // for r in graph g -- the backward of the contraction above (dS = [Z | AS] dC^T, d[Z | AS] = S dC: 970 k rows x
 // 100 / 196 columns at config-4 size, 1.6 ms each on the SIMT kernel = 21 % of the DiffPool step).
 //   * MMA: D [128 rows, N = M <= 256] += A [128 rows, K] . B [N, K]^T, the contraction index is the FEATURE index Kin,
-//     walked in chunks of SL_KC = 32 (4 k-steps of 8); a CTA takes a graph and walks its rows 128 at a time.
+//     walked in chunks of SL_KC = 16 (2 k-steps of 8); a CTA takes a graph and walks its rows 128 at a time; two CTAs per SM
+//     (<= 96 KB of shared memory, <= 256 TMEM columns and 56 registers each) so one CTA's epilogue and barrier waits hide
+//     behind the other's transform.
 //   * operands go global -> registers -> hi/lo TF32 tiles in the canonical K-major no-swizzle layout (the 3xTF32 split has
 //     to pass through registers anyway); A rows are K-major in memory (no transpose), B is K-major when W is stored
 //     transposed and MN-major otherwise (transposed on the fly, as in k_seg_contract_tc2).  Lane mapping: 8 rows x 4
@@ -444,22 +446,77 @@ static int launch_seg_contract_tc(const float* X, const float* Y, const int64_t*
 //     row) at the end of every 128-row tile.
 // Needs Kin % 4 == 0, M % 4 == 0, M <= 256, 16-byte aligned operands.
 // ------------------------------------------------------------------------------------------
-constexpr int SL_KC = 32;
+constexpr int SL_KC = 16;
 constexpr int SL_THREADS = 512;
 
-// K-major source: element (row, k) = src[row * ld + k]; rows >= nrows and k >= klen are zero
-__device__ __forceinline__ void sl_transform_kmajor(const float* __restrict__ src, int64_t ld, int nrows, int klen,
-                                                    int tile_rows, char* hi, char* lo) {
+// One chunk of one operand held in registers between its global loads and its shared-memory stores, so that ALL of a
+// chunk's loads are in flight together and the next chunk's loads overlap the barrier wait of this one (the first cut
+// loaded, converted and stored item by item: four exposed load latencies per chunk, ~4,400 cycles).
+//   K-major source (A rows; W stored transposed): element (row, k) = src[row * ld + k];
+//   MN-major source (W as [Kin, M]):              element (n, k)   = src[k * ld + n].
+// Item j of a tile with `trows` rows (a multiple of 8): K-major -> lane = 8 rows x 4 k-quads (64-byte row pieces from
+// global, all 32 banks per quarter-warp on the 16-byte stores); MN-major -> consecutive n per lane.
+template <int ITEMS>
+struct SlChunk {
+  float4 v[ITEMS];
+};
+// (row, k-quad) of every item of a thread, packed row | kq << 16, -1 = no item: chunk- and tile-invariant, so the
+// divisions by the runtime tile height happen once per thread, not once per item per chunk (ncu, first cut: 25 % of
+// the kernel's instructions were this index arithmetic)
+template <int ITEMS>
+struct SlMap {
+  int rk[ITEMS];
+};
+
+template <int ITEMS, bool KMAJOR>
+__device__ __forceinline__ void sl_map_init(SlMap<ITEMS>& m, int trows) {
+  const int ngroups = trows >> 3;
+#pragma unroll
+  for (int it = 0; it < ITEMS; ++it) {
+    const int j = threadIdx.x + it * SL_THREADS;
+    int row, kq;
+    if (KMAJOR) { const int u = j >> 5; row = (u % ngroups) * 8 + (j & 7); kq = (u / ngroups) * 4 + ((j >> 3) & 3); }
+    else { row = j % trows; kq = j / trows; }
+    m.rk[it] = j < trows * (SL_KC / 4) ? (row | (kq << 16)) : -1;
+  }
+}
+
+template <int ITEMS>
+__device__ __forceinline__ void sl_load_kmajor(SlChunk<ITEMS>& c, const SlMap<ITEMS>& m, const float* __restrict__ src,
+                                               int64_t ld, int nrows, int klen) {
+#pragma unroll
+  for (int it = 0; it < ITEMS; ++it) {
+    const int row = m.rk[it] & 0xffff, kq = m.rk[it] >> 16;
+    c.v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (m.rk[it] >= 0 && row < nrows && kq * 4 < klen)
+      c.v[it] = __ldg(reinterpret_cast<const float4*>(src + (int64_t)row * ld + kq * 4));
+  }
+}
+
+template <int ITEMS>
+__device__ __forceinline__ void sl_load_mnmajor(SlChunk<ITEMS>& c, const SlMap<ITEMS>& m, const float* __restrict__ src,
+                                                int64_t ld, int ncols, int klen) {
+#pragma unroll
+  for (int it = 0; it < ITEMS; ++it) {
+    const int n = m.rk[it] & 0xffff, kq = m.rk[it] >> 16;
+    float f[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int k = kq * 4 + i;
+      f[i] = (m.rk[it] >= 0 && n < ncols && k < klen) ? __ldg(src + (int64_t)k * ld + n) : 0.f;
+    }
+    c.v[it] = make_float4(f[0], f[1], f[2], f[3]);
+  }
+}
+
+template <int ITEMS>
+__device__ __forceinline__ void sl_store(const SlChunk<ITEMS>& c, const SlMap<ITEMS>& m, char* hi, char* lo) {
   constexpr uint32_t SBO = (SL_KC / 4) * 128;
-  const int items = tile_rows * (SL_KC / 4);
-  for (int j = threadIdx.x; j < items; j += SL_THREADS) {
-    const int r7 = j & 7, kqlo = (j >> 3) & 3, u = j >> 5;
-    const int ngroups = tile_rows >> 3;
-    const int rowgroup = u % ngroups, kqhi = u / ngroups;
-    const int row = rowgroup * 8 + r7, kq = kqhi * 4 + kqlo;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (row < nrows && kq * 4 < klen) v = __ldg(reinterpret_cast<const float4*>(src + (int64_t)row * ld + kq * 4));
-    const float f[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int it = 0; it < ITEMS; ++it) {
+    if (m.rk[it] < 0) continue;
+    const int row = m.rk[it] & 0xffff, kq = m.rk[it] >> 16;
+    const float f[4] = {c.v[it].x, c.v[it].y, c.v[it].z, c.v[it].w};
     uint32_t h[4], l[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) { h[i] = to_tf32(f[i]); l[i] = to_tf32(f[i] - __uint_as_float(h[i])); }
@@ -469,29 +526,8 @@ __device__ __forceinline__ void sl_transform_kmajor(const float* __restrict__ sr
   }
 }
 
-// MN-major source: element (n, k) = src[k * ld + n]; n >= ncols is never stored by the epilogue, k >= klen is zero
-__device__ __forceinline__ void sl_transform_mnmajor(const float* __restrict__ src, int64_t ld, int ncols, int klen,
-                                                     int tile_cols, char* hi, char* lo) {
-  constexpr uint32_t SBO = (SL_KC / 4) * 128;
-  const int items = tile_cols * (SL_KC / 4);
-  for (int j = threadIdx.x; j < items; j += SL_THREADS) {
-    const int n = j % tile_cols, kq = j / tile_cols;
-    uint32_t h[4], l[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int k = kq * 4 + i;
-      const float v = (n < ncols && k < klen) ? __ldg(src + (int64_t)k * ld + n) : 0.f;
-      h[i] = to_tf32(v);
-      l[i] = to_tf32(v - __uint_as_float(h[i]));
-    }
-    const uint32_t off = (uint32_t)(n >> 3) * SBO + (uint32_t)kq * 128 + (uint32_t)(n & 7) * 16;
-    *reinterpret_cast<uint4*>(hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
-    *reinterpret_cast<uint4*>(lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
-  }
-}
-
 template <int NPAD>
-__global__ void __launch_bounds__(SL_THREADS + 32)
+__global__ void __launch_bounds__(SL_THREADS + 32, 2)
 k_seg_linear_tc(const float* __restrict__ X, const float* __restrict__ W, const int64_t* __restrict__ gptr, int Kin, int M,
                 int Nmma, int w_transposed, float* __restrict__ Y, int* __restrict__ err) {
   extern __shared__ __align__(128) char sltc_smem[];
@@ -524,6 +560,20 @@ k_seg_linear_tc(const float* __restrict__ X, const float* __restrict__ W, const 
   const uint32_t tmem = tmem_base_s;
   bool ok = true;
   int ci = 0;                                                        // chunks issued so far (every role counts alike)
+  constexpr int A_ITEMS_ = TC_M * (SL_KC / 4) / SL_THREADS, B_ITEMS_ = (NPAD * (SL_KC / 4) + SL_THREADS - 1) / SL_THREADS;
+  SlMap<A_ITEMS_> map_a; SlMap<B_ITEMS_> map_b;
+  if (warp < TWARPS) {
+    sl_map_init<A_ITEMS_, true>(map_a, TC_M);
+    if (w_transposed) sl_map_init<B_ITEMS_, true>(map_b, Nmma); else sl_map_init<B_ITEMS_, false>(map_b, Nmma);
+  }
+
+  SlChunk<A_ITEMS_> ca0, ca1; SlChunk<B_ITEMS_> cb0, cb1;
+  auto load_chunk = [&](int64_t r0, int rows, int c, SlChunk<A_ITEMS_>& ca, SlChunk<B_ITEMS_>& cb) {
+    const int k0 = c * SL_KC, klen = min(SL_KC, Kin - k0);
+    sl_load_kmajor<A_ITEMS_>(ca, map_a, X + r0 * Kin + k0, Kin, rows, klen);
+    if (w_transposed) sl_load_kmajor<B_ITEMS_>(cb, map_b, Wg + k0, Kin, M, klen);
+    else sl_load_mnmajor<B_ITEMS_>(cb, map_b, Wg + (int64_t)k0 * M, M, M, klen);
+  };
 
   for (int64_t r0 = lo_r; r0 < hi_r; r0 += TC_M) {
     const int rows = (int)min((int64_t)TC_M, hi_r - r0);
@@ -551,18 +601,24 @@ k_seg_linear_tc(const float* __restrict__ X, const float* __restrict__ W, const 
         }
       }
     } else {
-      // ---------------- transform warps
-      for (int c = 0; c < nk && ok; ++c) {
+      // ---------------- transform warps: chunks c + 1 and c + 2 are in flight (registers) while chunk c's tile set is
+      // awaited and written
+      auto put_chunk = [&](int c, SlChunk<A_ITEMS_>& ca, SlChunk<B_ITEMS_>& cb) {
         const int i = ci + c, t = i & 1;
-        const int k0 = c * SL_KC, klen = min(SL_KC, Kin - k0);
         if (i >= 2) ok = mbar_wait2(smem_u32(&bar_mma[t]), (uint32_t)(((i >> 1) - 1) & 1));     // MMA(i-2) left set t
         char* set = sltc_smem + (size_t)t * MMA_SET;
-        sl_transform_kmajor(X + r0 * Kin + k0, Kin, rows, klen, TC_M, set, set + A_BYTES);
-        if (w_transposed) sl_transform_kmajor(Wg + k0, Kin, M, klen, Nmma, set + 2 * A_BYTES, set + 2 * A_BYTES + B_BYTES);
-        else sl_transform_mnmajor(Wg + (int64_t)k0 * M, M, M, klen, Nmma, set + 2 * A_BYTES, set + 2 * A_BYTES + B_BYTES);
+        sl_store<A_ITEMS_>(ca, map_a, set, set + A_BYTES);
+        sl_store<B_ITEMS_>(cb, map_b, set + 2 * A_BYTES, set + 2 * A_BYTES + B_BYTES);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes -> async proxy
         __syncwarp();
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(&bar_full[t])) : "memory");
+        if (c + 2 < nk) load_chunk(r0, rows, c + 2, ca, cb);
+      };
+      load_chunk(r0, rows, 0, ca0, cb0);
+      if (nk > 1) load_chunk(r0, rows, 1, ca1, cb1);
+      for (int c = 0; c < nk && ok; c += 2) {
+        put_chunk(c, ca0, cb0);
+        if (c + 1 < nk && ok) put_chunk(c + 1, ca1, cb1);
       }
     }
     ci += nk;
