@@ -284,6 +284,11 @@ int tsg_seg_linear(const float* X, const float* W, const int64_t* graph_ptr, int
  * aligned operands (TSG_EINVAL otherwise: call tsg_seg_linear); status_dev as for tsg_seg_contract. */
 int tsg_seg_linear_tc(const float* X, const float* W, const int64_t* graph_ptr, int64_t num_graphs, int64_t Kin, int64_t M,
                       int w_transposed, float* Y, int32_t* status_dev, void* stream);
+/* Y = X . W (W [Kin, M], or W stored [M, Kin] with w_transposed) for ONE shared weight on the same tcgen05 kernel (a CTA per
+ * 128 rows), then, if softmax != 0, Y = softmax(Y + bias) per row in place: DiffPool's assignment Linear + softmax
+ * (Code/sage+gat+diffpool/encoders.py:366-369).  Same shape limits as tsg_seg_linear_tc; bias only with softmax. */
+int tsg_linear_tc(const float* X, const float* W, const float* bias /*nullable*/, int64_t num_rows, int64_t Kin, int64_t M,
+                  int w_transposed, int softmax, float* Y, int32_t* status_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * K5a  per-graph top-k (deterministic: descending score, ties -> lower node id, NaN first)

@@ -88,6 +88,33 @@ def test_seg_linear_raw_tcgen05_and_simt(cuda, tc, transposed, kin, m):
     assert rel_err(y, ref) <= TOL, f"tensor_cores={tc} transposed={transposed}"
 
 
+@pytest.mark.parametrize("n,k,m", [(20000, 228, 100), (16385, 64, 32), (33000, 36, 128)])
+def test_assignment_linear_softmax_on_tcgen05(cuda, n, k, m):
+    """DiffPool's assignment Linear + softmax (encoders.py:366-369) at batch size: tsg_linear_tc (flat tcgen05 product +
+    in-place softmax(y + b)) and its input gradient on tcgen05, vs float64; small batches keep the fp32 SIMT kernel"""
+    from tsg import _lib, ops
+    g = torch.Generator().manual_seed(n + k)
+    x = torch.randn(n, k, generator=g); w = torch.randn(k, m, generator=g) / np.sqrt(k); b = torch.randn(m, generator=g)
+    dy = torch.randn(n, m, generator=g)
+    xo, wo, bo = (t.clone().double().requires_grad_(True) for t in (x, w, b))
+    yo = torch.softmax(xo @ wo + bo, dim=1)
+    yo.backward(dy.double())
+    xg, wg, bg = (t.to(cuda).requires_grad_(True) for t in (x, w, b))
+    prof = {}
+    _lib.profile = prof
+    try:
+        yg = ops.linear(xg, wg, bg, ops.LIN_SOFTMAX)
+        yg.backward(dy.to(cuda))
+    finally:
+        _lib.profile = None
+    assert len(prof.get("tsg_linear_tc", [])) == 2 and "tsg_linear_fwd" not in prof
+    assert rel_err(yg, yo) <= TOL and rel_err(xg.grad, xo.grad) <= TOL
+    assert rel_err(wg.grad, wo.grad) <= TOL and rel_err(bg.grad, bo.grad) <= TOL
+    # below the size threshold the SIMT epilogue kernel runs, same values within the tolerance
+    ys = ops.linear(x[:1000].to(cuda), w.to(cuda), b.to(cuda), ops.LIN_SOFTMAX)
+    assert rel_err(ys, yo[:1000]) <= TOL
+
+
 def _load_diffpool(d, cuda):
     from tsg import diffpool
     N, Fi, H, O, L = [int(v) for v in d["dims"]]

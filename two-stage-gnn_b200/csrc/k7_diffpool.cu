@@ -274,5 +274,54 @@ extern "C" int tsg_seg_linear_tc(const float* X, const float* W, const int64_t* 
   TSG_REQUIRE(G >= 0 && Kin > 0 && M > 0 && G < (int64_t)0x7fffffff && Kin < (int64_t)0x7fffffff, "seg_linear_tc: bad shape");
   if (G == 0) return TSG_OK;
   TSG_REQUIRE(X && W && graph_ptr && Y && status_dev, "seg_linear_tc: null pointer");
-  return launch_seg_linear_tc(X, W, graph_ptr, (int)G, (int)Kin, (int)M, w_transposed, Y, status_dev, (cudaStream_t)stream);
+  return launch_seg_linear_tc(X, W, graph_ptr, (int)G, 0, (int)Kin, (int)M, w_transposed, Y, status_dev, (cudaStream_t)stream);
+}
+
+// in-place softmax(Y[r, :] + bias) per row, M <= 256: a warp per row, the row in registers
+__global__ void __launch_bounds__(256)
+k_bias_softmax_rows(float* __restrict__ Y, const float* __restrict__ bias, int64_t N, int M) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < N; r += nwarps) {
+    float v[8];
+    float mx = -3.4e38f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = lane + 32 * i;
+      v[i] = c < M ? Y[r * M + c] + (bias ? bias[c] : 0.f) : -3.4e38f;
+      mx = fmaxf(mx, v[i]);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+    float se = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { v[i] = lane + 32 * i < M ? expf(v[i] - mx) : 0.f; se += v[i]; }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) se += __shfl_xor_sync(0xffffffffu, se, d);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = lane + 32 * i;
+      if (c < M) Y[r * M + c] = v[i] / se;
+    }
+  }
+}
+
+/* Y = X . W (W [Kin, M]; or W^T with W stored [M, Kin]) on tcgen05 (k_seg_linear_tc with one shared weight, a CTA per 128
+ * rows), then, with softmax != 0, Y = softmax(Y + bias) per row in place -- DiffPool's assignment Linear + softmax
+ * (encoders.py:366-369) at config-4 size is a 970 k x 228 x 100 product: 2.1 ms on the fp32 SIMT kernel. */
+extern "C" int tsg_linear_tc(const float* X, const float* W, const float* bias, int64_t N, int64_t Kin, int64_t M,
+                             int w_transposed, int softmax, float* Y, int32_t* status_dev, void* stream) {
+  TSG_REQUIRE(N >= 0 && Kin > 0 && M > 0 && Kin < (int64_t)0x7fffffff && N / 128 < (int64_t)0x7fffff00, "linear_tc: bad shape");
+  if (N == 0) return TSG_OK;
+  TSG_REQUIRE(X && W && Y && status_dev, "linear_tc: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = launch_seg_linear_tc(X, W, nullptr, 0, N, (int)Kin, (int)M, w_transposed, Y, status_dev, st);
+  if (rc) return rc;
+  if (softmax || bias) {
+    TSG_REQUIRE(softmax, "linear_tc: a bias without the softmax epilogue is not implemented");
+    const int64_t ctas = (N + 7) / 8;
+    k_bias_softmax_rows<<<(int)(ctas < (int64_t)TSG_NUM_SMS * 16 ? ctas : (int64_t)TSG_NUM_SMS * 16), 256, 0, st>>>(Y, bias, N, (int)M);
+    return check_launch("linear_tc(softmax)");
+  }
+  return TSG_OK;
 }

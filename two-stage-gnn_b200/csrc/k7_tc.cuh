@@ -528,8 +528,8 @@ __device__ __forceinline__ void sl_store(const SlChunk<ITEMS>& c, const SlMap<IT
 
 template <int NPAD>
 __global__ void __launch_bounds__(SL_THREADS + 32, 2)
-k_seg_linear_tc(const float* __restrict__ X, const float* __restrict__ W, const int64_t* __restrict__ gptr, int Kin, int M,
-                int Nmma, int w_transposed, float* __restrict__ Y, int* __restrict__ err) {
+k_seg_linear_tc(const float* __restrict__ X, const float* __restrict__ W, const int64_t* __restrict__ gptr, int64_t flat_rows,
+                int Kin, int M, int Nmma, int w_transposed, float* __restrict__ Y, int* __restrict__ err) {
   extern __shared__ __align__(128) char sltc_smem[];
   constexpr int A_BYTES = TC_M * SL_KC * 4, B_BYTES = NPAD * SL_KC * 4;
   constexpr int MMA_SET = 2 * A_BYTES + 2 * B_BYTES;                 // a_hi a_lo b_hi b_lo
@@ -538,10 +538,12 @@ k_seg_linear_tc(const float* __restrict__ X, const float* __restrict__ W, const 
   __shared__ __align__(8) uint64_t bar_mma[2];                       // MMAs that read the set are done (commit)
   __shared__ uint32_t tmem_base_s;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // gptr == nullptr: ONE shared weight, CTA b takes rows [128 b, 128 b + 128) of flat_rows (tsg_linear_tc)
   const int g = blockIdx.x;
-  const int64_t lo_r = gptr[g], hi_r = gptr[g + 1];
+  const int64_t lo_r = gptr ? gptr[g] : (int64_t)g * TC_M;
+  const int64_t hi_r = gptr ? gptr[g + 1] : min(flat_rows, lo_r + TC_M);
   const int nk = (Kin + SL_KC - 1) / SL_KC;
-  const float* Wg = W + (int64_t)g * Kin * M;
+  const float* Wg = gptr ? W + (int64_t)g * Kin * M : W;
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "r"((uint32_t)NPAD) : "memory");
@@ -663,8 +665,9 @@ k_seg_linear_tc(const float* __restrict__ X, const float* __restrict__ W, const 
   }
 }
 
-static int launch_seg_linear_tc(const float* X, const float* W, const int64_t* gptr, int G, int Kin, int M, int w_transposed,
-                                float* Y, int* err, cudaStream_t st) {
+// gptr == nullptr: flat mode over flat_rows rows with one shared W (G is ignored)
+static int launch_seg_linear_tc(const float* X, const float* W, const int64_t* gptr, int G, int64_t flat_rows, int Kin, int M,
+                                int w_transposed, float* Y, int* err, cudaStream_t st) {
   if (M > 256 || M % 4 || Kin % 4 || ((((uintptr_t)X) | ((uintptr_t)W) | ((uintptr_t)Y)) & 15)) {
     set_error("seg_linear(tcgen05): needs M <= 256, M %% 4 == 0, Kin %% 4 == 0 and 16-byte aligned operands (got Kin %d, M %d)", Kin, M);
     return TSG_EINVAL;
@@ -672,9 +675,10 @@ static int launch_seg_linear_tc(const float* X, const float* W, const int64_t* g
   int Nmma = (M + 15) / 16 * 16;
   const int npad = Nmma <= 64 ? 64 : (Nmma <= 128 ? 128 : 256);
   const size_t smem = 2 * (2 * (size_t)TC_M * SL_KC * 4 + 2 * (size_t)npad * SL_KC * 4) + 128;
+  const int grid = gptr ? G : (int)((flat_rows + TC_M - 1) / TC_M);
 #define TSG_GOSL(NP)                                                                                     \
   cudaFuncSetAttribute(k_seg_linear_tc<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
-  k_seg_linear_tc<NP><<<G, SL_THREADS + 32, smem, st>>>(X, W, gptr, Kin, M, Nmma, w_transposed, Y, err)
+  k_seg_linear_tc<NP><<<grid, SL_THREADS + 32, smem, st>>>(X, W, gptr, flat_rows, Kin, M, Nmma, w_transposed, Y, err)
   if (npad == 64) { TSG_GOSL(64); } else if (npad == 128) { TSG_GOSL(128); } else { TSG_GOSL(256); }
 #undef TSG_GOSL
   return check_launch("seg_linear(tcgen05)");

@@ -344,6 +344,24 @@ def linear_bwd_weight(x: torch.Tensor, dy: torch.Tensor, want_bias: bool):
     return dw, db
 
 
+LINEAR_TC = os.environ.get("TSG_LINEAR_NOTC", "0") != "1"
+
+
+def _linear_tc_ok(n: int, kin: int, m: int) -> bool:
+    return n >= 16384 and kin % 4 == 0 and m % 4 == 0 and 32 <= m <= 256 and kin >= 32
+
+
+def linear_tc_raw(x, w, bias, transposed: bool, softmax: bool):
+    """tsg_linear_tc: y = x @ w (w [Kin, M]; transposed: w [M, Kin] used as w^T) on tcgen05, optional softmax(y + bias)."""
+    x, w = x.contiguous(), w.contiguous()
+    m = w.size(0) if transposed else w.size(1)
+    y = torch.empty(x.size(0), m, dtype=torch.float32, device=x.device)
+    status = torch.zeros(1, dtype=torch.int32, device=x.device)
+    call("tsg_linear_tc", ptr(x), ptr(w), ptr(bias.contiguous()) if bias is not None else None, x.size(0), x.size(1), m,
+         int(transposed), int(softmax), ptr(y), ptr(status), stream_ptr())
+    return y
+
+
 class _Linear(torch.autograd.Function):
     """Y = epilogue(X W + b).  flags = 0: plain product (PyG GCNConv's `x @ weight`);
     flags = NORMALIZE|RELU|NODEBN: the dense GraphConv epilogue (encoders.py:36-40,177,134-138)."""
@@ -351,7 +369,9 @@ class _Linear(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, bias, flags: int):
         x, w = x.contiguous(), w.contiguous()
-        y = linear_raw(x, w, bias, False, flags)
+        # DiffPool's assignment Linear + softmax (encoders.py:366-369) at batch size is a tall GEMM: tcgen05 (3xTF32)
+        ctx.tc = bool(flags == LIN_SOFTMAX and USE_TCGEN05 and LINEAR_TC and _linear_tc_ok(x.size(0), x.size(1), w.size(1)))
+        y = linear_tc_raw(x, w, bias, False, True) if ctx.tc else linear_raw(x, w, bias, False, flags)
         ctx.flags = flags
         ctx.save_for_backward(x, w, bias, y if flags == LIN_SOFTMAX else None)
         return y
@@ -370,7 +390,10 @@ class _Linear(torch.autograd.Function):
             call("tsg_dense_epilogue_bwd", ptr(x), ptr(w), ptr(bias), ptr(dy), ptr(du), n, k, dy.size(1),
                  ctx.flags, stream_ptr())
             dy = du
-        dx = linear_raw(dy, w, None, True) if ctx.needs_input_grad[0] else None
+        dx = None
+        if ctx.needs_input_grad[0]:
+            tc = ctx.tc and _linear_tc_ok(dy.size(0), dy.size(1), w.size(0))
+            dx = linear_tc_raw(dy, w, None, True, False) if tc else linear_raw(dy, w, None, True)
         dw = db = None
         if ctx.needs_input_grad[1] or (bias is not None and ctx.needs_input_grad[2]):
             dw, db = linear_bwd_weight(x, dy, bias is not None)
