@@ -5,7 +5,7 @@ the packed layout.  State-dict keys match the reference (`assign_conv_first_modu
     Z  = gcn_forward(x, A)            (K2 + K3, masked rows do not exist in the packed layout)
     S  = softmax(Linear(gcn_forward_assign(x, A)))          [sum n, K],  K = int(max_nodes * ratio)
     T  = A S                          (K2 SpMM, F = K)
-    [X' | A'] = S^T [Z | T]           (K7: ONE per-graph contraction on tcgen05, 3xTF32)
+    X' = S^T Z, A' = S^T T            (K7: per-graph contractions on tcgen05, 3xTF32)
     Z' = gcn_forward(X', A')          (dense K x K weighted adjacency: K7 seg_linear + K3)
     out = [max_n Z (incl. zero padded rows) | max_K Z'] -> map_model
 """
@@ -18,6 +18,10 @@ import torch.nn.functional as F
 from . import ops
 from .dense import GcnStack, _pred_layers, _readout_max, gcn_forward
 from .ops import CSR, LIN_NODEBN, LIN_RELU, READOUT_MAX
+
+
+import os
+SPLIT_CONTRACT = os.environ.get("TSG_DIFFPOOL_ONE_CONTRACT", "0") != "1"
 
 
 def dense_gcn_forward(x, adj, graph_ptr, convs, bn=True):
@@ -75,9 +79,16 @@ class PackedSoftPoolEncoder(nn.Module):
         ap = self.assign_pred_modules[0]
         s = ops.linear(za, ap.weight.t(), ap.bias, ops.LIN_SOFTMAX)                          # :366-369: Linear + softmax in K3's epilogue
         t = ops.spmm(csr, s)                                                                 # adj @ S
-        c = ops.seg_contract(s, torch.cat([z, t], dim=1), graph_ptr)                         # :374-375
         D = z.size(1)
-        xp, apool = c[:, :, :D].contiguous(), c[:, :, D:].contiguous()
+        if SPLIT_CONTRACT:
+            # two contractions, no copies: the single S^T [Z | AS] product needs torch.cat before it, two strided slices +
+            # .contiguous() after it and their zero-fill + copy backward -- ~1.4 ms of ATen copies per step at config-4
+            # size against ~0.2 ms for splitting S into hi / lo TF32 parts twice
+            xp = ops.seg_contract(s, z, graph_ptr)                                           # :374  x = S^T Z
+            apool = ops.seg_contract(s, t, graph_ptr)                                        # :375  adj = S^T (A S)
+        else:
+            c = ops.seg_contract(s, torch.cat([z, t], dim=1), graph_ptr)                     # :374-375 in one product
+            xp, apool = c[:, :, :D].contiguous(), c[:, :, D:].contiguous()
         gptr2 = torch.arange(G + 1, device=x.device, dtype=torch.int64) * K
         convs2 = self._stack(self.conv_first_after_pool[0], self.conv_block_after_pool[0],
                              self.conv_last_after_pool[0])
