@@ -567,13 +567,16 @@ def run_config4(a, dev, kt, peaks, cpu):
     ms, loss = _timed_steps(step, a.config_steps, 3)
     K, D = 100, 96
     G = int(ids.shape[0])
-    s = torch.softmax(torch.randn(N, K, device=dev), dim=1); zt = torch.randn(N, D + K, device=dev)
-    kms = kt(lambda: ops.seg_contract_raw(s, zt, gptr, tensor_cores=True))
+    # dominant kernel of the step (profiles/r02f_launches_diffpool_step.csv): the row-local product d[Z | AS] = S dC of the
+    # contraction's backward on tcgen05 -- per graph [n_g, K] x [K, D + K]
+    s = torch.softmax(torch.randn(N, K, device=dev), dim=1); dc = torch.randn(G, K, D + K, device=dev)
+    kms = kt(lambda: ops.seg_linear_raw(s, dc, gptr, False, tensor_cores=True))
     alg = 4 * (N * K + N * (D + K) + G * K * (D + K))
     flops = 2.0 * N * K * (D + K)
-    rf = roofline_block(f"k_seg_contract_tc2 (tcgen05 3xTF32, S^T [Z | AS], K={K}, D+K={D + K}, {G} graphs)", alg, kms, peaks,
+    rf = roofline_block(f"k_seg_linear_tc (tcgen05 3xTF32, Y[r,:] = S[r,:] dC_g, K={K}, D+K={D + K}, {G} graphs)", alg, kms, peaks,
                         flops=flops, note="HBM bound by arithmetic intensity (%.1f flop/B); tflops = useful fp32 flops, the "
-                                          "tensor pipe issues 3 TF32 MMAs per product" % (flops / alg))
+                                          "tensor pipe issues 3 TF32 MMAs per product; bound in practice by the SIMT hi/lo split "
+                                          "(profiles/r02f_k7_seg_linear_tc.md)" % (flops / alg))
     out = {"workload": f"DiffPool 2stg triplet step, DD-shape, 3x{corpus.num_graphs} graphs packed, "
                        "SoftPoolingGcnEncoder(N=1000,32,32,32,2,L=3,assign_ratio=0.1): K=100, D=96",
            "value": G / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "graphs_per_step": G, "nodes_per_step": N,
