@@ -204,7 +204,7 @@ k_seg_contract_tc(const float* __restrict__ X, const float* __restrict__ Y, cons
 // Needs Kx % 4 == 0 and Ky % 4 == 0 (16-byte TMA granularity); other widths use v1.
 // ------------------------------------------------------------------------------------------
 constexpr int KC2 = 16;                   // contraction rows per chunk (2 MMA k-steps of 8)
-constexpr int RAW_STAGES = 4;
+constexpr int RAW_STAGES = 3;     // 3 raw stages keep the NPAD <= 128 kernel under 104 KB: two CTAs per SM
 constexpr int TC2_SPIN_LIMIT = 1 << 22;   // hang guard (a wait normally returns within microseconds)
 
 __device__ __forceinline__ bool mbar_wait2(uint32_t bar, uint32_t parity) {
