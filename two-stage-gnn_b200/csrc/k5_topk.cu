@@ -174,16 +174,83 @@ __device__ __forceinline__ void topk_runs_body(const float* __restrict__ score, 
   }
 }
 
+// A graph of at most 32 * KPT <= 128 keys is ONE run: a warp sorts it in registers and the rank is the position, no
+// shared memory and no CTA barrier -- the pooled levels of a DD-shape batch average 139 and 69 nodes, and a 256-thread CTA
+// per such graph left most of its warps without keys and only G / 8 graphs in flight per wave.
+template <int KPT>
+__device__ __forceinline__ void topk_warp_body(const float* __restrict__ score, int64_t base, int n, int k,
+                                               int64_t obase, int64_t* __restrict__ perm) {
+  constexpr int RL = 32 * KPT;
+  const int lane = threadIdx.x & 31;
+  unsigned long long key[KPT];
+#pragma unroll
+  for (int s = 0; s < KPT; ++s) {
+    const int i = s * 32 + lane;
+    key[s] = i < n ? (((unsigned long long)score_key(score[base + i]) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i)) : 0ull;
+  }
+#pragma unroll
+  for (int kk = 2; kk <= RL; kk <<= 1) {
+#pragma unroll
+    for (int j = kk >> 1; j > 0; j >>= 1) {
+      if (j >= 32) {
+        const int js = j >> 5;
+#pragma unroll
+        for (int s = 0; s < KPT; ++s) {
+          if ((s & js) == 0) {
+            const bool desc = ((s * 32 + lane) & kk) == 0;
+            const unsigned long long x = key[s], y = key[s | js];
+            if ((x < y) == desc) { key[s] = y; key[s | js] = x; }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int s = 0; s < KPT; ++s) {
+          const unsigned long long x = key[s];
+          const unsigned long long y = __shfl_xor_sync(0xffffffffu, x, j);
+          const bool keep_max = ((lane & j) == 0) == ((((s * 32 + lane) & kk)) == 0);
+          key[s] = keep_max ? (x > y ? x : y) : (x < y ? x : y);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < KPT; ++s) {
+    const int rank = s * 32 + lane;
+    if (key[s] != 0ull && rank < k) perm[obase + rank] = base + (int64_t)(0xFFFFFFFFu - (unsigned)(key[s] & 0xFFFFFFFFull));
+  }
+}
+
+constexpr int TOPK_WARP_KEYS = 128;
+
 __global__ void __launch_bounds__(TOPK_RUN_THREADS)
 k_topk_runs(const float* __restrict__ score, const int64_t* __restrict__ gptr, const int64_t* __restrict__ kptr,
-            int64_t* __restrict__ perm, int G) {
+            int64_t* __restrict__ perm, int G, int cta_blocks) {
   __shared__ __align__(16) unsigned long long runs[TOPK_RUN_THREADS * 4];
-  for (int g = blockIdx.x; g < G; g += gridDim.x) {
+  constexpr int NW = TOPK_RUN_THREADS / 32;
+  if ((int)blockIdx.x >= cta_blocks) {
+    // warp role: blocks behind the first cta_blocks give every warp one SMALL graph
+    const int nwarps = ((int)gridDim.x - cta_blocks) * NW;
+    for (int g = ((int)blockIdx.x - cta_blocks) * NW + (threadIdx.x >> 5); g < G; g += nwarps) {
+      const int64_t base = gptr[g];
+      const int n = (int)(gptr[g + 1] - base);
+      if (n <= 0 || n > TOPK_WARP_KEYS) continue;
+      const int64_t obase = kptr[g];
+      const int k = (int)(kptr[g + 1] - obase);
+      if (k <= 0) continue;
+      if (n <= 32) topk_warp_body<1>(score, base, n, k, obase, perm);
+      else if (n <= 64) topk_warp_body<2>(score, base, n, k, obase, perm);
+      else topk_warp_body<4>(score, base, n, k, obase, perm);
+    }
+    return;
+  }
+  // CTA role: a graph of 129 .. 1,024 keys per block iteration
+  for (int g = blockIdx.x; g < G; g += cta_blocks) {
     const int64_t base = gptr[g];
     const int n = (int)(gptr[g + 1] - base);
+    if (n <= TOPK_WARP_KEYS || n > TOPK_RUN_THREADS * 4) continue;     // CTA-uniform
     const int64_t obase = kptr[g];
     const int k = (int)(kptr[g + 1] - obase);
-    if (n > 0 && k > 0 && n <= TOPK_RUN_THREADS * 4) {
+    if (k > 0) {
       if (n <= TOPK_RUN_THREADS) topk_runs_body<1>(score, base, n, k, obase, perm, runs);
       else if (n <= 2 * TOPK_RUN_THREADS) topk_runs_body<2>(score, base, n, k, obase, perm, runs);
       else topk_runs_body<4>(score, base, n, k, obase, perm, runs);
@@ -460,8 +527,11 @@ extern "C" int tsg_topk_bounded(const float* score, const int64_t* gptr, const i
   const int max_pad = no_sort ? 0 : TOPK_SMEM_KEYS;
   const int runs_upto = (no_sort || no_runs) ? 0 : TOPK_RUN_THREADS * 4;
   if (runs_upto > 0) {
-    const int grid = (int)(G < (int64_t)TSG_NUM_SMS * 8 ? G : (int64_t)TSG_NUM_SMS * 8);
-    k_topk_runs<<<grid, TOPK_RUN_THREADS, 0, (cudaStream_t)stream>>>(score, gptr, kptr, perm, (int)G);
+    // CTA-per-graph blocks for graphs of 129 .. 1,024 keys, then warp-per-graph blocks for the smaller ones
+    const int cta_blocks = (int)(G < (int64_t)TSG_NUM_SMS * 8 ? G : (int64_t)TSG_NUM_SMS * 8);
+    const int64_t groups = (G + TOPK_RUN_THREADS / 32 - 1) / (TOPK_RUN_THREADS / 32);
+    const int warp_blocks = (int)(groups < (int64_t)TSG_NUM_SMS * 4 ? groups : (int64_t)TSG_NUM_SMS * 4);
+    k_topk_runs<<<cta_blocks + warp_blocks, TOPK_RUN_THREADS, 0, (cudaStream_t)stream>>>(score, gptr, kptr, perm, (int)G, cta_blocks);
   }
   // the caller's bound on the largest graph decides which of the three size ranges can be populated at all
   if (!no_sort && max_graph_nodes > runs_upto)
