@@ -271,15 +271,17 @@ k_gate_linear(const float4* __restrict__ x, const float* __restrict__ score, con
     *reinterpret_cast<float4*>(Tw + (sub + u * RPW) * PITCH + 4 * l) = w;
   }
   __syncthreads();                                    // Ws (whole CTA) and Tw (this warp)
+  // all GL_WU rows of the lane group against one pass over W: ncu on the two-rows-at-a-time version showed the kernel
+  // waiting on shared memory (short_scoreboard 5.7, mio_throttle 4.6 per issue), and W's float4 loads are what halves
+  if (base < K) {                                     // warp-uniform
+    const float* arow[GL_WU];
 #pragma unroll
-  for (int half = 0; half < GL_WU; half += 2) {       // two rows at a time: register budget
-    if (base + half * RPW >= K) break;                // warp-uniform: no row of this half exists
-    const float* arow[2] = {Tw + (sub + half * RPW) * PITCH, Tw + (sub + (half + 1) * RPW) * PITCH};
-    float acc[2][4];
-    gl_rows_times_w<F, 2>(Ws, arow, l, acc);
+    for (int u = 0; u < GL_WU; ++u) arow[u] = Tw + (sub + u * RPW) * PITCH;
+    float acc[GL_WU][4];
+    gl_rows_times_w<F, GL_WU>(Ws, arow, l, acc);
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int64_t i = base + sub + (half + u) * RPW;
+    for (int u = 0; u < GL_WU; ++u) {
+      const int64_t i = base + sub + u * RPW;
       if (i < K)     // "+ 0.f" = the bias-less add of k_linear_fwd_dense (turns -0 into +0 as it does)
         xw[i * F4 + l] = make_float4(acc[u][0] + 0.f, acc[u][1] + 0.f, acc[u][2] + 0.f, acc[u][3] + 0.f);
     }
